@@ -1,0 +1,304 @@
+"""htscodecs_b200 -- Python-side mirror of the C ABI in include/htscodecs_b200.h.
+
+The product is ``libhtscodecs_b200.so`` (hand-written sm_100a CUDA kernels behind the reference's
+own C entry points plus batched ones).  This module only binds it with ctypes so that tests and
+bench.py can call it the way a C caller would; no codec work happens in Python and there is no
+CPU fallback: if the library is missing, or no sm_100 GPU is usable, calls raise / return None.
+
+Function names follow the reference (htscodecs/rANS_static4x16.h:40-50, rANS_static.h:40-43).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhtscodecs_b200.so")
+
+RANS_ORDER_1, RANS_ORDER_X32, RANS_ORDER_STRIPE, RANS_ORDER_NOSZ = 0x01, 0x04, 0x08, 0x10
+RANS_ORDER_CAT, RANS_ORDER_RLE, RANS_ORDER_PACK = 0x20, 0x40, 0x80
+RANS4x16, RANS4x8 = 0, 1
+
+EXPORTS = [
+    "rans_compress_bound_4x16", "rans_compress_to_4x16", "rans_compress_4x16",
+    "rans_uncompress_to_4x16", "rans_uncompress_4x16", "rans_uncompress",
+    "hts_b200_create", "hts_b200_destroy", "hts_b200_last_error", "hts_b200_launch_count",
+    "hts_b200_stream", "hts_b200_uncompress_batch_dev", "hts_b200_uncompress_batch_host",
+    "hts_b200_compress_batch_dev", "hts_b200_compress_batch_host", "rans4x16_uncompress_batch",
+    "rans4x16_compress_batch", "hts_b200_peek_size", "hts_b200_host_alloc", "hts_b200_host_free",
+]
+
+_lib = None
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+
+
+def load_library():
+    """dlopen the in-tree library (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(htscodecs_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u64, i32, u32 = C.c_void_p, C.c_uint64, C.c_int32, C.c_uint32
+    lib.rans_compress_bound_4x16.restype = C.c_uint
+    lib.rans_compress_bound_4x16.argtypes = [C.c_uint, C.c_int]
+    lib.rans_compress_to_4x16.restype = vp
+    lib.rans_compress_to_4x16.argtypes = [vp, C.c_uint, vp, _u32p, C.c_int]
+    lib.rans_compress_4x16.restype = vp
+    lib.rans_compress_4x16.argtypes = [vp, C.c_uint, _u32p, C.c_int]
+    lib.rans_uncompress_to_4x16.restype = vp
+    lib.rans_uncompress_to_4x16.argtypes = [vp, C.c_uint, vp, _u32p]
+    lib.rans_uncompress_4x16.restype = vp
+    lib.rans_uncompress_4x16.argtypes = [vp, C.c_uint, _u32p]
+    lib.rans_uncompress.restype = vp
+    lib.rans_uncompress.argtypes = [vp, C.c_uint, _u32p]
+    lib.hts_b200_create.restype = vp
+    lib.hts_b200_create.argtypes = [C.c_int]
+    lib.hts_b200_destroy.argtypes = [vp]
+    lib.hts_b200_last_error.restype = C.c_char_p
+    lib.hts_b200_last_error.argtypes = [vp]
+    lib.hts_b200_launch_count.restype = C.c_ulonglong
+    lib.hts_b200_launch_count.argtypes = [vp]
+    lib.hts_b200_stream.restype = vp
+    lib.hts_b200_stream.argtypes = [vp]
+    batch = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.hts_b200_uncompress_batch_dev.argtypes = batch + [C.c_int]
+    lib.hts_b200_uncompress_batch_host.argtypes = batch
+    lib.hts_b200_compress_batch_dev.argtypes = batch + [C.c_int]
+    lib.hts_b200_compress_batch_host.argtypes = batch
+    lib.rans4x16_uncompress_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+    lib.rans4x16_compress_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.hts_b200_peek_size.argtypes = [vp, u32, C.c_int, _u32p]
+    lib.hts_b200_host_alloc.restype = vp
+    lib.hts_b200_host_alloc.argtypes = [C.c_size_t]
+    lib.hts_b200_host_free.argtypes = [vp]
+    _libc = C.CDLL(None)
+    _libc.free.argtypes = [vp]
+    lib._free = _libc.free
+    _lib = lib
+    return lib
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-in single-block calls (what htslib would call)
+# ------------------------------------------------------------------------------------------------
+def _inbuf(data):
+    data = bytes(data)
+    return (C.c_uint8 * max(1, len(data))).from_buffer_copy(data if data else b"\0"), len(data)
+
+
+def rans_compress_bound_4x16(size, order):
+    return load_library().rans_compress_bound_4x16(size, order)
+
+
+def rans_compress_4x16(data, order):
+    """bytes -> compressed bytes, or None on failure (the C call returns NULL)."""
+    lib = load_library()
+    buf, n = _inbuf(data)
+    osz = C.c_uint32(0)
+    p = lib.rans_compress_4x16(buf, n, C.byref(osz), order)
+    if not p:
+        return None
+    out = C.string_at(p, osz.value)
+    lib._free(p)
+    return out
+
+
+def rans_compress_to_4x16(data, order, capacity=None):
+    lib = load_library()
+    buf, n = _inbuf(data)
+    cap = lib.rans_compress_bound_4x16(n, order) if capacity is None else capacity
+    out = (C.c_uint8 * max(1, cap))()
+    osz = C.c_uint32(cap)
+    p = lib.rans_compress_to_4x16(buf, n, out, C.byref(osz), order)
+    return bytes(out[: osz.value]) if p else None
+
+
+def rans_uncompress_4x16(data):
+    lib = load_library()
+    buf, n = _inbuf(data)
+    osz = C.c_uint32(0)
+    p = lib.rans_uncompress_4x16(buf, n, C.byref(osz))
+    if not p:
+        return None
+    out = C.string_at(p, osz.value)
+    lib._free(p)
+    return out
+
+
+def rans_uncompress_to_4x16(data, out_size):
+    """Decode into a caller-sized buffer (required for X_NOSZ streams)."""
+    lib = load_library()
+    buf, n = _inbuf(data)
+    out = (C.c_uint8 * max(1, out_size))()
+    osz = C.c_uint32(out_size)
+    p = lib.rans_uncompress_to_4x16(buf, n, out, C.byref(osz))
+    return bytes(out[: osz.value]) if p else None
+
+
+def rans_uncompress(data):
+    """Legacy rANS 4x8 (CRAM 3.0) decode."""
+    lib = load_library()
+    buf, n = _inbuf(data)
+    osz = C.c_uint32(0)
+    p = lib.rans_uncompress(buf, n, C.byref(osz))
+    if not p:
+        return None
+    out = C.string_at(p, osz.value)
+    lib._free(p)
+    return out
+
+
+def peek_size(data, method=RANS4x16):
+    lib = load_library()
+    buf, n = _inbuf(data)
+    v = C.c_uint32(0)
+    return v.value if lib.hts_b200_peek_size(buf, n, method, C.byref(v)) == 0 else None
+
+
+# ------------------------------------------------------------------------------------------------
+# batched calls
+# ------------------------------------------------------------------------------------------------
+def _ptr(a):
+    """Address of a numpy array, a torch tensor (host or device), an int, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+class PinnedArray:
+    """A numpy view over cudaHostAlloc'ed memory (freed with the object)."""
+
+    def __init__(self, nbytes):
+        self.lib = load_library()
+        self.nbytes = int(nbytes)
+        self.ptr = self.lib.hts_b200_host_alloc(max(1, self.nbytes))
+        if not self.ptr:
+            raise MemoryError("cudaHostAlloc failed")
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(1, self.nbytes)).from_address(self.ptr))[: self.nbytes]
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self.lib.hts_b200_host_free(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """hts_b200_ctx: one per host thread and device."""
+
+    def __init__(self, device=-1):
+        self.lib = load_library()
+        self.h = self.lib.hts_b200_create(device)
+        if not self.h:
+            raise RuntimeError("hts_b200_create failed: no usable sm_100 CUDA device (there is no CPU fallback)")
+
+    def close(self):
+        if self.h:
+            self.lib.hts_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.hts_b200_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.hts_b200_stream(self.h)
+
+    def last_error(self):
+        return self.lib.hts_b200_last_error(self.h).decode()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("htscodecs_b200 batch call failed: " + self.last_error())
+
+    # -- device-resident (all arguments are device pointers / CUDA tensors) ----------------------
+    def uncompress_batch_dev(self, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status,
+                             method=None, sync=True):
+        self._check(self.lib.hts_b200_uncompress_batch_dev(
+            self.h, nblk, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
+            _ptr(out_len), _ptr(status), _ptr(method), 1 if sync else 0))
+
+    def compress_batch_dev(self, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, order,
+                           sync=True):
+        self._check(self.lib.hts_b200_compress_batch_dev(
+            self.h, nblk, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
+            _ptr(out_len), _ptr(status), _ptr(order), 1 if sync else 0))
+
+    # -- host-resident (numpy arrays; pinned or pageable) ------------------------------------------
+    def uncompress_batch_host(self, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status,
+                              method=None):
+        self._check(self.lib.hts_b200_uncompress_batch_host(
+            self.h, nblk, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
+            _ptr(out_len), _ptr(status), _ptr(method)))
+
+    def compress_batch_host(self, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, order):
+        self._check(self.lib.hts_b200_compress_batch_host(
+            self.h, nblk, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
+            _ptr(out_len), _ptr(status), _ptr(order)))
+
+    # -- convenience: lists of bytes in, lists of bytes out ----------------------------------------
+    def uncompress_many(self, streams, sizes=None, methods=None):
+        """Decode a list of streams.  sizes[i] = expected size (needed for X_NOSZ); returns
+        (list of bytes-or-None, status array)."""
+        n = len(streams)
+        if n == 0:
+            return [], np.zeros(0, np.int32)
+        if sizes is None:
+            sizes = [peek_size(s, methods[i] if methods is not None else RANS4x16) for i, s in enumerate(streams)]
+        caps = np.array([0 if s is None else s for s in sizes], np.uint32)
+        in_len = np.array([len(s) for s in streams], np.uint32)
+        in_off = np.zeros(n, np.uint64)
+        out_off = np.zeros(n, np.uint64)
+        if n > 1:
+            in_off[1:] = np.cumsum((in_len[:-1].astype(np.uint64) + 15) // 16 * 16)
+            out_off[1:] = np.cumsum((caps[:-1].astype(np.uint64) + 15) // 16 * 16)
+        ib = np.zeros(int(in_off[-1] + in_len[-1]) + 16, np.uint8)
+        for i, s in enumerate(streams):
+            ib[int(in_off[i]): int(in_off[i]) + len(s)] = np.frombuffer(bytes(s), np.uint8)
+        ob = np.zeros(int(out_off[-1] + caps[-1]) + 16, np.uint8)
+        out_len = caps.copy()
+        status = np.zeros(n, np.int32)
+        meth = None if methods is None else np.array(methods, np.uint8)
+        self.uncompress_batch_host(n, ib, in_off, in_len, ob, out_off, out_len, status, meth)
+        res = [bytes(ob[int(out_off[i]): int(out_off[i]) + int(out_len[i])]) if status[i] == 0 else None
+               for i in range(n)]
+        return res, status
+
+    def compress_many(self, blocks, orders):
+        n = len(blocks)
+        if n == 0:
+            return [], np.zeros(0, np.int32)
+        lib = self.lib
+        in_len = np.array([len(b) for b in blocks], np.uint32)
+        order = np.array(orders, np.int32)
+        caps = np.array([lib.rans_compress_bound_4x16(int(in_len[i]), int(order[i])) for i in range(n)], np.uint32)
+        in_off = np.zeros(n, np.uint64)
+        out_off = np.zeros(n, np.uint64)
+        if n > 1:
+            in_off[1:] = np.cumsum((in_len[:-1].astype(np.uint64) + 15) // 16 * 16)
+            out_off[1:] = np.cumsum((caps[:-1].astype(np.uint64) + 15) // 16 * 16)
+        ib = np.zeros(int(in_off[-1] + in_len[-1]) + 16, np.uint8)
+        for i, b in enumerate(blocks):
+            ib[int(in_off[i]): int(in_off[i]) + len(b)] = np.frombuffer(bytes(b), np.uint8)
+        ob = np.zeros(int(out_off[-1] + caps[-1]) + 16, np.uint8)
+        out_len = caps.copy()
+        status = np.zeros(n, np.int32)
+        self.compress_batch_host(n, ib, in_off, in_len, ob, out_off, out_len, status, order)
+        res = [bytes(ob[int(out_off[i]): int(out_off[i]) + int(out_len[i])]) if status[i] == 0 else None
+               for i in range(n)]
+        return res, status

@@ -1,0 +1,622 @@
+// api.cu -- the C ABI of libhtscodecs_b200.so (see include/htscodecs_b200.h).
+//
+// Host code does no codec work: it sizes work lists and arenas, moves bytes between host and
+// device, enqueues the kernels of decode.cu / encode.cu and gathers per-block sizes and status.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/htscodecs_b200.h"
+#include "decode.h"
+#include "encode.h"
+
+using namespace hb;
+
+#define CK(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s", __FILE__, __LINE__,           \
+                     cudaGetErrorString(e_));                                              \
+            return -1;                                                                     \
+        }                                                                                  \
+    } while (0)
+
+namespace {
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        size_t want = std::max(n, cap + cap / 2);
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T> struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        size_t want = std::max(n, cap + cap / 2);
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        if (cudaHostAlloc(&p, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Device-side lists + arena for one in-flight decode batch.
+struct DecSlot {
+    DevBuf<uint8_t> work;       // DecWork header
+    DevBuf<uint8_t> lists;      // jobs, chains, index lists, stripe ops
+    DevBuf<uint8_t> arena;
+    DevBuf<uint32_t> cap_save;  // copy of the caller's capacities, for retries
+    PinBuf<DecWork> h_work;     // header as sent / as read back
+    uint32_t job_cap = 0, chain_cap = 0, stripe_cap = 0;
+    void release() { work.release(); lists.release(); arena.release(); cap_save.release(); h_work.release(); }
+};
+
+// Staging for the host-resident API: one pipeline stage.
+struct Stage {
+    DevBuf<uint8_t> d_in, d_out;
+    DevBuf<uint64_t> d_off;     // [in_off | out_off]
+    DevBuf<uint32_t> d_u32;     // [in_len | out_len | status | order]
+    DevBuf<uint8_t> d_method;
+    PinBuf<uint64_t> h_off;
+    PinBuf<uint32_t> h_u32;
+    PinBuf<uint8_t> h_method;
+    DecSlot dec;
+    EncSlot enc;
+    cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+    void release() {
+        d_in.release(); d_out.release(); d_off.release(); d_u32.release(); d_method.release();
+        h_off.release(); h_u32.release(); h_method.release(); dec.release(); enc.release();
+        if (h2d_done) cudaEventDestroy(h2d_done);
+        if (compute_done) cudaEventDestroy(compute_done);
+        if (d2h_done) cudaEventDestroy(d2h_done);
+    }
+};
+
+constexpr int NSTAGE = 3;
+
+}  // namespace
+
+struct hts_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // compute (and the whole device-resident API)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    DecSlot dec;                        // device-resident API
+    EncSlot enc;
+    Stage stage[NSTAGE];
+    PinBuf<uint8_t> pin_in, pin_out;    // pointer-array wrappers
+    size_t arena_hint = 0;
+    unsigned long long launches = 0;
+    char err[256] = {0};
+};
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" hts_b200_ctx* hts_b200_create(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return nullptr; }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return nullptr;
+    if (device >= ndev || cudaSetDevice(device) != cudaSuccess) return nullptr;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return nullptr;
+    if (prop.major < 10) {
+        fprintf(stderr, "htscodecs_b200: device %d is sm_%d%d; this library is built for sm_100a only\n",
+                device, prop.major, prop.minor);
+        return nullptr;
+    }
+    hts_b200_ctx* ctx = new hts_b200_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess ||
+        decode_init(device) != 0 || encode_init(device) != 0) {
+        fprintf(stderr, "htscodecs_b200: initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return nullptr;
+    }
+    for (int s = 0; s < NSTAGE; s++) {
+        cudaEventCreateWithFlags(&ctx->stage[s].h2d_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->stage[s].compute_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->stage[s].d2h_done, cudaEventDisableTiming);
+    }
+    return ctx;
+}
+
+extern "C" void hts_b200_destroy(hts_b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->dec.release();
+    ctx->enc.release();
+    for (int s = 0; s < NSTAGE; s++) ctx->stage[s].release();
+    ctx->pin_in.release(); ctx->pin_out.release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    delete ctx;
+}
+
+extern "C" const char* hts_b200_last_error(const hts_b200_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+extern "C" unsigned long long hts_b200_launch_count(const hts_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* hts_b200_stream(const hts_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" void* hts_b200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void hts_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------
+// decode: device-resident
+// ------------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Lay the lists out inside slot.lists and fill the host copy of the header.
+static int dec_prepare(hts_b200_ctx* ctx, DecSlot& s, int nblk, size_t arena_bytes) {
+    uint32_t job_cap = std::max<uint32_t>(s.job_cap, 2u * nblk + 1024u);
+    uint32_t chain_cap = std::max<uint32_t>(s.chain_cap, (uint32_t)nblk + 1024u);
+    uint32_t stripe_cap = std::max<uint32_t>(s.stripe_cap, (uint32_t)nblk + 16u);
+    size_t off = 0, o_jobs[JK_NKINDS];
+    for (int k = 0; k < JK_NKINDS; k++) { o_jobs[k] = off; off += align_up(sizeof(DecJob) * job_cap, 256); }
+    size_t o_chains = off; off += align_up(sizeof(Chain) * chain_cap, 256);
+    size_t o_rle = off; off += align_up(4 * (size_t)chain_cap, 256);
+    size_t o_unp = off; off += align_up(4 * (size_t)chain_cap, 256);
+    size_t o_str = off; off += align_up(sizeof(StripeOp) * stripe_cap, 256);
+    if (s.lists.ensure(off) || s.work.ensure(sizeof(DecWork)) || s.h_work.ensure(2) ||
+        s.arena.ensure(std::max<size_t>(arena_bytes, 1 << 20)) || s.cap_save.ensure(nblk)) {
+        snprintf(ctx->err, sizeof(ctx->err), "out of device memory (lists %zu B, arena %zu B)", off, arena_bytes);
+        return -1;
+    }
+    s.job_cap = job_cap; s.chain_cap = chain_cap; s.stripe_cap = stripe_cap;
+    DecWork& h = s.h_work.p[0];
+    memset(&h, 0, sizeof(h));
+    h.job_cap = job_cap; h.chain_cap = chain_cap; h.stripe_cap = stripe_cap;
+    h.arena_cap = s.arena.cap;
+    for (int k = 0; k < JK_NKINDS; k++) h.jobs[k] = reinterpret_cast<DecJob*>(s.lists.p + o_jobs[k]);
+    h.chains = reinterpret_cast<Chain*>(s.lists.p + o_chains);
+    h.rle_list = reinterpret_cast<uint32_t*>(s.lists.p + o_rle);
+    h.unpack_list = reinterpret_cast<uint32_t*>(s.lists.p + o_unp);
+    h.stripes = reinterpret_cast<StripeOp*>(s.lists.p + o_str);
+    h.arena = s.arena.p;
+    return 0;
+}
+
+// Enqueue one decode attempt on `st` (header upload, kernels, header download into h_work[1]).
+static int dec_enqueue(hts_b200_ctx* ctx, DecSlot& s, const DecodeBatch& b, cudaStream_t st) {
+    CK(cudaMemcpyAsync(s.work.p, &s.h_work.p[0], sizeof(DecWork), cudaMemcpyHostToDevice, st));
+    DecodeBatch bb = b;
+    bb.work = reinterpret_cast<DecWork*>(s.work.p);
+    ctx->launches += decode_launch(bb, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&s.h_work.p[1], s.work.p, sizeof(DecWork), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+// After the stream drained: did the attempt run out of list or arena space?  If so grow.
+static bool dec_needs_retry(DecSlot& s, size_t* arena_bytes) {
+    const DecWork& r = s.h_work.p[1];
+    bool retry = false;
+    if (r.arena_used > r.arena_cap) { *arena_bytes = (size_t)(r.arena_used + r.arena_used / 4 + (1 << 20)); retry = true; }
+    if (r.overflow) {
+        uint32_t mj = 0;
+        for (int k = 0; k < JK_NKINDS; k++) mj = std::max(mj, r.njobs[k]);
+        s.job_cap = std::max(s.job_cap, mj + mj / 4 + 1024);
+        s.chain_cap = std::max(s.chain_cap, std::max(r.nchains, std::max(r.nrle, r.nunpack)) * 5 / 4 + 1024);
+        s.stripe_cap = std::max(s.stripe_cap, r.nstripe * 5 / 4 + 16);
+        retry = true;
+    }
+    return retry;
+}
+
+extern "C" int hts_b200_uncompress_batch_dev(hts_b200_ctx* ctx, int nblk, const uint8_t* in_base,
+                                             const uint64_t* in_off, const uint32_t* in_len, uint8_t* out_base,
+                                             const uint64_t* out_off, uint32_t* out_len, int32_t* status,
+                                             const uint8_t* method, int sync) {
+    if (!ctx || nblk < 0) return -1;
+    if (nblk == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    DecSlot& s = ctx->dec;
+    size_t arena_bytes = std::max<size_t>(ctx->arena_hint, 64u << 20);
+    DecodeBatch b;
+    b.work = nullptr; b.in_base = in_base; b.in_off = in_off; b.in_len = in_len;
+    b.out_base = out_base; b.out_off = out_off; b.out_len = out_len; b.status = status; b.method = method;
+    b.nblk = nblk; b.kinds = method ? ~0u : ~((1u << JK_R8_O0) | (1u << JK_R8_O1)); b.post = 7u;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        if (dec_prepare(ctx, s, nblk, arena_bytes)) return -1;
+        if (sync) {
+            if (attempt == 0) CK(cudaMemcpyAsync(s.cap_save.p, out_len, 4 * (size_t)nblk, cudaMemcpyDeviceToDevice, ctx->stream));
+            else CK(cudaMemcpyAsync(out_len, s.cap_save.p, 4 * (size_t)nblk, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        if (dec_enqueue(ctx, s, b, ctx->stream)) return -1;
+        if (!sync) return 0;
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!dec_needs_retry(s, &arena_bytes)) { ctx->arena_hint = std::max(ctx->arena_hint, (size_t)s.h_work.p[1].arena_used); return 0; }
+        ctx->arena_hint = arena_bytes;
+    }
+    snprintf(ctx->err, sizeof(ctx->err), "decode work area kept overflowing");
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-resident batches: chunked H2D -> kernels -> D2H pipeline over NSTAGE staging slots
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Range { uint64_t lo, hi; bool dense; };
+
+// Byte range covered by blocks [a,b) and whether they tile it without gaps or overlap.
+Range span_of(const uint64_t* off, const uint32_t* len, int a, int b) {
+    Range r{UINT64_MAX, 0, true};
+    uint64_t sum = 0;
+    for (int i = a; i < b; i++) {
+        r.lo = std::min(r.lo, off[i]);
+        r.hi = std::max(r.hi, off[i] + len[i]);
+        sum += len[i];
+    }
+    if (a >= b) { r.lo = r.hi = 0; }
+    r.dense = (r.hi - r.lo) <= sum + 64ull * (b - a);   // allow a little alignment padding between blocks
+    return r;
+}
+
+}  // namespace
+
+// One direction-agnostic driver: `enc` selects compress (order != NULL) or uncompress.
+static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* in_base, const uint64_t* in_off,
+                          const uint32_t* in_len, uint8_t* out_base, const uint64_t* out_off, uint32_t* out_len,
+                          int32_t* status, const uint8_t* method, const int32_t* order) {
+    if (!ctx || nblk < 0) return -1;
+    if (nblk == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    // ---- chunking: ~64 MiB of (in + out) per chunk keeps three stages busy without hogging HBM
+    const uint64_t target = 96ull << 20;
+    std::vector<int> cuts{0};
+    {
+        uint64_t acc = 0;
+        for (int i = 0; i < nblk; i++) {
+            uint64_t w = (uint64_t)in_len[i] + out_len[i];
+            if (acc && acc + w > target) { cuts.push_back(i); acc = 0; }
+            acc += w;
+        }
+        cuts.push_back(nblk);
+    }
+    const int nchunk = (int)cuts.size() - 1;
+    std::vector<int> redo;
+    std::vector<uint32_t> caps(out_len, out_len + nblk);           // capacities, for retries
+
+    auto launch_chunk = [&](int k, Stage& S, bool sync_mode) -> int {
+        const int a = cuts[k], b = cuts[k + 1], n = b - a;
+        Range ri = span_of(in_off, in_len, a, b);
+        Range ro = span_of(out_off, caps.data(), a, b);
+        // staging layout mirrors the host layout when dense, else blocks are packed 256-byte aligned
+        uint64_t in_bytes = 0, out_bytes = 0;
+        if (S.h_off.ensure(2 * (size_t)n) || S.h_u32.ensure(4 * (size_t)n) || S.h_method.ensure(n) ||
+            S.d_off.ensure(2 * (size_t)n) || S.d_u32.ensure(4 * (size_t)n) || S.d_method.ensure(n)) return -1;
+        uint64_t* h_in_off = S.h_off.p; uint64_t* h_out_off = S.h_off.p + n;
+        uint32_t* h_in_len = S.h_u32.p; uint32_t* h_out_len = S.h_u32.p + n;
+        uint32_t* h_order = S.h_u32.p + 3 * (size_t)n;
+        for (int i = 0; i < n; i++) {
+            h_in_len[i] = in_len[a + i];
+            h_out_len[i] = caps[a + i];
+            if (ri.dense) h_in_off[i] = in_off[a + i] - ri.lo; else { h_in_off[i] = in_bytes; in_bytes += align_up(in_len[a + i], 256); }
+            if (ro.dense) h_out_off[i] = out_off[a + i] - ro.lo; else { h_out_off[i] = out_bytes; out_bytes += align_up(caps[a + i], 256); }
+            if (method) S.h_method.p[i] = method[a + i];
+            if (order) h_order[i] = (uint32_t)order[a + i];
+        }
+        if (ri.dense) in_bytes = ri.hi - ri.lo;
+        if (ro.dense) out_bytes = ro.hi - ro.lo;
+        if (S.d_in.ensure(in_bytes + 256) || S.d_out.ensure(out_bytes + 256)) {
+            snprintf(ctx->err, sizeof(ctx->err), "out of device memory for staging");
+            return -1;
+        }
+        // ---- H2D
+        CK(cudaStreamWaitEvent(ctx->s_in, S.d2h_done, 0));           // previous user of this stage is done
+        if (ri.dense) CK(cudaMemcpyAsync(S.d_in.p, in_base + ri.lo, in_bytes, cudaMemcpyHostToDevice, ctx->s_in));
+        else for (int i = 0; i < n; i++)
+            CK(cudaMemcpyAsync(S.d_in.p + h_in_off[i], in_base + in_off[a + i], in_len[a + i], cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaMemcpyAsync(S.d_off.p, S.h_off.p, 16 * (size_t)n, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaMemcpyAsync(S.d_u32.p, S.h_u32.p, 16 * (size_t)n, cudaMemcpyHostToDevice, ctx->s_in));
+        if (method) CK(cudaMemcpyAsync(S.d_method.p, S.h_method.p, n, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(S.h2d_done, ctx->s_in));
+        // ---- kernels
+        CK(cudaStreamWaitEvent(ctx->stream, S.h2d_done, 0));
+        uint32_t* d_status = S.d_u32.p + 2 * (size_t)n;
+        if (!enc) {
+            if (dec_prepare(ctx, S.dec, n, std::max<size_t>(ctx->arena_hint, 64u << 20))) return -1;
+            DecodeBatch db;
+            db.work = nullptr; db.in_base = S.d_in.p; db.in_off = S.d_off.p; db.in_len = S.d_u32.p;
+            db.out_base = S.d_out.p; db.out_off = S.d_off.p + n; db.out_len = S.d_u32.p + n;
+            db.status = reinterpret_cast<int32_t*>(d_status); db.method = method ? S.d_method.p : nullptr; db.nblk = n;
+            // host hint: which kernels can be needed (first byte of each stream; stripes hide their sub-streams)
+            uint32_t kinds = 0, post = 0;
+            for (int i = 0; i < n; i++) {
+                if (!in_len[a + i]) continue;
+                uint8_t f = in_base[in_off[a + i]];
+                if (method && method[a + i] == 1) { kinds |= f ? (1u << JK_R8_O1) : (1u << JK_R8_O0); continue; }
+                if (f & F_STRIPE) { kinds |= ~((1u << JK_R8_O0) | (1u << JK_R8_O1)); post |= 7u; continue; }
+                bool x32 = f & F_X32;
+                if (f & F_CAT) kinds |= 1u << JK_COPY;
+                else if (f & F_ORDER1) kinds |= 1u << (x32 ? JK_O1_32 : JK_O1_4);
+                else kinds |= 1u << (x32 ? JK_O0_32 : JK_O0_4);
+                if (f & F_RLE) { post |= 1u; kinds |= 1u << (x32 ? JK_O0_32 : JK_O0_4); }
+                if (f & F_PACK) post |= 2u;
+            }
+            db.kinds = kinds; db.post = post;
+            if (dec_enqueue(ctx, S.dec, db, ctx->stream)) return -1;
+        } else {
+            EncodeBatch eb;
+            eb.in_base = S.d_in.p; eb.in_off = S.d_off.p; eb.in_len = S.d_u32.p;
+            eb.out_base = S.d_out.p; eb.out_off = S.d_off.p + n; eb.out_len = S.d_u32.p + n;
+            eb.status = reinterpret_cast<int32_t*>(d_status);
+            eb.order = reinterpret_cast<const int32_t*>(S.d_u32.p + 3 * (size_t)n);
+            eb.nblk = n;
+            int l = encode_run(S.enc, eb, h_in_len, reinterpret_cast<const int32_t*>(h_order), ctx->stream, ctx->err, sizeof(ctx->err));
+            if (l < 0) return -1;
+            ctx->launches += l;
+        }
+        CK(cudaEventRecord(S.compute_done, ctx->stream));
+        // ---- D2H
+        CK(cudaStreamWaitEvent(ctx->s_out, S.compute_done, 0));
+        CK(cudaMemcpyAsync(S.h_u32.p + n, S.d_u32.p + n, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->s_out));   // out_len + status
+        if (ro.dense) CK(cudaMemcpyAsync(out_base + ro.lo, S.d_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+        else for (int i = 0; i < n; i++)
+            CK(cudaMemcpyAsync(out_base + out_off[a + i], S.d_out.p + h_out_off[i], caps[a + i], cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaEventRecord(S.d2h_done, ctx->s_out));
+        (void)sync_mode;
+        return 0;
+    };
+    auto collect_chunk = [&](int k, Stage& S) -> int {               // after S.d2h_done
+        const int a = cuts[k], n = cuts[k + 1] - a;
+        bool retry = false;
+        if (!enc) {
+            size_t ab = 0;
+            if (dec_needs_retry(S.dec, &ab)) { ctx->arena_hint = std::max(ctx->arena_hint, ab); retry = true; }
+            else ctx->arena_hint = std::max(ctx->arena_hint, (size_t)S.dec.h_work.p[1].arena_used);
+        }
+        if (retry) { redo.push_back(k); return 0; }
+        memcpy(out_len + a, S.h_u32.p + n, 4 * (size_t)n);
+        memcpy(status + a, S.h_u32.p + 2 * (size_t)n, 4 * (size_t)n);
+        return 0;
+    };
+
+    // ---- software pipeline: chunk k uses stage k % NSTAGE; collect k - NSTAGE before reusing it
+    for (int k = 0; k < nchunk; k++) {
+        Stage& S = ctx->stage[k % NSTAGE];
+        if (k >= NSTAGE) {
+            CK(cudaEventSynchronize(S.d2h_done));
+            if (collect_chunk(k - NSTAGE, S)) return -1;
+        }
+        if (launch_chunk(k, S, false)) return -1;
+    }
+    for (int k = std::max(0, nchunk - NSTAGE); k < nchunk; k++) {
+        Stage& S = ctx->stage[k % NSTAGE];
+        CK(cudaEventSynchronize(S.d2h_done));
+        if (collect_chunk(k, S)) return -1;
+    }
+    // ---- rare: chunks whose scratch overflowed are redone one at a time with the grown arena
+    for (int attempt = 0; !redo.empty() && attempt < 3; attempt++) {
+        std::vector<int> again;
+        again.swap(redo);
+        for (int k : again) {
+            Stage& S = ctx->stage[0];
+            if (launch_chunk(k, S, true)) return -1;
+            CK(cudaEventSynchronize(S.d2h_done));
+            if (collect_chunk(k, S)) return -1;
+        }
+    }
+    if (!redo.empty()) { snprintf(ctx->err, sizeof(ctx->err), "work area kept overflowing"); return -1; }
+    return 0;
+}
+
+extern "C" int hts_b200_uncompress_batch_host(hts_b200_ctx* ctx, int nblk, const uint8_t* in_base,
+                                              const uint64_t* in_off, const uint32_t* in_len, uint8_t* out_base,
+                                              const uint64_t* out_off, uint32_t* out_len, int32_t* status,
+                                              const uint8_t* method) {
+    return run_host_batch(ctx, false, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, method, nullptr);
+}
+
+extern "C" int hts_b200_compress_batch_host(hts_b200_ctx* ctx, int nblk, const uint8_t* in_base,
+                                            const uint64_t* in_off, const uint32_t* in_len, uint8_t* out_base,
+                                            const uint64_t* out_off, uint32_t* out_len, int32_t* status,
+                                            const int32_t* order) {
+    if (!order) return -1;
+    return run_host_batch(ctx, true, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, nullptr, order);
+}
+
+extern "C" int hts_b200_compress_batch_dev(hts_b200_ctx* ctx, int nblk, const uint8_t* in_base,
+                                           const uint64_t* in_off, const uint32_t* in_len, uint8_t* out_base,
+                                           const uint64_t* out_off, uint32_t* out_len, int32_t* status,
+                                           const int32_t* order, int sync) {
+    if (!ctx || nblk < 0 || !order) return -1;
+    if (nblk == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    EncodeBatch eb;
+    eb.in_base = in_base; eb.in_off = in_off; eb.in_len = in_len; eb.out_base = out_base; eb.out_off = out_off;
+    eb.out_len = out_len; eb.status = status; eb.order = order; eb.nblk = nblk;
+    int l = encode_run(ctx->enc, eb, nullptr, nullptr, ctx->stream, ctx->err, sizeof(ctx->err));
+    if (l < 0) return -1;
+    ctx->launches += l;
+    if (sync) CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// pointer-array wrappers
+// ------------------------------------------------------------------------------------------
+static int run_ptr_batch(hts_b200_ctx* ctx, bool enc, int nblk, const unsigned char* const* in,
+                         const unsigned int* in_size, unsigned char* const* out, unsigned int* out_size,
+                         const int* order, int* status, const uint8_t* method) {
+    if (!ctx || nblk < 0) return -1;
+    if (nblk == 0) return 0;
+    std::vector<uint64_t> off(2 * (size_t)nblk);
+    uint64_t ib = 0, ob = 0;
+    for (int i = 0; i < nblk; i++) {
+        off[i] = ib; ib += align_up(in_size[i], 16);
+        off[nblk + i] = ob; ob += align_up(out_size[i], 16);
+    }
+    if (ctx->pin_in.ensure(ib + 16) || ctx->pin_out.ensure(ob + 16)) { snprintf(ctx->err, sizeof(ctx->err), "out of pinned memory"); return -1; }
+    for (int i = 0; i < nblk; i++) memcpy(ctx->pin_in.p + off[i], in[i], in_size[i]);
+    std::vector<int32_t> st(nblk), ord;
+    if (order) ord.assign(order, order + nblk);
+    int rc = run_host_batch(ctx, enc, nblk, ctx->pin_in.p, off.data(), in_size, ctx->pin_out.p, off.data() + nblk,
+                            out_size, st.data(), method, order ? ord.data() : nullptr);
+    if (rc) return rc;
+    for (int i = 0; i < nblk; i++) {
+        status[i] = st[i];
+        if (st[i] == 0) memcpy(out[i], ctx->pin_out.p + off[nblk + i], out_size[i]);
+    }
+    return 0;
+}
+
+extern "C" int rans4x16_uncompress_batch(hts_b200_ctx* ctx, int nblk, const unsigned char* const* in,
+                                         const unsigned int* in_size, unsigned char* const* out,
+                                         unsigned int* out_size, int* status) {
+    return run_ptr_batch(ctx, false, nblk, in, in_size, out, out_size, nullptr, status, nullptr);
+}
+
+extern "C" int rans4x16_compress_batch(hts_b200_ctx* ctx, int nblk, const unsigned char* const* in,
+                                       const unsigned int* in_size, unsigned char* const* out,
+                                       unsigned int* out_size, const int* order, int* status) {
+    if (!order) return -1;
+    return run_ptr_batch(ctx, true, nblk, in, in_size, out, out_size, order, status, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// drop-in single-block API
+// ------------------------------------------------------------------------------------------
+static hts_b200_ctx* tls_ctx() {
+    struct Holder { hts_b200_ctx* c = nullptr; ~Holder() { if (c) hts_b200_destroy(c); } };
+    static thread_local Holder h;
+    if (!h.c) h.c = hts_b200_create(-1);
+    return h.c;
+}
+
+static int host_var_get_u32(const uint8_t* p, const uint8_t* end, uint32_t* v) {   // varint.h:131-160
+    uint32_t x = 0;
+    int n = 0;
+    *v = 0;
+    if (p >= end) return 0;
+    for (;;) {
+        uint8_t c = p[n++];
+        x = (x << 7) | (c & 0x7f);
+        if (!(c & 0x80) || p + n >= end) break;
+    }
+    *v = x;
+    return n;
+}
+
+extern "C" int hts_b200_peek_size(const uint8_t* in, uint32_t in_len, int method, uint32_t* ulen) {
+    if (method == HTS_B200_RANS4x8) {
+        if (in_len < 9) return -1;
+        *ulen = (uint32_t)in[5] | ((uint32_t)in[6] << 8) | ((uint32_t)in[7] << 16) | ((uint32_t)in[8] << 24);
+        return 0;
+    }
+    if (in_len < 2 || ((in[0] & RANS_ORDER_NOSZ) && !(in[0] & RANS_ORDER_STRIPE))) return -1;
+    return host_var_get_u32(in + 1, in + in_len, ulen) ? 0 : -1;
+}
+
+// rans_compress_bound_4x16, reference rANS_static4x16pr.c:360-372 (double arithmetic on purpose)
+extern "C" unsigned int rans_compress_bound_4x16(unsigned int size, int order) {
+    int N = order >> 8;
+    if (!N) N = 4;
+    order &= 0xff;
+    double d = 1.05 * size;
+    d += (order == 0) ? (257 * 3 + 4) : (257 * 257 * 3 + 4 + 257 * 3 + 4);
+    d += (order & RANS_ORDER_PACK) ? 1 : 0;
+    d += (order & RANS_ORDER_RLE) ? (1 + 257 * 3 + 4) : 0;
+    d += 20;
+    d += (order & RANS_ORDER_STRIPE) ? (1 + 5 * N) : 0;
+    int sz = (int)d;
+    return (unsigned int)(sz + (sz & 1) + 2);
+}
+
+static unsigned char* uncompress_one(unsigned char* in, unsigned int in_size, unsigned char* out,
+                                     unsigned int* out_size, int method) {
+    if (!in || !out_size) return nullptr;
+    uint32_t ulen = 0;
+    bool have = hts_b200_peek_size(in, in_size, method, &ulen) == 0;
+    if (method == HTS_B200_RANS4x16) {
+        if (in_size == 0) return nullptr;                            // :1357
+        if (in[0] & RANS_ORDER_STRIPE) {
+            if (!have) return nullptr;
+            if (out && ulen != *out_size) return nullptr;            // :1379 exact size required
+        } else if (in[0] & RANS_ORDER_NOSZ) {
+            if (!out) return nullptr;                                // :1456
+            ulen = *out_size; have = true;
+        } else if (!have) return nullptr;
+        if (out && *out_size < ulen) return nullptr;                 // :1464
+    } else if (!have) return nullptr;
+    if (ulen >= 0x7fffffffu) return nullptr;
+    hts_b200_ctx* ctx = tls_ctx();
+    if (!ctx) { fprintf(stderr, "htscodecs_b200: no usable sm_100 device (there is no CPU fallback)\n"); return nullptr; }
+    unsigned char* dst = out ? out : (unsigned char*)malloc(ulen ? ulen : 1);
+    if (!dst) return nullptr;
+    const unsigned char* ins[1] = {in};
+    unsigned char* outs[1] = {dst};
+    unsigned int isz[1] = {in_size}, osz[1] = {out ? *out_size : ulen};
+    if (method == HTS_B200_RANS4x16 && (in[0] & RANS_ORDER_STRIPE)) osz[0] = ulen;
+    int st[1] = {0};
+    uint8_t m[1] = {(uint8_t)method};
+    int rc = run_ptr_batch(ctx, false, 1, ins, isz, outs, osz, nullptr, st, method ? m : nullptr);
+    if (rc != 0 || st[0] != 0) {
+        if (!out) free(dst);
+        return nullptr;
+    }
+    *out_size = osz[0];
+    return dst;
+}
+
+extern "C" unsigned char* rans_uncompress_to_4x16(unsigned char* in, unsigned int in_size, unsigned char* out,
+                                                  unsigned int* out_size) {
+    return uncompress_one(in, in_size, out, out_size, HTS_B200_RANS4x16);
+}
+extern "C" unsigned char* rans_uncompress_4x16(unsigned char* in, unsigned int in_size, unsigned int* out_size) {
+    return uncompress_one(in, in_size, nullptr, out_size, HTS_B200_RANS4x16);
+}
+extern "C" unsigned char* rans_uncompress(unsigned char* in, unsigned int in_size, unsigned int* out_size) {
+    if (in_size < 9) return nullptr;                                 // rANS_static.c:938
+    return uncompress_one(in, in_size, nullptr, out_size, HTS_B200_RANS4x8);
+}
+
+extern "C" unsigned char* rans_compress_to_4x16(unsigned char* in, unsigned int in_size, unsigned char* out,
+                                                unsigned int* out_size, int order) {
+    if (!out_size || (!in && in_size)) return nullptr;
+    unsigned int bound = rans_compress_bound_4x16(in_size, order);
+    if (out && *out_size < bound) return nullptr;                    // the reference's sub-encoders refuse too (:396)
+    hts_b200_ctx* ctx = tls_ctx();
+    if (!ctx) { fprintf(stderr, "htscodecs_b200: no usable sm_100 device (there is no CPU fallback)\n"); return nullptr; }
+    unsigned char* dst = out ? out : (unsigned char*)malloc(bound);
+    if (!dst) return nullptr;
+    static unsigned char dummy = 0;
+    const unsigned char* ins[1] = {in ? in : &dummy};
+    unsigned char* outs[1] = {dst};
+    unsigned int isz[1] = {in_size}, osz[1] = {bound};
+    int st[1] = {0}, ord[1] = {order};
+    int rc = run_ptr_batch(ctx, true, 1, ins, isz, outs, osz, ord, st, nullptr);
+    if (rc != 0 || st[0] != 0) {
+        if (!out) free(dst);
+        return nullptr;
+    }
+    *out_size = osz[0];
+    return dst;
+}
+extern "C" unsigned char* rans_compress_4x16(unsigned char* in, unsigned int in_size, unsigned int* out_size, int order) {
+    return rans_compress_to_4x16(in, in_size, nullptr, out_size, order);
+}

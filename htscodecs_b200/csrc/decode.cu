@@ -1,0 +1,1245 @@
+// decode.cu -- sm_100a kernels for batched rANS Nx16 / 4x8 decode and the inverse transforms.
+//
+// Pipeline for one batch (one stream, no host round trip in between):
+//   plan_kernel      1 thread / block: parses the container (rANS_static4x16pr.c:1352-1572),
+//                    emits jobs, chains and stripe ops, bump-allocates temporaries from the arena
+//   dec_o0_kernel    persistent, 1 warp / CTA: order-0 entropy decode  (…4x16pr.c:501-616, rANS_static.c:225-363)
+//   dec_o1_kernel    persistent, 1 warp / CTA: order-1 entropy decode  (…4x16pr.c:870-1130, rANS_static.c:676-922)
+//   copy_kernel      X_CAT bodies                                      (…4x16pr.c:1578-1584)
+//   rle_kernel       un-RLE  (rle.c:142-187)
+//   unpack_kernel    un-PACK (pack.c:211-348)
+//   unstripe_kernel  byte de-interleave (utils.h:41-73)
+//
+// Lane mapping of the entropy kernels: a *group* of NWAY lanes owns one job and lane z holds
+// rANS state z.  NWAY = 32 (X_32): one job per warp.  NWAY = 4: eight independent jobs per
+// warp.  Every step each lane decodes one symbol through shared-memory tables, then the lanes
+// whose state fell below the lower bound fetch their renormalisation words from a
+// shared-memory ring: __ballot_sync gives the set of hungry lanes and __popc of the lower lanes
+// gives each lane its word index (the format stores the words in state order,
+// rANS_word.h:356-410).  The ring is refilled by coalesced 128-bit loads issued half a ring
+// ahead.  Table set-up runs per group (group-masked warp syncs); the decode loop runs converged.
+#include "decode.h"
+
+namespace hb {
+
+// ------------------------------------------------------------------------------------------
+// arena + list helpers (device)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t* arena_alloc(DecWork* W, uint64_t bytes) {
+    bytes = (bytes + 255) & ~255ull;
+    unsigned long long at = atomicAdd(&W->arena_used, (unsigned long long)bytes);
+    if (at + bytes > W->arena_cap) return nullptr;
+    return W->arena + at;
+}
+
+__device__ __forceinline__ bool push_job(DecWork* W, uint32_t kind, const DecJob& j) {
+    uint32_t at = atomicAdd(&W->njobs[kind], 1u);
+    if (at >= W->job_cap) { W->overflow = 1; return false; }
+    W->jobs[kind][at] = j;
+    return true;
+}
+
+__device__ __forceinline__ DecJob make_job(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len,
+                                           uint32_t blk) {
+    DecJob j;
+    j.in = in; j.in_len = in_len; j.out = out; j.out_len = out_len; j.blk = blk; j.pad = 0; j.aux = nullptr;
+    return j;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan_kernel
+// ------------------------------------------------------------------------------------------
+struct PlanArgs {
+    DecWork* W;
+    const uint8_t* in_base;
+    const uint64_t* in_off;
+    const uint32_t* in_len;
+    uint8_t* out_base;
+    const uint64_t* out_off;
+    uint32_t* out_len;
+    int32_t* status;
+    const uint8_t* method;
+    int nblk;
+};
+
+// hts_unpack_meta, pack.c:165-198.  Returns bytes consumed (0 = failure).
+__device__ int unpack_meta(const uint8_t* d, uint32_t len, uint8_t* map, uint32_t* per) {
+    if (!len) return 0;
+    uint32_t ns = d[0] ? d[0] : 256;
+    if (ns <= 1) *per = 0; else if (ns <= 2) *per = 8; else if (ns <= 4) *per = 4; else if (ns <= 16) *per = 2;
+    else { *per = 1; return 1; }
+    if (len <= 1) return 0;
+    uint32_t c = 0, j = 1;
+    do { map[c++] = d[j++]; } while (c < ns && j < len);
+    return c < ns ? 0 : (int)j;
+}
+
+// One non-striped container, rANS_static4x16pr.c:1435-1629, turned into a plan.  `cap` is the
+// caller's capacity (the exact size for X_NOSZ); expect != 0xffffffff marks a stripe sub-stream
+// that must produce exactly that many bytes.  `ci` is the chain slot reserved by the caller.
+__device__ int32_t plan_chain(DecWork* W, const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap,
+                              uint32_t expect, uint32_t blk, uint32_t* out_len_slot, uint32_t ci) {
+    Chain c;
+    c.t1 = c.t2 = c.t3 = out; c.meta = nullptr;
+    c.blk = blk; c.flags = 0; c.u_meta = 0; c.t1_size = 0; c.osz = 0; c.t2_size = 0;
+    c.final_size = 0xfffffffeu; c.expect = expect; c.per = 0;
+    for (int k = 0; k < 16; k++) c.map[k] = 0;
+    W->chains[ci] = c;                                               // a failed plan leaves a harmless chain
+
+    if (in_len == 0) return ST_FORMAT;
+    const uint8_t* end = in + in_len;
+    uint32_t flags = *in++; in_len--;
+    if (flags & F_STRIPE) return ST_NESTED;
+    uint32_t osz;
+    if (!(flags & F_NOSZ)) {
+        int s = var_get_u32(in, end, &osz);
+        in += s; in_len -= s;
+    } else {
+        osz = cap;
+    }
+    if (cap < osz) return ST_SIZE;                                   // :1464
+    if (osz >= 0x7fffffffu) return ST_FORMAT;                        // :506
+    c.flags = flags & (F_RLE | F_PACK);
+    c.osz = osz;
+
+    uint8_t* tmp = nullptr;
+    if (flags & (F_PACK | F_RLE)) {                                  // :1498-1513
+        tmp = arena_alloc(W, (uint64_t)osz + 16);
+        if (!tmp) return ST_ARENA;
+    }
+    if ((flags & F_PACK) && (flags & F_RLE)) { c.t1 = out; c.t2 = tmp; c.t3 = out; }
+    else if (flags & F_PACK)                 { c.t1 = tmp; c.t2 = tmp; c.t3 = out; }
+    else if (flags & F_RLE)                  { c.t1 = tmp; c.t2 = out; c.t3 = out; }
+    uint32_t t1_size = osz;
+
+    if (flags & F_PACK) {                                            // :1527-1545
+        int m = unpack_meta(in, in_len, c.map, &c.per);
+        if (!m) return ST_FORMAT;
+        in += m; in_len -= m;
+        uint32_t psz;
+        int s = var_get_u32(in, end, &psz);
+        if ((uint32_t)s > in_len) return ST_FORMAT;
+        in += s; in_len -= s;
+        if (psz > t1_size) return ST_FORMAT;
+        t1_size = psz;
+    }
+
+    const bool x32 = (flags & F_X32) != 0;
+    if (flags & F_RLE) {                                             // :1549-1572
+        uint32_t u_meta, rle_len, c_meta;
+        uint32_t s = var_get_u32(in, end, &u_meta);
+        if (s > in_len) return ST_FORMAT;
+        s += var_get_u32(in + s, end, &rle_len);
+        if (s > in_len) return ST_FORMAT;
+        if (rle_len > t1_size) return ST_FORMAT;
+        if (u_meta & 1) {
+            c.meta = in + s;
+            uint32_t avail = (uint32_t)(end - c.meta);
+            u_meta = (u_meta / 2 > avail) ? avail : u_meta / 2;
+            c_meta = u_meta;
+        } else {
+            s += var_get_u32(in + s, end, &c_meta);
+            u_meta /= 2;
+            if (s > in_len) return ST_FORMAT;
+            // A valid encoder keeps lits+meta < .99*size (:1287), so the meta never exceeds osz.
+            if (u_meta > osz + 1024u) return ST_FORMAT;
+            uint8_t* mb = arena_alloc(W, (uint64_t)u_meta + 16);
+            if (!mb) return ST_ARENA;
+            if (!push_job(W, x32 ? JK_O0_32 : JK_O0_4, make_job(in + s, in_len - s, mb, u_meta, blk))) return ST_ARENA;
+            c.meta = mb;
+        }
+        if ((uint64_t)c_meta + s > in_len) return ST_FORMAT;
+        in += c_meta + s; in_len -= c_meta + s;
+        c.u_meta = u_meta;
+        t1_size = rle_len;
+        if (u_meta == 0) return ST_FORMAT;                           // :1600
+    }
+
+    if (in_len) {                                                    // :1577-1595
+        DecJob j = make_job(in, in_len, c.t1, t1_size, blk);
+        if (flags & F_CAT) {
+            if (t1_size > in_len || t1_size > osz) return ST_FORMAT;
+            if (!push_job(W, JK_COPY, j)) return ST_ARENA;
+        } else if (flags & F_ORDER1) {
+            if (in[0] & 1) {                                         // O0-compressed table: scratch for it
+                uint32_t usz;
+                var_get_u32(in + 1, end, &usz);
+                if (usz > 257u * 257u * 3u + 1024u) return ST_FORMAT;
+                j.aux = arena_alloc(W, (uint64_t)usz + 16);
+                if (!j.aux) return ST_ARENA;
+            }
+            if (!push_job(W, x32 ? JK_O1_32 : JK_O1_4, j)) return ST_ARENA;
+        } else {
+            if (!push_job(W, x32 ? JK_O0_32 : JK_O0_4, j)) return ST_ARENA;
+        }
+    } else {
+        t1_size = 0;
+    }
+    c.t1_size = t1_size;
+    c.t2_size = t1_size;
+    if (!(flags & (F_RLE | F_PACK))) c.final_size = t1_size;
+
+    if (flags & F_RLE) {
+        uint32_t at = atomicAdd(&W->nrle, 1u);
+        if (at >= W->chain_cap) { W->overflow = 1; return ST_ARENA; }
+        W->rle_list[at] = ci;
+    }
+    if (flags & F_PACK) {
+        uint32_t at = atomicAdd(&W->nunpack, 1u);
+        if (at >= W->chain_cap) { W->overflow = 1; return ST_ARENA; }
+        W->unpack_list[at] = ci;
+    }
+    W->chains[ci] = c;
+    if (out_len_slot && !(flags & (F_RLE | F_PACK))) *out_len_slot = t1_size;
+    return ST_OK;
+}
+
+__device__ __forceinline__ bool reserve_chains(DecWork* W, uint32_t n, uint32_t* first) {
+    uint32_t at = atomicAdd(&W->nchains, n);
+    if ((uint64_t)at + n > W->chain_cap) { W->overflow = 1; return false; }
+    *first = at;
+    return true;
+}
+
+__global__ void plan_kernel(PlanArgs A) {
+    int blk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= A.nblk) return;
+    DecWork* W = A.W;
+    const uint8_t* in = A.in_base + A.in_off[blk];
+    uint32_t in_len = A.in_len[blk];
+    uint8_t* out = A.out_base + A.out_off[blk];
+    uint32_t cap = A.out_len[blk];
+    int32_t st = ST_OK;
+
+    if (A.method && A.method[blk] == 1) {                            // rANS 4x8, rANS_static.c:934-943
+        if (in_len < 9 || in[0] > 1 || in_len < (in[0] ? 27u : 26u)) st = ST_FORMAT;   // :241 / :708
+        else {
+            uint32_t clen = ld_u32_le(in + 1), n = ld_u32_le(in + 5);
+            if (clen != in_len - 9 || n >= 0x7fffffffu) st = ST_FORMAT;
+            else if (n > cap) st = ST_SIZE;
+            else {
+                if (!push_job(W, in[0] ? JK_R8_O1 : JK_R8_O0, make_job(in, in_len, out, n, blk))) st = ST_ARENA;
+                A.out_len[blk] = n;
+            }
+        }
+    } else if (in_len == 0) {
+        st = ST_FORMAT;                                              // :1357
+    } else if (in[0] & F_STRIPE) {                                   // :1360-1433
+        const uint8_t* end = in + in_len;
+        uint32_t ulen, pos = 1;
+        pos += var_get_u32(in + pos, end, &ulen);
+        if (pos >= in_len) st = ST_FORMAT;
+        else {
+            uint32_t N = in[pos++];
+            uint64_t ctot = 0;
+            uint32_t p2 = pos;
+            if (N == 0 || ulen >= 0x7fffffffu) st = ST_FORMAT;
+            else if (ulen > cap) st = ST_SIZE;
+            for (uint32_t j = 0; st == ST_OK && j < N; j++) {
+                uint32_t cl;
+                p2 += var_get_u32(in + p2, end, &cl);
+                ctot += cl;
+                if (p2 > in_len || cl > in_len || cl < 1) st = ST_FORMAT;
+            }
+            if (st == ST_OK && (uint64_t)p2 + ctot > in_len) st = ST_FORMAT;
+            uint32_t chain0 = 0, so = 0;
+            uint8_t* parts = nullptr;
+            if (st == ST_OK) {
+                parts = arena_alloc(W, (uint64_t)ulen + 16);
+                if (!parts || !reserve_chains(W, N, &chain0)) st = ST_ARENA;
+            }
+            if (st == ST_OK) {
+                so = atomicAdd(&W->nstripe, 1u);
+                if (so >= W->stripe_cap) { W->overflow = 1; st = ST_ARENA; }
+            }
+            if (st == ST_OK) {
+                const uint32_t tot_len = (uint32_t)(p2 + ctot);
+                uint32_t at = 0, data = p2;
+                for (uint32_t j = 0; j < N; j++) {
+                    uint32_t cl;
+                    pos += var_get_u32(in + pos, end, &cl);
+                    uint32_t ul = ulen / N + ((ulen % N) > j);
+                    int32_t s2 = plan_chain(W, in + data, tot_len - data, parts + at, ul, ul, blk, nullptr, chain0 + j);
+                    if (s2 != ST_OK && st == ST_OK) st = s2;
+                    at += ul;
+                    data += cl;
+                }
+                StripeOp op;
+                op.parts = parts; op.out = out; op.blk = blk; op.ulen = ulen; op.N = N; op.chain0 = chain0;
+                W->stripes[so] = op;
+                A.out_len[blk] = ulen;
+            }
+        }
+    } else {
+        uint32_t ci;
+        if (!reserve_chains(W, 1, &ci)) st = ST_ARENA;
+        else st = plan_chain(W, in, in_len, out, cap, 0xffffffffu, blk, &A.out_len[blk], ci);
+    }
+    A.status[blk] = st;
+}
+
+// ------------------------------------------------------------------------------------------
+// entropy decode: shared pieces
+// ------------------------------------------------------------------------------------------
+template <int NWAY> struct GroupCfg {
+    static constexpr int G = 32 / NWAY;                 // jobs per warp
+    static constexpr int U = (NWAY == 32) ? 1 : 2;      // 16-byte chunks per lane per half ring
+    static constexpr int HALF = NWAY * 16 * U;          // bytes
+    static constexpr int RING = 2 * HALF;
+    static constexpr uint32_t GM = (NWAY == 32) ? 0xffffffffu : ((1u << NWAY) - 1u);
+};
+
+// Lane coordinates + group-scoped warp primitives.
+template <int NWAY> struct Grp {
+    uint32_t g, glane, gshift, gmask;
+    __device__ __forceinline__ Grp() {
+        uint32_t lane = lane_id();
+        g = lane / NWAY; glane = lane % NWAY; gshift = g * NWAY;
+        gmask = GroupCfg<NWAY>::GM << gshift;
+    }
+    __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
+    template <typename T> __device__ __forceinline__ T bcast(T v) const { return __shfl_sync(gmask, v, 0, NWAY); }
+    __device__ __forceinline__ const uint8_t* bcast_ptr(const uint8_t* p) const {
+        return reinterpret_cast<const uint8_t*>(__shfl_sync(gmask, (unsigned long long)(uintptr_t)p, 0, NWAY));
+    }
+    __device__ __forceinline__ bool all(bool p) const { return __all_sync(gmask, p) != 0; }
+    // exclusive prefix sum over the group; *total = group sum
+    __device__ __forceinline__ uint32_t exscan(uint32_t v, uint32_t* total) const {
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < NWAY; d <<= 1) {
+            uint32_t y = __shfl_up_sync(gmask, x, d, NWAY);
+            if (glane >= (uint32_t)d) x += y;
+        }
+        *total = __shfl_sync(gmask, x, NWAY - 1, NWAY);
+        return x - v;
+    }
+};
+
+// Streaming view of the compressed words of one job.  The ring holds the bytes
+// [filled - RING, filled) counted from `abase` (the 16-byte aligned address at or below the first
+// word); `pre` holds the next half ring, already on its way from global memory.
+template <int NWAY> struct WordRing {
+    using C = GroupCfg<NWAY>;
+    const uint8_t* abase;
+    const uint8_t* in_end;
+    uint32_t ring;          // shared-memory address of this group's ring
+    uint32_t head;          // byte offset (from abase) of the next unread byte
+    uint32_t filled;
+    uint4 pre[C::U];
+
+    __device__ __forceinline__ uint4 fetch(uint32_t byte_off) const {
+        const uint8_t* gp = abase + byte_off;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (gp < in_end) v = __ldcs(reinterpret_cast<const uint4*>(gp));
+        return v;
+    }
+    // called by the lanes of one group (group-uniform `active`)
+    __device__ __forceinline__ void init(const uint8_t* first, const uint8_t* end, uint32_t ring_addr,
+                                         const Grp<NWAY>& G, bool active) {
+        abase = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(first) & ~uintptr_t(15));
+        in_end = end;
+        ring = ring_addr;
+        head = active ? (uint32_t)(first - abase) : 0u;
+        filled = C::RING;
+#pragma unroll
+        for (int u = 0; u < C::U; u++) pre[u] = make_uint4(0, 0, 0, 0);
+        if (active) {
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int u = 0; u < C::U; u++) {
+                    uint32_t off = h * C::HALF + (u * NWAY + G.glane) * 16;
+                    sts_v4(ring + off, fetch(off));
+                }
+#pragma unroll
+            for (int u = 0; u < C::U; u++) pre[u] = fetch(filled + (u * NWAY + G.glane) * 16);
+        }
+        G.sync();
+    }
+    // End of every step, called converged by the whole warp.  Groups whose head moved past the
+    // older half overwrite it with `pre` and start fetching the half after that.
+    __device__ __forceinline__ void advance(uint32_t glane, bool active) {
+        bool need = active && head >= filled - C::HALF;
+        if (__any_sync(0xffffffffu, need)) {
+            if (need) {
+#pragma unroll
+                for (int u = 0; u < C::U; u++)
+                    sts_v4(ring + ((filled + (u * NWAY + glane) * 16) & (C::RING - 1)), pre[u]);
+                filled += C::HALF;
+#pragma unroll
+                for (int u = 0; u < C::U; u++) pre[u] = fetch(filled + (u * NWAY + glane) * 16);
+            }
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ uint32_t byte_at(uint32_t off) const { return lds_u8(ring + (off & (C::RING - 1))); }
+    template <bool ALIGNED> __device__ __forceinline__ uint32_t word_at(uint32_t off) const {
+        if (ALIGNED) return lds_u16(ring + (off & (C::RING - 1)));
+        return byte_at(off) | (byte_at(off + 1) << 8);
+    }
+};
+
+// The renormalisation step shared by the order-0 and order-1 loops (whole warp, converged).
+// BYTE: rANS_byte.h:435-551, up to two single bytes, L = 2^23.  Else rANS_word.h:356-410, at
+// most one little-endian u16, L = 2^15.
+template <int NWAY, bool BYTE, bool ALIGNED>
+__device__ __forceinline__ uint32_t renorm_step(uint32_t R, bool act, WordRing<NWAY>& ring, uint32_t lt, uint32_t gshift) {
+    constexpr uint32_t GM = GroupCfg<NWAY>::GM;
+    if (BYTE) {
+        bool p1 = act && R < (1u << 23), p2 = act && R < (1u << 15);
+        uint32_t m1 = (__ballot_sync(0xffffffffu, p1) >> gshift) & GM;
+        uint32_t m2 = (__ballot_sync(0xffffffffu, p2) >> gshift) & GM;
+        uint32_t off = ring.head + __popc(m1 & lt) + __popc(m2 & lt);
+        if (p1) {
+            R = (R << 8) | ring.byte_at(off);
+            if (p2) R = (R << 8) | ring.byte_at(off + 1);
+        }
+        ring.head += __popc(m1) + __popc(m2);
+    } else {
+        bool p = act && R < (1u << 15);
+        uint32_t m = (__ballot_sync(0xffffffffu, p) >> gshift) & GM;
+        if (p) R = (R << 16) | ring.template word_at<ALIGNED>(ring.head + 2 * __popc(m & lt));
+        ring.head += 2 * __popc(m);
+    }
+    return R;
+}
+
+// Copy `nchunks` 16-byte chunks starting at the aligned address `gp` into shared memory at `dst`
+// (chunks at or beyond `end` become zeros).  Called by the NWAY lanes of a group.
+template <int NWAY>
+__device__ __forceinline__ void stage_chunks(uint32_t dst, const uint8_t* gp, const uint8_t* end, int nchunks,
+                                             uint32_t glane) {
+    for (int c = glane; c < nchunks; c += NWAY) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (gp + 16 * c < end) v = __ldg(reinterpret_cast<const uint4*>(gp + 16 * c));
+        sts_v4(dst + 16 * c, v);
+    }
+}
+
+// bounded reader over shared-memory bytes
+struct SRd {
+    uint32_t a, end;
+    __device__ __forceinline__ bool more() const { return a < end; }
+    __device__ __forceinline__ uint32_t peek() const { return a < end ? lds_u8(a) : 0u; }
+    __device__ __forceinline__ uint32_t get() { uint32_t v = peek(); a++; return v; }
+    __device__ __forceinline__ uint32_t varint() {           // varint.h:131-160
+        uint32_t x = 0;
+        if (a >= end) return 0;
+        for (;;) {
+            uint32_t c = get();
+            x = (x << 7) | (c & 0x7f);
+            if (!(c & 0x80) || a >= end) break;
+        }
+        return x;
+    }
+};
+
+// bounded reader over global-memory bytes
+struct GRd {
+    const uint8_t* p; const uint8_t* end;
+    __device__ __forceinline__ bool more() const { return p < end; }
+    __device__ __forceinline__ uint32_t peek() const { return p < end ? *p : 0u; }
+    __device__ __forceinline__ uint32_t get() { uint32_t v = peek(); p++; return v; }
+    __device__ __forceinline__ uint32_t varint() {
+        uint32_t x = 0;
+        if (p >= end) return 0;
+        for (;;) {
+            uint32_t c = get();
+            x = (x << 7) | (c & 0x7f);
+            if (!(c & 0x80) || p >= end) break;
+        }
+        return x;
+    }
+};
+
+// decode_alphabet (rANS_static4x16pr.c:208-255): marks present symbols by storing `mark` into
+// the byte table at shared address `tab`.  Returns false when the bytes run out.
+template <typename RD>
+__device__ bool read_alphabet(RD& r, uint32_t tab, uint32_t mark) {
+    if (!r.more()) return false;
+    uint32_t run = 0, j = r.get();
+    do {
+        sts_u8(tab + j, mark);
+        if (!r.more()) return false;
+        if (!run && j + 1 == r.peek()) {
+            r.get();
+            if (!r.more()) return false;
+            j++;
+            run = r.get();
+        } else if (run) {
+            run--;
+            if (++j > 255) return false;
+        } else {
+            j = r.get();
+        }
+    } while (j && r.more());
+    return true;
+}
+
+// decode_freq, rANS_static4x16pr.c:271-289, read from shared memory by ONE lane.  F is a zeroed
+// 256-entry u32 array in shared memory, `pres` a zeroed 256-byte table.  Returns the table length
+// in bytes (0 = malformed) and the frequency sum.
+__device__ uint32_t parse_o0_table_4x16(uint32_t src, uint32_t lim, uint32_t F, uint32_t pres, uint32_t* sum) {
+    SRd r{src, src + lim};
+    if (!read_alphabet(r, pres, 1u)) return 0;
+    uint32_t tot = 0;
+    for (uint32_t s = 0; s < 256; s++) {
+        if (!lds_u8(pres + s)) continue;
+        uint32_t f = r.varint();
+        sts_u32(F + 4 * s, f);
+        tot += f;
+    }
+    *sum = tot;
+    return r.a - src;
+}
+
+// One 4x8 "sym [run] freq ... 0" table (rANS_static.c:271-303; zero_is_4096 for the order-1
+// inner tables, :775-776).  Returns false when malformed; *sum = frequency total.
+template <typename RD>
+__device__ bool parse_table_4x8(RD& r, uint32_t F, uint32_t* sum, bool zero_is_4096) {
+    uint32_t run = 0, x = 0, j = r.get();
+    do {
+        uint32_t f = r.get();
+        if (f >= 128) f = ((f & 127) << 8) | r.get();
+        if (!f && zero_is_4096) f = 4096;
+        if (x + f > 4096) return false;
+        sts_u32(F + 4 * j, f);
+        x += f;
+        if (!run && j + 1 == r.peek()) { r.get(); j++; run = r.get(); }
+        else if (run) { run--; if (++j > 255) return false; }
+        else j = r.get();
+        if (!r.more()) return false;
+    } while (j);
+    *sum = x;
+    return true;
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// order-0
+// ------------------------------------------------------------------------------------------
+// Shared memory of dec_o0_kernel: G symbol LUTs (4096 B each; during set-up a LUT doubles as
+// header staging [0,1040), presence bytes [1280,1536) and frequency scratch [2048,3072)),
+// then G fc tables (256 x {F, -C}), then G word rings.
+template <int NWAY> struct O0Smem {
+    static constexpr int G = GroupCfg<NWAY>::G;
+    static constexpr int LUT = 0, FC = G * 4096, RINGO = G * 6144;
+    static constexpr int TOTAL = G * (6144 + GroupCfg<NWAY>::RING);
+};
+constexpr int HDR_STAGE = 1040;     // bytes of stream head staged for the table parser
+
+// Turn 256 frequencies (shared u32 array F) into the decode tables of one group:
+//   fc[s]  = { F[s], -C[s] }       so that   x' = F*(x>>12) + (m - C)
+//   lut[m] = s                     for C[s] <= m < C[s]+F[s]
+// Group-synchronous.  Returns false unless the frequencies sum to `want` (or `want_alt`).
+template <int NWAY>
+__device__ bool build_o0_tables(const Grp<NWAY>& G, uint32_t F, uint32_t fc, uint32_t lut, uint32_t want,
+                                uint32_t want_alt) {
+    constexpr int K = 256 / NWAY;
+    uint32_t mine = 0;
+    bool bad = false;
+    for (int k = 0; k < K; k++) {
+        uint32_t f = lds_u32(F + 4 * (G.glane * K + k));
+        if (f > 4096) bad = true;                                    // :540
+        mine += f;
+    }
+    uint32_t total;
+    uint32_t c = G.exscan(bad ? 8192u : mine, &total);
+    if (total != want && total != want_alt) return false;            // :551 (group-uniform)
+    for (int k = 0; k < K; k++) {
+        uint32_t s = G.glane * K + k;
+        uint32_t f = lds_u32(F + 4 * s);
+        sts_v2(fc + 8 * s, make_uint2(f, 0u - c));
+        c += f;
+    }
+    G.sync();
+    for (uint32_t s = 0; s < 256; s++) {                             // :538-549, the group fills one symbol at a time
+        uint2 e = lds_v2(fc + 8 * s);
+        uint32_t f = e.x, cs = 0u - e.y;
+        for (uint32_t k = G.glane; k < f; k += NWAY) sts_u8(lut + cs + k, s);
+    }
+    G.sync();
+    return true;
+}
+
+// Per-group set-up: stage the stream head, parse the table, load the states, build the tables.
+// Returns group-uniform success; *R = this lane's state, *first = offset of the first word.
+template <int NWAY, bool BYTE>
+__device__ bool o0_setup(const Grp<NWAY>& G, const DecJob& job, uint32_t lut, uint32_t fc, uint32_t* R,
+                         uint32_t* first_word) {
+    const uint8_t* in_end = job.in + job.in_len;
+    const uint8_t* a0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(job.in) & ~uintptr_t(15));
+    const uint32_t skew = (uint32_t)(job.in - a0);
+    const uint32_t pres = lut + 1280, Ftmp = lut + 2048;
+    stage_chunks<NWAY>(lut, a0, in_end, HDR_STAGE / 16, G.glane);
+    for (uint32_t k = G.glane; k < 256; k += NWAY) { sts_u32(Ftmp + 4 * k, 0u); sts_u8(pres + k, 0u); }
+    G.sync();
+    const uint32_t hdr0 = BYTE ? 9u : 0u;                // 4x8: [order][clen][ulen] precede the table
+    uint32_t tab = 0, sum = 0;
+    if (G.glane == 0 && job.in_len >= hdr0 + 4 * NWAY) {                         // :503
+        uint32_t lim = min(job.in_len, (uint32_t)HDR_STAGE - 16u);
+        if (BYTE) {
+            SRd r{lut + skew + hdr0, lut + skew + lim};
+            if (parse_table_4x8(r, Ftmp, &sum, false)) tab = r.a - (lut + skew + hdr0);
+        } else {
+            tab = parse_o0_table_4x16(lut + skew, lim, Ftmp, pres, &sum);
+        }
+    }
+    tab = G.bcast(tab);
+    sum = G.bcast(sum);
+    const uint32_t first = hdr0 + tab;                   // offset of the NWAY initial states
+    if (tab == 0 || first + 4 * NWAY > job.in_len || first + 4 * NWAY > HDR_STAGE - 16) return false;
+    // normalise_freq_shift (…4x16pr.c:168-179): stored sums are powers of two <= 4096
+    if (!BYTE && sum != 0 && sum < 4096) {
+        uint32_t sh = 0;
+        while ((sum << sh) < 4096) sh++;
+        for (uint32_t k = G.glane; k < 256; k += NWAY) sts_u32(Ftmp + 4 * k, lds_u32(Ftmp + 4 * k) << sh);
+    }
+    uint32_t p = lut + skew + first + 4 * G.glane;
+    uint32_t r0 = lds_u8(p) | (lds_u8(p + 1) << 8) | (lds_u8(p + 2) << 16) | (lds_u8(p + 3) << 24);
+    G.sync();
+    if (!G.all(r0 >= (BYTE ? (1u << 23) : (1u << 15)))) return false;            // :557-561
+    *R = r0;
+    *first_word = first + 4 * NWAY;
+    return build_o0_tables<NWAY>(G, Ftmp, fc, lut, 4096u, BYTE ? 4095u : 4096u); // 4x8 tables may sum to 4095 (:305)
+}
+
+template <int NWAY, bool BYTE, bool ALIGNED>
+__device__ __forceinline__ void o0_loop(uint32_t R, WordRing<NWAY>& ring, uint32_t lut, uint32_t fc, uint8_t* out,
+                                        uint32_t iters, uint32_t rem, uint32_t maxit, const Grp<NWAY>& G) {
+    const uint32_t lt = (NWAY == 32) ? lanemask_lt() : ((1u << G.glane) - 1u);
+    uint8_t* op = out + G.glane;
+    for (uint32_t i = 0; i < maxit; i++) {
+        const bool act = (NWAY == 32) ? true : (i < iters);
+        uint32_t m = R & 0xfffu;
+        uint32_t s = lds_u8(lut + m);
+        uint2 e = lds_v2(fc + s * 8);
+        uint32_t Rn = e.x * (R >> 12) + (m + e.y);
+        if (act) { R = Rn; *op = (uint8_t)s; op += NWAY; }
+        R = renorm_step<NWAY, BYTE, ALIGNED>(R, act, ring, lt, G.gshift);
+        ring.advance(G.glane, act);
+    }
+    // the last n % NWAY symbols: peek only (rANS_static.c:346-355; for Nx16 nothing follows them)
+    if (G.glane < rem) *op = (uint8_t)lds_u8(lut + (R & 0xfffu));
+}
+
+template <int NWAY, bool BYTE>
+__global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status, uint32_t kind) {
+    using C = GroupCfg<NWAY>;
+    using S = O0Smem<NWAY>;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const Grp<NWAY> G;
+    const uint32_t base = smem_addr(smem_raw);
+    const uint32_t lut = base + S::LUT + G.g * 4096, fc = base + S::FC + G.g * 2048;
+    const uint32_t ringa = base + S::RINGO + G.g * C::RING;
+    const uint32_t njobs = W->njobs[kind];
+    const DecJob* jobs = W->jobs[kind];
+
+    for (;;) {
+        uint32_t j0 = 0;
+        if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], (uint32_t)C::G);
+        j0 = __shfl_sync(0xffffffffu, j0, 0);
+        if (j0 >= njobs) break;
+        const uint32_t ji = j0 + G.g;
+        const bool active = ji < njobs;
+        DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
+        uint32_t R = 0, first_word = 0;
+        bool ok = false;
+        WordRing<NWAY> ring;
+        if (active) {
+            job = jobs[ji];
+            ok = o0_setup<NWAY, BYTE>(G, job, lut, fc, &R, &first_word);
+            if (!ok && G.glane == 0) set_status(status, job.blk, ST_FORMAT);
+        }
+        ring.init(job.in + first_word, job.in + job.in_len, ringa, G, ok);
+        __syncwarp();
+        const uint32_t iters = ok ? job.out_len / NWAY : 0, rem = ok ? job.out_len % NWAY : 0;
+        const uint32_t maxit = (NWAY == 32) ? iters : __reduce_max_sync(0xffffffffu, iters);
+        const bool aligned = (NWAY == 32) && !BYTE && ((ring.head & 1u) == 0);
+        if (aligned) o0_loop<NWAY, BYTE, true >(R, ring, lut, fc, job.out, iters, rem, maxit, G);
+        else         o0_loop<NWAY, BYTE, false>(R, ring, lut, fc, job.out, iters, rem, maxit, G);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// order-1
+// ------------------------------------------------------------------------------------------
+// Tables are compacted over the alphabet: rank r = index of a symbol among the present ones.
+//   rows[r_ctx][m]        -> rank of the decoded symbol          (ns rows of 1<<shift bytes)
+//   fc[r_ctx * ns + r]    -> F << 16 | C
+// They live in shared memory when they fit (8 symbols at shift 10 need 8.3 KB), else in the arena
+// (global memory, L1/L2 cached).  Shared memory of one group: [0,256) rank -> symbol,
+// [256,512) symbol -> rank, [512,1536) frequency scratch, the word ring, then TAB table bytes.
+template <int NWAY> struct O1Smem {
+    static constexpr int UNRANK = 0, RANK = 256, FTMP = 512, RINGO = 1536;
+    static constexpr int TABO = 1536 + GroupCfg<NWAY>::RING;
+    static constexpr int TAB = (NWAY == 32) ? 16896 : 6144;          // >= 6144: the nested O0 decoder's scratch
+    static constexpr int STRIDE = TABO + TAB;                        // multiple of 16
+    static constexpr int TOTAL = STRIDE * GroupCfg<NWAY>::G;
+};
+
+// Scalar rANS 4x16 order-0 decode of a short stream (the compressed order-1 table,
+// …4x16pr.c:944-955) by ONE lane.  `scr` = 6144 bytes of shared scratch.
+__device__ bool nested_o0_decode(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t n, uint32_t scr) {
+    if (in_len < 16) return false;                                   // :503
+    const uint32_t F = scr, lut = scr + 1024, fq = scr + 5120;       // F: 256 x u32 (+ presence in the lut area)
+    for (uint32_t k = 0; k < 256; k++) { sts_u32(F + 4 * k, 0u); sts_u8(lut + k, 0u); }
+    GRd r{in, in + in_len - 8};                                      // :516
+    if (!read_alphabet(r, lut, 1u)) return false;
+    uint32_t tot = 0;
+    for (uint32_t s = 0; s < 256; s++) {
+        if (!lds_u8(lut + s)) continue;
+        uint32_t f = r.varint();
+        sts_u32(F + 4 * s, f);
+        tot += f;
+    }
+    uint32_t sh = 0;
+    if (tot != 0 && tot < 4096) while ((tot << sh) < 4096) sh++;
+    uint32_t x = 0;
+    for (uint32_t s = 0; s < 256; s++) {
+        uint32_t f = lds_u32(F + 4 * s) << sh;
+        if (!f) continue;
+        if (f > 4096 - x) return false;
+        sts_u32(fq + 4 * s, (f << 16) | x);
+        for (uint32_t y = 0; y < f; y++) sts_u8(lut + x + y, s);
+        x += f;
+    }
+    if (x != 4096) return false;
+    const uint8_t* p = r.p;
+    const uint8_t* lim = in + in_len;
+    if (p + 16 > lim) return false;
+    uint32_t R[4];
+    for (int z = 0; z < 4; z++) { R[z] = ld_u32_le(p); p += 4; if (R[z] < (1u << 15)) return false; }
+    for (uint32_t i = 0; i < n; i += 4) {
+#pragma unroll
+        for (int z = 0; z < 4; z++) {
+            if (i + z < n) {
+                uint32_t m = R[z] & 0xfff, s = lds_u8(lut + m), e = lds_u32(fq + 4 * s);
+                out[i + z] = (uint8_t)s;
+                R[z] = (e >> 16) * (R[z] >> 12) + m - (e & 0xffff);
+                if (R[z] < (1u << 15) && p + 1 < lim) { R[z] = (R[z] << 16) | p[0] | (p[1] << 8); p += 2; }
+            }
+        }
+    }
+    return true;
+}
+
+struct O1Tables {
+    uint8_t* rows;          // generic pointer: shared or global
+    uint32_t* fc;
+    uint32_t ns, shift;
+};
+
+// Group-cooperative: frequencies of one context (shared u32 array F, indexed by rank, `nsr`
+// entries used, all 256 zero-initialised) -> fc row + symbol row.  Returns false if they do not
+// sum to M after the power-of-two shift (…4x16pr.c:982-997); sums of M-1 are accepted for 4x8.
+template <int NWAY>
+__device__ bool build_o1_row(const Grp<NWAY>& G, uint32_t F, const O1Tables& T, uint32_t ctx, uint32_t Tsum,
+                             bool allow_4095) {
+    constexpr int K = 256 / NWAY;
+    const uint32_t M = 1u << T.shift;
+    uint32_t sh = 0;
+    if (Tsum < M) while ((Tsum << sh) < M) sh++;
+    uint32_t mine = 0;
+    bool bad = false;
+    for (int k = 0; k < K; k++) {
+        uint32_t f = lds_u32(F + 4 * (G.glane * K + k)) << sh;
+        if (f > M) bad = true;
+        mine += f;
+    }
+    uint32_t total;
+    uint32_t c = G.exscan(bad ? 2 * M : mine, &total);
+    if (total != M && !(allow_4095 && total == M - 1)) return false;
+    for (int k = 0; k < K; k++) {
+        uint32_t sj = G.glane * K + k;
+        uint32_t f = lds_u32(F + 4 * sj) << sh;
+        if (sj < T.ns) T.fc[ctx * T.ns + sj] = (f << 16) | c;
+        sts_u32(F + 4 * sj, (f << 16) | c);
+        c += f;
+    }
+    G.sync();
+    for (uint32_t sj = 0; sj < T.ns; sj++) {
+        uint32_t e = lds_u32(F + 4 * sj);
+        uint32_t f = e >> 16, cs = e & 0xffffu;
+        for (uint32_t k = G.glane; k < f; k += NWAY) T.rows[(size_t)ctx * M + cs + k] = (uint8_t)sj;
+    }
+    if (total == M - 1 && G.glane == 0) T.rows[(size_t)ctx * M + M - 1] = T.rows[(size_t)ctx * M + M - 2];   // rANS_static.c:799
+    G.sync();
+    return true;
+}
+
+// Per-group order-1 set-up.  Returns 0 ok, ST_FORMAT or ST_ARENA (group-uniform).
+template <int NWAY, bool BYTE>
+__device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, uint8_t* gsm, O1Tables* Tout,
+                            uint32_t* R, const uint8_t** first_word, uint32_t* ctx0) {
+    using S = O1Smem<NWAY>;
+    const uint32_t base = smem_addr(gsm);
+    const uint32_t unrank = base + S::UNRANK, rank = base + S::RANK, Ftmp = base + S::FTMP, tabs = base + S::TABO;
+    const uint8_t* in_end = job.in + job.in_len;
+
+    // ---- phase 1 (one lane): locate the table bytes, read the alphabet
+    for (uint32_t k = G.glane; k < 256; k += NWAY) { sts_u8(rank + k, BYTE ? k : 0xffu); sts_u8(unrank + k, BYTE ? k : 0u); }
+    G.sync();
+    uint32_t err = 0, shift = 12, ns = BYTE ? 256u : 0u;
+    GRd rd{nullptr, nullptr};
+    const uint8_t* body = nullptr;
+    if (G.glane == 0) {
+        if (BYTE) {                                          // rANS_static.c:676-: tables follow the 9-byte header
+            if (job.in_len < 27) err = 1;
+            rd.p = job.in + 9; rd.end = in_end;
+        } else if (job.in_len < 4 * NWAY) {                  // :872
+            err = 1;
+        } else {
+            uint32_t h = job.in[0];
+            shift = h >> 4;
+            if (shift != 10 && shift != 12) err = 1;         // the reference has loops for 12 and 10 only
+            if (h & 1) {                                     // :944-955
+                uint32_t usz, csz;
+                const uint8_t* p = job.in + 1;
+                p += var_get_u32(p, in_end, &usz);
+                p += var_get_u32(p, in_end, &csz);
+                if ((int64_t)csz >= (int64_t)(in_end - p) - 16 || !job.aux) err = 1;      // :948 (quirk kept)
+                else if (!nested_o0_decode(p, csz, job.aux, usz, tabs)) err = 1;
+                rd.p = job.aux; rd.end = job.aux + usz;
+                body = p + csz;
+            } else {
+                rd.p = job.in + 1; rd.end = in_end;
+            }
+            if (!err) {
+                if (!read_alphabet(rd, rank, 0u) || !rd.more()) err = 1;         // :959-965
+                for (uint32_t s = 0; s < 256 && !err; s++)
+                    if (lds_u8(rank + s) == 0) { sts_u8(unrank + ns, s); sts_u8(rank + s, 0xfeu); ns++; }
+                // second pass: 0xfe marks -> ranks (a rank can legitimately be 0xfe/0xff when ns > 254)
+                uint32_t r2 = 0;
+                for (uint32_t s = 0; s < 256 && !err; s++)
+                    if (lds_u8(rank + s) == 0xfeu) sts_u8(rank + s, r2++);
+                if (!err && (ns == 0 || lds_u8(unrank + 0) != 0)) err = 1;       // symbol 0 = context of segment starts
+            }
+        }
+    }
+    G.sync();
+    err = G.bcast(err); ns = G.bcast(ns); shift = G.bcast(shift);
+    if (err) return ST_FORMAT;
+    const uint32_t M = 1u << shift;
+
+    // ---- table storage
+    O1Tables T;
+    T.ns = ns; T.shift = shift;
+    const uint64_t rows_bytes = ((uint64_t)ns * M + 15) & ~15ull;
+    const uint64_t need = rows_bytes + (uint64_t)ns * ns * 4;
+    if (need <= (uint64_t)S::TAB) {
+        T.rows = gsm + S::TABO;
+    } else {
+        uint8_t* a = nullptr;
+        if (G.glane == 0) a = arena_alloc(W, need);
+        T.rows = const_cast<uint8_t*>(G.bcast_ptr(a));
+        if (!T.rows) return ST_ARENA;
+    }
+    T.fc = reinterpret_cast<uint32_t*>(T.rows + rows_bytes);
+    for (uint32_t k = G.glane; k < ns * ns; k += NWAY) T.fc[k] = 0u;   // absent (ctx,sym) pairs: F = 0
+    G.sync();
+
+    // ---- phase 2: one row per context; lane 0 parses, the group fills
+    if (!BYTE) {
+        for (uint32_t ci = 0; ci < ns; ci++) {               // :967-998 (ascending symbol == ascending rank)
+            for (uint32_t k = G.glane; k < 256; k += NWAY) sts_u32(Ftmp + 4 * k, 0u);
+            G.sync();
+            uint32_t Tsum = 0;
+            if (G.glane == 0) {                              // decode_freq_d :327-358
+                if (!rd.more()) err = 1;
+                uint32_t zrun = 0;
+                for (uint32_t sj = 0; sj < ns && rd.more() && !err; sj++) {
+                    uint32_t f = 0;
+                    if (zrun) zrun--;
+                    else {
+                        f = rd.varint();
+                        if (f == 0) { if (!rd.more()) { err = 1; break; } zrun = rd.get(); }
+                    }
+                    sts_u32(Ftmp + 4 * sj, f);
+                    Tsum += f;
+                }
+            }
+            G.sync();
+            err = G.bcast(err); Tsum = G.bcast(Tsum);
+            if (err) return ST_FORMAT;
+            if (!Tsum) continue;                             // :977-980
+            if (!build_o1_row<NWAY>(G, Ftmp, T, ci, Tsum, false)) return ST_FORMAT;
+        }
+    } else {
+        // rANS_static.c:748-813: outer "sym [run]" list of contexts, one 4x8 table each
+        uint32_t run_i = 0, ctx = 0;
+        if (G.glane == 0) ctx = rd.get();
+        for (;;) {
+            for (uint32_t k = G.glane; k < 256; k += NWAY) sts_u32(Ftmp + 4 * k, 0u);
+            G.sync();
+            uint32_t x = 0;
+            if (G.glane == 0) {
+                if (rd.p + 16 > rd.end || !parse_table_4x8(rd, Ftmp, &x, true)) err = 1;
+                else if (x < 4095 || x > 4096) err = 1;      // :797
+            }
+            G.sync();
+            err = G.bcast(err); ctx = G.bcast(ctx); x = G.bcast(x);
+            if (err) return ST_FORMAT;
+            if (!build_o1_row<NWAY>(G, Ftmp, T, ctx, 4096u, true)) return ST_FORMAT;
+            uint32_t more = 0;
+            if (G.glane == 0) {
+                if (!run_i && ctx + 1 == rd.peek()) { rd.get(); ctx++; run_i = rd.get(); }
+                else if (run_i) { run_i--; if (++ctx > 255) err = 1; }
+                else ctx = rd.get();
+                more = (!err && ctx != 0) ? 1u : 0u;
+            }
+            more = G.bcast(more); err = G.bcast(err);
+            if (err) return ST_FORMAT;
+            if (!more) break;
+        }
+    }
+    __threadfence_block();
+    G.sync();
+
+    // ---- states
+    const uint8_t* sp = nullptr;
+    if (G.glane == 0) sp = body ? body : rd.p;
+    sp = G.bcast_ptr(sp);
+    if (sp + 4 * NWAY > in_end) return ST_FORMAT;            // :1005
+    uint32_t r0 = ld_u32_le(sp + 4 * G.glane);
+    if (!G.all(r0 >= (BYTE ? (1u << 23) : (1u << 15)))) return ST_FORMAT;
+    *R = r0;
+    *first_word = sp + 4 * NWAY;
+    *ctx0 = lds_u8(rank + 0);
+    *Tout = T;
+    return ST_OK;
+}
+
+template <int NWAY, bool BYTE>
+__device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const O1Tables T, uint32_t unrank,
+                                        uint32_t ctx0, uint8_t* out, uint32_t seg, uint32_t tail, uint32_t maxit,
+                                        const Grp<NWAY>& G) {
+    const uint32_t lt = (NWAY == 32) ? lanemask_lt() : ((1u << G.glane) - 1u);
+    const uint32_t shift = T.shift, mask = (1u << shift) - 1u, ns = T.ns;
+    const uint32_t mine = seg + ((G.glane == NWAY - 1) ? tail : 0u);   // symbols this lane decodes
+    const uint32_t group_steps = seg + tail;
+    uint8_t* op = out + (size_t)G.glane * seg;
+    uint32_t ctx = ctx0;
+    for (uint32_t i = 0; i < maxit; i++) {
+        const bool act = i < mine;
+        if (act) {                                           // :1033-1047 / rANS_static.c:850-878
+            uint32_t m = R & mask;
+            uint32_t sr = T.rows[(size_t)ctx * (mask + 1u) + m];
+            sr = min(sr, ns - 1u);                           // rows of never-seen contexts are uninitialised
+            uint32_t e = T.fc[ctx * ns + sr];
+            R = (e >> 16) * (R >> shift) + m - (e & 0xffffu);
+            *op++ = (uint8_t)lds_u8(unrank + sr);
+            ctx = sr;
+        }
+        R = renorm_step<NWAY, BYTE, false>(R, act, ring, lt, G.gshift);
+        ring.advance(G.glane, i < group_steps);
+    }
+}
+
+template <int NWAY, bool BYTE>
+__global__ void __launch_bounds__(32) dec_o1_kernel(DecWork* W, int32_t* status, uint32_t kind) {
+    using C = GroupCfg<NWAY>;
+    using S = O1Smem<NWAY>;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const Grp<NWAY> G;
+    uint8_t* gsm = smem_raw + G.g * S::STRIDE;
+    const uint32_t base = smem_addr(gsm);
+    const uint32_t njobs = W->njobs[kind];
+    const DecJob* jobs = W->jobs[kind];
+
+    for (;;) {
+        uint32_t j0 = 0;
+        if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], (uint32_t)C::G);
+        j0 = __shfl_sync(0xffffffffu, j0, 0);
+        if (j0 >= njobs) break;
+        const uint32_t ji = j0 + G.g;
+        const bool active = ji < njobs;
+        DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
+        O1Tables T;
+        T.rows = nullptr; T.fc = nullptr; T.ns = 1; T.shift = 12;
+        uint32_t R = 0, ctx0 = 0;
+        const uint8_t* first_word = nullptr;
+        bool ok = false;
+        if (active) {
+            job = jobs[ji];
+            int32_t st = o1_setup<NWAY, BYTE>(G, W, job, gsm, &T, &R, &first_word, &ctx0);
+            ok = st == ST_OK;
+            if (!ok && G.glane == 0) set_status(status, job.blk, st);
+        }
+        WordRing<NWAY> ring;
+        ring.init(first_word, job.in + job.in_len, base + S::RINGO, G, ok);
+        __syncwarp();
+        const uint32_t seg = ok ? job.out_len / NWAY : 0, tail = ok ? job.out_len - seg * NWAY : 0;
+        const uint32_t maxit = __reduce_max_sync(0xffffffffu, seg + tail);
+        o1_loop<NWAY, BYTE>(R, ring, T, base + S::UNRANK, ctx0, job.out, seg, tail, maxit, G);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// X_CAT copy: one CTA per job
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) copy_kernel(DecWork* W) {
+    const uint32_t njobs = W->njobs[JK_COPY];
+    for (uint32_t ji = blockIdx.x; ji < njobs; ji += gridDim.x) {
+        DecJob job = W->jobs[JK_COPY][ji];
+        const uint8_t* s = job.in;
+        uint8_t* d = job.out;
+        uint32_t n = job.out_len;
+        if ((((uintptr_t)s ^ (uintptr_t)d) & 15) == 0 && n >= 64) {
+            uint32_t head = (uint32_t)((16 - ((uintptr_t)d & 15)) & 15);
+            for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) d[i] = s[i];
+            uint32_t nv = (n - head) / 16;
+            const uint4* sv = reinterpret_cast<const uint4*>(s + head);
+            uint4* dv = reinterpret_cast<uint4*>(d + head);
+            for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) dv[i] = sv[i];
+            for (uint32_t i = head + nv * 16 + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+        } else {
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// un-RLE, rle.c:142-187.  One 256-thread CTA per chain.
+//   pass A: run-length varints -> values (scratch u32 per varint, carried across tiles)
+//   pass B: literals -> output offsets (block scan with carry) -> fill
+// ------------------------------------------------------------------------------------------
+constexpr int RLE_T = 256;
+
+template <typename T>
+__device__ __forceinline__ T block_exscan(T v, T* warp_tot, T* total) {
+    uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    T x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { T y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    T pre = 0, tot = 0;
+    for (int k = 0; k < RLE_T / 32; k++) { T t = warp_tot[k]; if (k < (int)w) pre += t; tot += t; }
+    __syncthreads();
+    *total = tot;
+    return pre + x - v;
+}
+
+__global__ void __launch_bounds__(RLE_T) rle_kernel(DecWork* W, int32_t* status, uint32_t* out_len) {
+    __shared__ uint8_t is_rle[256];
+    __shared__ uint32_t wtot[RLE_T / 32];
+    __shared__ unsigned long long wtot64[RLE_T / 32];
+    __shared__ uint32_t* runval_s;
+    __shared__ int skip_s;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t li = blockIdx.x; li < W->nrle; li += gridDim.x) {
+        const uint32_t ci = W->rle_list[li];
+        const Chain c = W->chains[ci];
+        __syncthreads();
+        if (tid == 0) {
+            int skip = status[c.blk] != ST_OK;
+            uint32_t nrs0 = 0;
+            runval_s = nullptr;
+            if (!skip) {
+                nrs0 = c.meta[0] ? c.meta[0] : 256u;
+                if (c.u_meta < 1 + nrs0) { set_status(status, c.blk, ST_FORMAT); skip = 1; }     // …4x16pr.c:1604
+            }
+            if (!skip) {
+                runval_s = reinterpret_cast<uint32_t*>(arena_alloc(W, 4ull * (c.u_meta + 1)));
+                if (!runval_s) { set_status(status, c.blk, ST_ARENA); skip = 1; }
+            }
+            skip_s = skip;
+        }
+        is_rle[tid] = 0;
+        __syncthreads();
+        if (skip_s) continue;
+        const uint8_t* meta = c.meta;
+        const uint32_t nrs = meta[0] ? meta[0] : 256u;
+        if (tid < nrs) is_rle[meta[1 + tid]] = 1;
+        uint32_t* runval = runval_s;
+        __syncthreads();
+        const uint8_t* run = meta + 1 + nrs;
+        const uint32_t run_len = c.u_meta - (1 + nrs);
+
+        // pass A: a varint ends at a byte without the continuation bit (or at the last byte)
+        uint32_t nvar = 0;
+        for (uint32_t t0 = 0; t0 < run_len; t0 += RLE_T) {
+            uint32_t i = t0 + tid;
+            uint32_t term = 0;
+            if (i < run_len) term = (!(run[i] & 0x80) || i + 1 == run_len) ? 1u : 0u;
+            uint32_t tot, idx = block_exscan<uint32_t>(term, wtot, &tot);
+            if (term) {                                      // walk back to the start of this varint
+                uint32_t s = i;
+                while (s > 0 && (run[s - 1] & 0x80)) s--;
+                uint32_t v = 0;
+                for (uint32_t k = s; k <= i; k++) v = (v << 7) | (run[k] & 0x7f);
+                runval[nvar + idx] = v;
+            }
+            nvar += tot;
+        }
+        __syncthreads();
+
+        // pass B
+        const uint8_t* lit = c.t1;
+        const uint32_t nlit = c.t1_size;
+        uint8_t* out = c.t2;
+        unsigned long long opos = 0;
+        uint32_t kbase = 0;
+        int overflow = 0;
+        for (uint32_t t0 = 0; t0 < nlit; t0 += RLE_T) {
+            uint32_t i = t0 + tid;
+            uint32_t b = 0, isr = 0;
+            if (i < nlit) { b = lit[i]; isr = is_rle[b]; }
+            uint32_t tot, k = block_exscan<uint32_t>(isr, wtot, &tot);
+            unsigned long long len = 0;
+            if (i < nlit) {
+                len = 1;
+                if (isr) { uint32_t kk = kbase + k; len += (kk < nvar) ? runval[kk] : 0u; }
+            }
+            unsigned long long ltot, off = block_exscan<unsigned long long>(len, wtot64, &ltot);
+            off += opos;
+            if (i < nlit) {
+                if (off + len > c.osz) overflow = 1;         // rle.c:161,172
+                else for (unsigned long long q = 0; q < len; q++) out[off + q] = (uint8_t)b;
+            }
+            opos += ltot;
+            kbase += tot;
+        }
+        overflow = __syncthreads_or(overflow);
+        if (tid == 0) {
+            if (overflow || opos > c.osz) set_status(status, c.blk, ST_FORMAT);
+            else {
+                W->chains[ci].t2_size = (uint32_t)opos;
+                if (!(c.flags & F_PACK)) {
+                    W->chains[ci].final_size = (uint32_t)opos;
+                    if (c.expect == 0xffffffffu) out_len[c.blk] = (uint32_t)opos;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// un-PACK, pack.c:211-348.  One CTA per chain.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unpack_kernel(DecWork* W, int32_t* status, uint32_t* out_len) {
+    __shared__ uint8_t map[16];
+    __shared__ int skip_s;
+    for (uint32_t li = blockIdx.x; li < W->nunpack; li += gridDim.x) {
+        const uint32_t ci = W->unpack_list[li];
+        __syncthreads();
+        const Chain c = W->chains[ci];
+        if (threadIdx.x == 0) skip_s = status[c.blk] != ST_OK;
+        if (threadIdx.x < 16) map[threadIdx.x] = c.map[threadIdx.x];
+        __syncthreads();
+        if (skip_s) continue;
+        const uint8_t* in = c.t2;
+        const uint32_t len = c.t2_size;
+        uint8_t* out = c.t3;
+        const uint32_t olen = (c.per == 1) ? len : c.osz;    // rANS_static4x16pr.c:1616-1617
+        bool bad = false;
+        if (c.per == 1) {
+            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) out[i] = in[i];
+        } else if (c.per == 0) {
+            for (uint32_t i = threadIdx.x; i < olen; i += blockDim.x) out[i] = map[0];
+        } else {
+            const uint32_t per = c.per, bits = 8 / per, mask = (1u << bits) - 1u;
+            if (((uint64_t)olen + per - 1) / per > len) bad = true;              // pack.c:238,279,314
+            else {
+                const uint32_t nin = (olen + per - 1) / per; // each thread expands whole input bytes
+                for (uint32_t j = threadIdx.x; j < nin; j += blockDim.x) {
+                    uint32_t v = in[j];
+                    uint32_t o = j * per;
+                    for (uint32_t k = 0; k < per && o + k < olen; k++) out[o + k] = map[(v >> (k * bits)) & mask];
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            if (bad) set_status(status, c.blk, ST_FORMAT);
+            else {
+                W->chains[ci].final_size = olen;
+                if (c.expect == 0xffffffffu) out_len[c.blk] = olen;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// unstripe, utils.h:41-73.  One CTA per striped block.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unstripe_kernel(DecWork* W, int32_t* status) {
+    __shared__ uint32_t at[256];
+    __shared__ int bad;
+    for (uint32_t si = blockIdx.x; si < W->nstripe; si += gridDim.x) {
+        const StripeOp op = W->stripes[si];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bad = status[op.blk] != ST_OK ? 2 : 0;
+            uint32_t a = 0;
+            for (uint32_t j = 0; j < op.N; j++) { at[j] = a; a += op.ulen / op.N + ((op.ulen % op.N) > j); }
+        }
+        __syncthreads();
+        if (threadIdx.x < op.N && bad == 0) {
+            const Chain& c = W->chains[op.chain0 + threadIdx.x];
+            if (c.final_size != c.expect) bad = 1;           // rANS_static4x16pr.c:1419-1420
+        }
+        __syncthreads();
+        if (bad) { if (threadIdx.x == 0 && bad == 1) set_status(status, op.blk, ST_FORMAT); continue; }
+        const uint32_t N = op.N, ulen = op.ulen;
+        for (uint32_t i = threadIdx.x; i < ulen; i += blockDim.x) op.out[i] = op.parts[at[i % N] + i / N];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int g_grid[JK_NKINDS];
+static int g_sms = 0;
+
+template <typename K>
+static int persistent_grid(K kernel, int smem, int threads, int sms) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    return per_sm * sms;
+}
+
+int decode_init(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    g_sms = prop.multiProcessorCount;
+    g_grid[JK_O0_32] = persistent_grid(dec_o0_kernel<32, false>, O0Smem<32>::TOTAL, 32, g_sms);
+    g_grid[JK_O0_4]  = persistent_grid(dec_o0_kernel<4, false>,  O0Smem<4>::TOTAL, 32, g_sms);
+    g_grid[JK_R8_O0] = persistent_grid(dec_o0_kernel<4, true>,   O0Smem<4>::TOTAL, 32, g_sms);
+    g_grid[JK_O1_32] = persistent_grid(dec_o1_kernel<32, false>, O1Smem<32>::TOTAL, 32, g_sms);
+    g_grid[JK_O1_4]  = persistent_grid(dec_o1_kernel<4, false>,  O1Smem<4>::TOTAL, 32, g_sms);
+    g_grid[JK_R8_O1] = persistent_grid(dec_o1_kernel<4, true>,   O1Smem<4>::TOTAL, 32, g_sms);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// Enqueue the whole decode pipeline for one batch.  Returns the number of kernels launched.
+int decode_launch(const DecodeBatch& b, cudaStream_t st) {
+    PlanArgs A;
+    A.W = b.work; A.in_base = b.in_base; A.in_off = b.in_off; A.in_len = b.in_len;
+    A.out_base = b.out_base; A.out_off = b.out_off; A.out_len = b.out_len;
+    A.status = b.status; A.method = b.method; A.nblk = b.nblk;
+    int launches = 0;
+    plan_kernel<<<(b.nblk + 127) / 128, 128, 0, st>>>(A); launches++;
+    auto want = [&](uint32_t k) { return (b.kinds >> k) & 1u; };
+    if (want(JK_O0_32)) { dec_o0_kernel<32, false><<<g_grid[JK_O0_32], 32, O0Smem<32>::TOTAL, st>>>(b.work, b.status, JK_O0_32); launches++; }
+    if (want(JK_O0_4))  { dec_o0_kernel<4, false><<<g_grid[JK_O0_4], 32, O0Smem<4>::TOTAL, st>>>(b.work, b.status, JK_O0_4); launches++; }
+    if (want(JK_O1_32)) { dec_o1_kernel<32, false><<<g_grid[JK_O1_32], 32, O1Smem<32>::TOTAL, st>>>(b.work, b.status, JK_O1_32); launches++; }
+    if (want(JK_O1_4))  { dec_o1_kernel<4, false><<<g_grid[JK_O1_4], 32, O1Smem<4>::TOTAL, st>>>(b.work, b.status, JK_O1_4); launches++; }
+    if (want(JK_R8_O0)) { dec_o0_kernel<4, true><<<g_grid[JK_R8_O0], 32, O0Smem<4>::TOTAL, st>>>(b.work, b.status, JK_R8_O0); launches++; }
+    if (want(JK_R8_O1)) { dec_o1_kernel<4, true><<<g_grid[JK_R8_O1], 32, O1Smem<4>::TOTAL, st>>>(b.work, b.status, JK_R8_O1); launches++; }
+    if (want(JK_COPY))  { copy_kernel<<<g_sms * 4, 256, 0, st>>>(b.work); launches++; }
+    if (b.post & 1u) { rle_kernel<<<g_sms * 4, RLE_T, 0, st>>>(b.work, b.status, b.out_len); launches++; }
+    if (b.post & 2u) { unpack_kernel<<<g_sms * 4, 256, 0, st>>>(b.work, b.status, b.out_len); launches++; }
+    if (b.post & 4u) { unstripe_kernel<<<g_sms * 4, 256, 0, st>>>(b.work, b.status); launches++; }
+    return launches;
+}
+
+}  // namespace hb

@@ -1,0 +1,155 @@
+/*
+ * htscodecs_b200.h -- C ABI of libhtscodecs_b200.so: the B200 (sm_100a) implementation of
+ * htscodecs' static-rANS hot path.  Plain C, pointers and sizes only.
+ *
+ * Section 1 re-exports the reference's own entry points unchanged (a drop-in for
+ * htscodecs/rANS_static4x16.h:40-50 and rANS_static.h:40-43 of the reference): same names, same
+ * argument meaning, same NULL-on-error behaviour, malloc'ed results the caller free()s.
+ * Section 2 is new: batched entry points (many independent CRAM blocks per call), which is
+ * what a GPU needs to be fast.  Every byte of codec work happens in CUDA kernels; there is no
+ * CPU fallback -- the calls fail (NULL / negative status) if no sm_100 device is usable.
+ */
+#ifndef HTSCODECS_B200_H
+#define HTSCODECS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Drop-in API (replaces the reference symbols of the same name)
+ * ---------------------------------------------------------------------------------------- */
+
+/* order argument / first stream byte (reference rANS_static4x16pr.c:39-43).  Bits 8-15 of
+ * `order` carry the stripe count N (0 means 4).  RANS_ORDER_X32 (0x04) selects the 32-way
+ * interleave; it is not in the v1.1 reference and is defined as its N=32 generalisation. */
+#define RANS_ORDER_1      0x01
+#define RANS_ORDER_X32    0x04
+#define RANS_ORDER_STRIPE 0x08
+#define RANS_ORDER_NOSZ   0x10
+#define RANS_ORDER_CAT    0x20
+#define RANS_ORDER_RLE    0x40
+#define RANS_ORDER_PACK   0x80
+
+/* replaces rans_compress_bound_4x16, reference rANS_static4x16.h:40 (.c:360-372) */
+unsigned int rans_compress_bound_4x16(unsigned int size, int order);
+
+/* replaces rans_compress_to_4x16, reference rANS_static4x16.h:41-43 (.c:1138-1345).
+ * out == NULL: a bound-sized buffer is malloc'ed.  out != NULL: *out_size is the capacity on
+ * entry (must be >= rans_compress_bound_4x16(in_size, order)) and the stream length on return. */
+unsigned char *rans_compress_to_4x16(unsigned char *in, unsigned int in_size,
+                                     unsigned char *out, unsigned int *out_size, int order);
+
+/* replaces rans_compress_4x16, reference rANS_static4x16.h:44-45 (.c:1347-1350) */
+unsigned char *rans_compress_4x16(unsigned char *in, unsigned int in_size,
+                                  unsigned int *out_size, int order);
+
+/* replaces rans_uncompress_to_4x16, reference rANS_static4x16.h:46-47 (.c:1352-1636).
+ * out == NULL: the result is malloc'ed.  out != NULL: *out_size is the capacity on entry
+ * (exactly the stored size for X_STRIPE streams, the expected size for X_NOSZ streams). */
+unsigned char *rans_uncompress_to_4x16(unsigned char *in, unsigned int in_size,
+                                       unsigned char *out, unsigned int *out_size);
+
+/* replaces rans_uncompress_4x16, reference rANS_static4x16.h:48-49 (.c:1638-1641) */
+unsigned char *rans_uncompress_4x16(unsigned char *in, unsigned int in_size,
+                                    unsigned int *out_size);
+
+/* replaces rans_uncompress (legacy CRAM 3.0 rANS 4x8), reference rANS_static.h:42-43
+ * (rANS_static.c:934-943).  The 4x8 encoder is out of scope. */
+unsigned char *rans_uncompress(unsigned char *in, unsigned int in_size, unsigned int *out_size);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Batched API (new; no reference equivalent -- the reference's callers loop over blocks,
+ *    e.g. tests/rANS_static4x16pr_test.c:190-215, one call per block per thread)
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct hts_b200_ctx hts_b200_ctx;
+
+/* per-block status codes */
+#define HTS_B200_OK            0
+#define HTS_B200_ERR_FORMAT   (-1)   /* malformed stream (the reference returns NULL) */
+#define HTS_B200_ERR_SIZE     (-2)   /* output capacity too small / size mismatch */
+#define HTS_B200_ERR_NESTED   (-4)   /* X_STRIPE inside X_STRIPE: never written by the encoder */
+#define HTS_B200_ERR_INTERNAL (-5)
+
+/* block codec selector for the batched decoders */
+#define HTS_B200_RANS4x16 0          /* CRAM 3.1 rANS Nx16 (block method RANSPR = 5) */
+#define HTS_B200_RANS4x8  1          /* CRAM 3.0 rANS 4x8  (block method RANS   = 4) */
+
+/* One context per (host thread, device).  Owns a CUDA stream, work lists and scratch arenas that
+ * grow on demand and are reused across calls.  Not thread-safe: use one per thread (the drop-in
+ * calls above keep a thread-local one).  device < 0 means the current CUDA device. */
+hts_b200_ctx *hts_b200_create(int device);
+void hts_b200_destroy(hts_b200_ctx *ctx);
+const char *hts_b200_last_error(const hts_b200_ctx *ctx);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+unsigned long long hts_b200_launch_count(const hts_b200_ctx *ctx);
+/* the context's CUDA stream (a cudaStream_t), so callers can order their own work or events */
+void *hts_b200_stream(const hts_b200_ctx *ctx);
+
+/*
+ * Device-resident batched decode.  Every pointer argument is a DEVICE pointer on the context's
+ * device.  Block i reads in_base[in_off[i] .. +in_len[i]) and writes out_base[out_off[i] ..).
+ * out_len[i] is the capacity on entry (and the expected size for X_NOSZ streams) and the decoded
+ * size on return; status[i] receives HTS_B200_OK or an error.  method[i] picks the codec
+ * (NULL = all RANS4x16).  Work is enqueued on the context's stream; the call returns after the
+ * stream has drained (sync != 0) or immediately (sync == 0: results are valid once the stream
+ * has been synchronised; a rare scratch-arena overflow is then reported per block as
+ * HTS_B200_ERR_INTERNAL instead of being retried).
+ * Returns 0, or a negative value if the batch could not be run at all.
+ */
+int hts_b200_uncompress_batch_dev(hts_b200_ctx *ctx, int nblk,
+                                  const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
+                                  uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
+                                  int32_t *status, const uint8_t *method, int sync);
+
+/*
+ * Host-resident batched decode: same contract with HOST pointers (pinned or pageable).  Inputs
+ * are copied to the device, decoded and copied back in overlapping chunks on the context's
+ * streams.  This is the end-to-end path bench.py times ("e2e").
+ */
+int hts_b200_uncompress_batch_host(hts_b200_ctx *ctx, int nblk,
+                                   const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
+                                   uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
+                                   int32_t *status, const uint8_t *method);
+
+/*
+ * Device-resident batched encode (rANS 4x16 only).  order[i] is the reference's `order` argument
+ * for block i.  out_len[i]: capacity on entry (>= rans_compress_bound_4x16(in_len[i], order[i])),
+ * stream length on return.
+ */
+int hts_b200_compress_batch_dev(hts_b200_ctx *ctx, int nblk,
+                                const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
+                                uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
+                                int32_t *status, const int32_t *order, int sync);
+
+int hts_b200_compress_batch_host(hts_b200_ctx *ctx, int nblk,
+                                 const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
+                                 uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
+                                 int32_t *status, const int32_t *order);
+
+/* Pointer-array convenience forms (what a caller holding one malloc'ed buffer per CRAM block
+ * uses); thin wrappers that stage through pinned memory and call the *_host functions. */
+int rans4x16_uncompress_batch(hts_b200_ctx *ctx, int nblk,
+                              const unsigned char *const *in, const unsigned int *in_size,
+                              unsigned char *const *out, unsigned int *out_size, int *status);
+int rans4x16_compress_batch(hts_b200_ctx *ctx, int nblk,
+                            const unsigned char *const *in, const unsigned int *in_size,
+                            unsigned char *const *out, unsigned int *out_size,
+                            const int *order, int *status);
+
+/* Stored uncompressed size of a 4x16 (method 0) or 4x8 (method 1) stream held in HOST memory;
+ * returns 0 and sets *ulen, or -1 (X_NOSZ stream / truncated header). */
+int hts_b200_peek_size(const uint8_t *in, uint32_t in_len, int method, uint32_t *ulen);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA runtime. */
+void *hts_b200_host_alloc(size_t bytes);
+void hts_b200_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HTSCODECS_B200_H */

@@ -1,0 +1,64 @@
+"""CPU-only: the C-ABI library builds, loads, and exports every symbol include/htscodecs_b200.h
+declares (no compute calls here -- there is no GPU in the authoring container)."""
+import ctypes
+import os
+import re
+
+import htscodecs_b200 as hb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "htscodecs_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(\w+)\s*\(", src))
+    return {n for n in names if n.startswith(("rans", "hts_b200_"))}
+
+
+def test_header_and_binding_agree():
+    assert _declared() == set(hb.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    from htscodecs_b200 import build
+    build.build()
+    lib = ctypes.CDLL(hb.LIB_PATH)
+    for name in sorted(_declared()):
+        assert getattr(lib, name) is not None, name
+
+
+def test_bound_matches_reference_numbers():
+    # pure host arithmetic (reference rANS_static4x16pr.c:360-372); SURVEY 8a values
+    assert hb.rans_compress_bound_4x16(1048576, 0) == 1101802
+    assert hb.rans_compress_bound_4x16(1048576, 1) == 1299952
+    assert hb.rans_compress_bound_4x16(1048576, 64) == 1300728
+
+
+def test_bound_matches_oracle(oracle):
+    for n in (0, 1, 20, 21, 1000, 65536, 1 << 20, (1 << 24) + 3):
+        for order in (0, 1, 4, 5, 64, 65, 128, 193, 8, 9, 0xc9, 0x208, 0x2009):
+            assert hb.rans_compress_bound_4x16(n, order) == oracle.bound(n, order)
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        return
+    try:
+        hb.Context(0)
+    except RuntimeError as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("Context() must fail without a GPU")
+    assert hb.rans_uncompress_4x16(b"\x00\x05hello") is None
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product path may not import / link / execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "htscodecs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in text.replace("no CPU fallback", ""), os.path.join(dirpath, fn)
