@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the static-rANS hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--blocks B]
+
+Workload (BASELINE.json configs[1]): batched decode of 4096 synthetic 1 MiB Illumina-binned
+quality blocks, rANS Nx16 order-0, X_32 (32-way interleave), per GPU.  One step = one pass of the
+hot path over the whole batch.
+
+* value  : uncompressed GB/s (1e9), inputs and outputs resident in HBM, CUDA-event timed.
+* e2e    : the same batch through the host-buffer C-ABI call (pinned host memory, H2D of the
+           compressed bytes and D2H of the decoded bytes inside the timed region).
+* roofline: HBM, algorithmic bytes (compressed read + uncompressed write) over the step time.
+* cpu_baseline / --impl reference: the unmodified reference C (oracle/_ref/libref.so, built from
+  /root/reference by oracle/Makefile) decoding the same blocks on all host cores, one block per
+  thread.  The v1.1 reference has no X_32, so it decodes the 4-way stream of the same data
+  (identical tables and entropy).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rANS4x16 o0 X_32 batched decode throughput (uncompressed)"
+UNIT = "GB/s"
+BLOCK = 1 << 20
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def mark(self):
+        """Samples before this call (set-up, warm-up) are dropped."""
+        self.lines = []
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_blocks(distinct, rank):
+    from htscodecs_b200 import synth
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        return list(ex.map(lambda i: synth.qual_block(rank * 100003 + i, BLOCK), range(distinct)))
+
+
+def cpu_reference_decode(blocks, seconds_budget, threads):
+    """Times oracle/_ref/libref.so (the unmodified reference) decoding 4-way order-0 streams of the
+    same blocks: `threads` pthreads inside C (oracle/ref_mt.c), one block per thread, dynamic
+    schedule.  Returns (GB/s, sample text, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import RefLib, Oracle, mt_run
+    lib, kind = (RefLib(), "reference") if RefLib.available() else (Oracle(), "port")
+    nd = min(len(blocks), 32)
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        comp = list(ex.map(lambda b: lib.compress(b.tobytes(), 0), blocks[:nd]))
+    olens = [BLOCK] * nd
+    t1, _ = mt_run(lib.lib, comp, olens=olens, threads=threads, reps=1)          # warm-up + calibration
+    assert t1 > 0, "reference decode failed"
+    reps = max(1, min(2000, int(seconds_budget / t1)))
+    t, produced = mt_run(lib.lib, comp, olens=olens, threads=threads, reps=reps)
+    assert t > 0 and produced == reps * nd * BLOCK
+    return produced / t / 1e9, (f"{reps} passes over {nd} x 1 MiB blocks (4-way order-0 streams of the same "
+                                f"data), {threads} threads, {t:.1f} s"), kind
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    blocks = make_blocks(min(args.distinct, 16), 0)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference_decode(blocks, 0.5, threads)
+    t0 = time.perf_counter()
+    sample = kind = None
+    for _ in range(args.steps):
+        v, sample, kind = cpu_reference_decode(blocks, args.cpu_seconds / max(1, args.steps), threads)
+        vals.append(v)
+    total = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
+        "config": {"workload": "host-CPU decode of 1 MiB Illumina-binned quality blocks, rANS 4x16 order-0 "
+                               "(reference has no X_32), one block per thread", "block_bytes": BLOCK},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import htscodecs_b200 as hb
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                          # nvidia-smi needs ~1 s before its first sample
+    ctx = hb.Context(local_rank)
+    nblk, distinct = args.blocks, min(args.distinct, args.blocks)
+    blocks = make_blocks(distinct, rank)
+    # compressed inputs: X_32 order-0 streams (the bench measures DECODE; the streams come from the
+    # encoder under test when available, else from the CPU oracle as data preparation only)
+    oracle = Oracle()
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        comps = list(ex.map(lambda b: oracle.compress(b.tobytes(), 4), blocks))
+    in_len = np.array([len(comps[i % distinct]) for i in range(nblk)], np.uint32)
+    in_off = np.zeros(nblk, np.uint64)
+    in_off[1:] = np.cumsum(in_len[:-1].astype(np.uint64))
+    c_bytes = int(in_len.astype(np.uint64).sum())
+    u_bytes = nblk * BLOCK
+    out_off = np.arange(nblk, dtype=np.uint64) * BLOCK
+
+    # pinned host copies (e2e) and device-resident copies (value)
+    pin_in = hb.PinnedArray(c_bytes + 64)
+    for i in range(nblk):
+        pin_in.array[int(in_off[i]): int(in_off[i]) + int(in_len[i])] = np.frombuffer(comps[i % distinct], np.uint8)
+    pin_out = hb.PinnedArray(u_bytes + 64)
+    d_in = torch.empty(c_bytes + 64, dtype=torch.uint8, device="cuda")
+    d_in[: c_bytes].copy_(torch.from_numpy(pin_in.array[:c_bytes]))
+    d_in_off = torch.from_numpy(in_off.view(np.int64)).cuda()
+    d_in_len = torch.from_numpy(in_len.view(np.int32)).cuda()
+    d_out = torch.empty(u_bytes + 64, dtype=torch.uint8, device="cuda")
+    d_out_off = torch.from_numpy(out_off.view(np.int64)).cuda()
+    caps = torch.full((nblk,), BLOCK, dtype=torch.int32, device="cuda")
+    d_out_len = caps.clone()
+    d_status = torch.zeros(nblk, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    def step_dev():
+        # out_len is in/out (capacity -> decoded size); every block decodes to exactly its capacity,
+        # so the array can be reused across steps without a reset
+        ctx.uncompress_batch_dev(nblk, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_len, d_status, sync=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up + correctness of the timed path
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    torch.cuda.synchronize()
+    assert int((d_status != 0).sum()) == 0, "decode reported errors"
+    chk = d_out[: distinct * BLOCK].cpu().numpy()
+    for i in range(distinct):
+        assert np.array_equal(chk[i * BLOCK:(i + 1) * BLOCK], blocks[i]), "decoded bytes differ from the source"
+
+    # ---- timed: device-resident
+    sampler.mark()
+    barrier()
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launches - l0
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * u_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- timed: end to end through the host-buffer C-ABI call
+    h_out_len = np.full(nblk, BLOCK, np.uint32)
+    h_status = np.zeros(nblk, np.int32)
+
+    def step_host():
+        h_out_len[:] = BLOCK
+        ctx.uncompress_batch_host(nblk, pin_in.array, in_off, in_len, pin_out.array, out_off, h_out_len, h_status)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    if args.skip_e2e:
+        e2e_steps, e2e_s = 0, float("inf")
+    else:
+        for _ in range(2):
+            step_host()
+        assert (h_status == 0).all()
+        for i in (0, distinct - 1, nblk - 1):
+            assert np.array_equal(pin_out.array[i * BLOCK:(i + 1) * BLOCK], blocks[i % distinct]), "e2e output differs"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * u_bytes / e2e_s / 1e9
+    clocks = sampler.stop()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline (HBM) for the dominant kernel, dec_o0_kernel<32,false>
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    algo_bytes = c_bytes + u_bytes
+    achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dec_o0_32_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+
+    if args.skip_cpu:
+        cpu_v, cpu_sample, cpu_kind = None, "skipped (--skip-cpu)", "reference"
+    else:
+        cpu_v, cpu_sample, cpu_kind = cpu_reference_decode(blocks, args.cpu_seconds, os.cpu_count() or 1)
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/u32", "data": "synthetic",
+        "config": {"workload": f"batched decode of {nblk} x 1 MiB Illumina-binned quality blocks per GPU, "
+                               "rANS Nx16 order-0 X_32 (BASELINE configs[1])",
+                   "blocks_per_gpu": nblk, "block_bytes": BLOCK, "distinct_blocks": distinct,
+                   "compressed_bytes_per_gpu": c_bytes, "ratio": c_bytes / u_bytes,
+                   "l2": "inputs+outputs (%.1f GiB) exceed the 126 MB L2; no flush needed" % ((c_bytes + u_bytes) / 2**30),
+                   "parallelism": f"blocks sharded over {world} GPU(s), no collective"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": c_bytes, "d2h_bytes_per_step": u_bytes,
+                "steps": e2e_steps, "timer": "host perf_counter around hts_b200_uncompress_batch_host (synchronous)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                     "kernel": "dec_o0_kernel<32,false>",
+                     "note": "algorithmic bytes = compressed read + uncompressed write per step; duration = "
+                             "CUDA-event step time (plan_kernel + decode kernel), so frac is a lower bound"},
+        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": cpu_kind, "sample": cpu_sample},
+    }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--blocks", type=int, default=4096, help="blocks per GPU")
+    ap.add_argument("--distinct", type=int, default=64, help="distinct blocks generated, tiled to --blocks")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the CPU baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget for the reference leg")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

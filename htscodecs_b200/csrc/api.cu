@@ -201,9 +201,9 @@ static int dec_prepare(hts_b200_ctx* ctx, DecSlot& s, int nblk, size_t arena_byt
 
 // Enqueue one decode attempt on `st` (header upload, kernels, header download into h_work[1]).
 static int dec_enqueue(hts_b200_ctx* ctx, DecSlot& s, const DecodeBatch& b, cudaStream_t st) {
-    CK(cudaMemcpyAsync(s.work.p, &s.h_work.p[0], sizeof(DecWork), cudaMemcpyHostToDevice, st));
     DecodeBatch bb = b;
     bb.work = reinterpret_cast<DecWork*>(s.work.p);
+    bb.hdr = &s.h_work.p[0];
     ctx->launches += decode_launch(bb, st);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&s.h_work.p[1], s.work.p, sizeof(DecWork), cudaMemcpyDeviceToHost, st));
@@ -236,7 +236,7 @@ extern "C" int hts_b200_uncompress_batch_dev(hts_b200_ctx* ctx, int nblk, const 
     DecSlot& s = ctx->dec;
     size_t arena_bytes = std::max<size_t>(ctx->arena_hint, 64u << 20);
     DecodeBatch b;
-    b.work = nullptr; b.in_base = in_base; b.in_off = in_off; b.in_len = in_len;
+    b.work = nullptr; b.hdr = nullptr; b.in_base = in_base; b.in_off = in_off; b.in_len = in_len;
     b.out_base = out_base; b.out_off = out_off; b.out_len = out_len; b.status = status; b.method = method;
     b.nblk = nblk; b.kinds = method ? ~0u : ~((1u << JK_R8_O0) | (1u << JK_R8_O1)); b.post = 7u;
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -341,7 +341,7 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
         if (!enc) {
             if (dec_prepare(ctx, S.dec, n, std::max<size_t>(ctx->arena_hint, 64u << 20))) return -1;
             DecodeBatch db;
-            db.work = nullptr; db.in_base = S.d_in.p; db.in_off = S.d_off.p; db.in_len = S.d_u32.p;
+            db.work = nullptr; db.hdr = nullptr; db.in_base = S.d_in.p; db.in_off = S.d_off.p; db.in_len = S.d_u32.p;
             db.out_base = S.d_out.p; db.out_off = S.d_off.p + n; db.out_len = S.d_u32.p + n;
             db.status = reinterpret_cast<int32_t*>(d_status); db.method = method ? S.d_method.p : nullptr; db.nblk = n;
             // host hint: which kernels can be needed (first byte of each stream; stripes hide their sub-streams)

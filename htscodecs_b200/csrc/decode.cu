@@ -1220,6 +1220,10 @@ int decode_init(int device) {
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// The per-batch header travels as a kernel argument (copied at launch), so the host may reuse
+// its copy immediately even when several batches are in flight on the stream.
+__global__ void work_init_kernel(DecWork* dst, DecWork hdr) { *dst = hdr; }
+
 // Enqueue the whole decode pipeline for one batch.  Returns the number of kernels launched.
 int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     PlanArgs A;
@@ -1227,6 +1231,7 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     A.out_base = b.out_base; A.out_off = b.out_off; A.out_len = b.out_len;
     A.status = b.status; A.method = b.method; A.nblk = b.nblk;
     int launches = 0;
+    work_init_kernel<<<1, 1, 0, st>>>(b.work, *b.hdr); launches++;
     plan_kernel<<<(b.nblk + 127) / 128, 128, 0, st>>>(A); launches++;
     auto want = [&](uint32_t k) { return (b.kinds >> k) & 1u; };
     if (want(JK_O0_32)) { dec_o0_kernel<32, false><<<g_grid[JK_O0_32], 32, O0Smem<32>::TOTAL, st>>>(b.work, b.status, JK_O0_32); launches++; }

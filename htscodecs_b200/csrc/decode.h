@@ -6,6 +6,7 @@ namespace hb {
 
 struct DecodeBatch {
     DecWork* work;              // device
+    const DecWork* hdr;         // host: initial header (counters zero, capacities, list pointers)
     const uint8_t* in_base;     // device
     const uint64_t* in_off;     // device
     const uint32_t* in_len;     // device

@@ -23,6 +23,25 @@ def _buf(b):
     return (C.c_uint8 * max(1, len(b))).from_buffer_copy(bytes(b) + (b"\0" if not len(b) else b""))
 
 
+def mt_run(lib, streams, olens=None, orders=None, threads=1, reps=1, encode=False, method=0):
+    """Time `reps` passes over `streams` on `threads` pthreads inside C (oracle/ref_mt.c).
+    Returns (seconds, bytes produced)."""
+    import numpy as np
+    n = len(streams)
+    ilen = np.array([len(s) for s in streams], np.uint32)
+    off = np.zeros(n, np.uint64)
+    off[1:] = np.cumsum(ilen[:-1].astype(np.uint64))
+    base = np.frombuffer(b"".join(bytes(s) for s in streams) + b"\0" * 16, np.uint8)
+    olen = np.array(olens if olens is not None else [0] * n, np.uint32)
+    order = np.array(orders if orders is not None else [0] * n, np.int32)
+    produced = C.c_uint64(0)
+    lib.ref_mt_run.restype = C.c_double
+    lib.ref_mt_run.argtypes = [C.c_void_p] * 5 + [C.c_int] * 5 + [C.POINTER(C.c_uint64)]
+    t = lib.ref_mt_run(base.ctypes.data, off.ctypes.data, ilen.ctypes.data, olen.ctypes.data, order.ctypes.data,
+                       n, threads, reps, 1 if encode else 0, method, C.byref(produced))
+    return t, produced.value
+
+
 def build_oracle():
     so = os.path.join(ORACLE_DIR, "libhtsoracle.so")
     src = os.path.join(ORACLE_DIR, "hts_oracle.c")
@@ -55,7 +74,7 @@ class Oracle:
         rc = self.lib.ho_compress(_buf(data), len(data), out, C.byref(osz), order)
         if rc != 0:
             return None
-        return bytes(out[: osz.value])
+        return C.string_at(out, osz.value)
 
     def peek_size(self, comp):
         v = C.c_uint32(0)
@@ -73,7 +92,7 @@ class Oracle:
         rc = self.lib.ho_uncompress(_buf(comp), len(comp), out, C.byref(osz))
         if rc != 0:
             return None
-        return bytes(out[: osz.value])
+        return C.string_at(out, osz.value)
 
     def uncompress_4x8(self, comp):
         comp = bytes(comp)
@@ -85,7 +104,7 @@ class Oracle:
         rc = self.lib.ho_uncompress_4x8(_buf(comp), len(comp), out, C.byref(osz))
         if rc != 0:
             return None
-        return bytes(out[: osz.value])
+        return C.string_at(out, osz.value)
 
     def var_put(self, v):
         b = (C.c_uint8 * 8)()
@@ -129,7 +148,7 @@ class RefLib:
         r = self.lib.rans_compress_to_4x16(_buf(data), len(data), out, C.byref(osz), order)
         if not r:
             return None
-        return bytes(out[: osz.value])
+        return C.string_at(out, osz.value)
 
     def uncompress(self, comp, ulen):
         comp = bytes(comp)
@@ -138,7 +157,7 @@ class RefLib:
         r = self.lib.rans_uncompress_to_4x16(_buf(comp), len(comp), out, C.byref(osz))
         if not r:
             return None
-        return bytes(out[: osz.value])
+        return C.string_at(out, osz.value)
 
     def compress_4x8(self, data, order):
         data = bytes(data)

@@ -164,8 +164,10 @@ def test_size_contract(ctx, oracle):
     assert hb.rans_uncompress_to_4x16(cn, len(data)) == data
     # garbage / truncated input fails cleanly
     assert hb.rans_uncompress_4x16(b"") is None
-    out, status = ctx.uncompress_many([c[: len(c) // 2], b"\x00", c], [len(data)] * 3)
-    assert out[2] == data and out[1] is None
+    out, status = ctx.uncompress_many([c[: len(c) // 2], b"\x00", c, b"\x08\x05"], [len(data)] * 4)
+    assert out[2] == data
+    assert out[1] == b""            # the reference also accepts this: flags 0, no size, no body -> 0 bytes
+    assert out[3] is None           # truncated stripe header
 
 
 def test_fuzz_no_crash(ctx, oracle):
