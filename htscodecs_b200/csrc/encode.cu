@@ -1,11 +1,1199 @@
-// encode.cu -- placeholder until the encode kernels land (next milestone).
+// encode.cu -- sm_100a kernels for batched rANS Nx16 encode (order-0/1, 4-way and X_32) with the
+// PACK / RLE / STRIPE / CAT / NOSZ container logic of rans_compress_to_4x16
+// (reference rANS_static4x16pr.c:1138-1345).
+//
+// The host expands each block into *leaves* (one non-striped container each: a whole block, or
+// one candidate method for one stripe sub-array, :1190-1211) and *streams* (one entropy-coded
+// byte string each: a leaf's body, or its RLE run-length meta data).  All "try it and keep the
+// smallest" decisions of the reference are taken on the device from the candidate sizes.
+//
+//   enc_stripe_kernel     byte transpose of X_STRIPE blocks                       (:1161-1180)
+//   enc_transform_kernel  PACK (pack.c:56-151) and RLE (rle.c:48-138) per leaf, RLE keep rule (:1287)
+//   enc_hist_kernel       order-0 histogram; order-1 pair counts over the compacted alphabet
+//                         (utils.h:81-202, + the segment-start counts of :720-723)
+//   enc_table_kernel      normalise_freq (:116-163), compute_shift (:629-691, doubles), table
+//                         serialisation (:182-325), encoder symbol tables (rANS_word.h:190-266),
+//                         optional order-0 compression of the order-1 table (:767-780)
+//   enc_rans_kernel       the reverse rANS loop, lane = state; renormalisation words are placed by
+//                         __ballot_sync / __popc suffix offsets                  (:442-485, :805-839)
+//   enc_finish_kernel     container assembly, CAT fallback (:1332-1337), RLE-meta raw/rANS choice (:1298-1308)
+//   enc_block_kernel      stripe candidate selection (:1192-1208) and block output
+#include <limits.h>
+#include <math.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "encode.h"
+
 namespace hb {
-void EncSlot::release() {}
-int encode_init(int) { return 0; }
-int encode_run(EncSlot&, const EncodeBatch&, const uint32_t*, const int32_t*, cudaStream_t, char* err, size_t errlen) {
-    snprintf(err, errlen, "encode kernels not built yet");
-    return -1;
+
+// ------------------------------------------------------------------------------------------
+// descriptors
+// ------------------------------------------------------------------------------------------
+struct EncSym {            // RansEncSymbol, rANS_word.h:170-181 (16 bytes)
+    uint32_t x_max, rcp_freq, bias, cmpl_shift;   // cmpl_freq | (rcp_shift - 32) << 16
+};
+
+struct EncStream {
+    const uint8_t* src;    // bytes to code (dynamic for transformed leaves)
+    uint32_t n;
+    uint32_t order;        // requested order (0/1)
+    uint32_t nway;         // 4 or 32
+    uint32_t leaf;
+    uint8_t* out;          // [table ... free ... payload written backwards from out + cap]
+    uint32_t cap;          // even
+    uint32_t order_eff;    // order actually used (0 when n is too small, :1322)
+    uint32_t tab_len;      // table bytes at out[0..tab_len)
+    uint32_t pay_off;      // payload = out[pay_off .. cap)
+    uint32_t size;         // tab_len + payload length; 0xffffffff = failed
+    uint32_t ns;           // alphabet size (order-1: including the forced symbol 0)
+    uint32_t shift;        // order-1 table bits (10 / 12)
+    uint32_t* F0;          // 256 x u32: order-0 histogram / presence
+    uint32_t* F1;          // order-1: ns x ns pair counts, then normalised freqs (compact by rank)
+    EncSym* syms;          // order-0: 256 entries; order-1: ns x ns entries (compact)
+    uint8_t* ctab;         // scratch for the order-0 compressed order-1 table
+    uint32_t pad0, pad1;
+};
+
+struct EncLeaf {
+    const uint8_t* src;    // leaf input
+    uint8_t* out;          // assembled container
+    uint8_t* packed;       // PACK scratch (n + 16)
+    uint8_t* lits;         // RLE literal scratch (n + 16)
+    uint8_t* rmeta;        // RLE meta scratch: header grows down from rmeta + 272, runs up from there
+    uint32_t n;
+    uint32_t flags;        // requested flag byte
+    uint32_t blk;
+    uint32_t body;         // stream index
+    uint32_t meta;         // stream index of the RLE meta (or 0xffffffff)
+    uint32_t out_flags;    // flag byte as emitted
+    uint32_t pmeta_len;    // PACK meta bytes ([nsym][symbols])
+    uint32_t packed_len;
+    uint32_t rmeta_len;    // RLE meta length (0 = RLE not used)
+    uint32_t rmeta_off;    // meta starts at rmeta + rmeta_off
+    uint32_t lit_len;
+    uint32_t cur_n;        // bytes handed to the entropy coder
+    uint32_t out_size;     // container size (device result)
+    int32_t status;
+    uint8_t pmeta[20];
+};
+
+struct EncBlock {
+    uint8_t* out;          // block output
+    const uint8_t* in;
+    uint8_t* tr;           // transposed copy (stripe)
+    uint32_t n;
+    uint32_t order;        // as passed by the caller
+    uint32_t cap;
+    uint32_t mode;         // 0 plain leaf, 1 stripe, 2 X_CAT requested, 3 error
+    uint32_t leaf0;        // first leaf
+    uint32_t N, ncand;     // stripe: leaves are [j * ncand + c]
+    uint32_t pad;
+};
+
+struct EncWork {
+    EncLeaf* leaves; EncStream* streams; EncBlock* blocks;
+    uint32_t nleaves, nstreams, nblocks;
+    uint32_t next_stream[2][2];    // persistent-kernel cursors: [nway32][order]
+    uint32_t next_misc[8];
+};
+
+__constant__ double c_log10[257];   // log(1024 + k)  (host libm, see encode_init)
+__constant__ double c_log12[257];   // log(4096 + k)
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pow2_ceil(uint32_t v) {      // round2, :105-114
+    if (v == 0) return 0;
+    uint32_t p = 1;
+    while (p < v && p) p <<= 1;
+    return p;
 }
+
+// normalise_freq, rANS_static4x16pr.c:116-163, on `cnt` entries (absent symbols carry 0 and are
+// skipped exactly like the reference's `if (!F[j]) continue`).  Serial, one thread.
+__device__ int scale_freqs(uint32_t* F, uint32_t cnt, uint32_t total, uint32_t target) {
+    if (!total) return 0;
+    int sum_in = (int)total;
+    uint32_t big_at = 0;
+    for (int attempt = 0;; attempt++) {
+        unsigned long long mul = ((unsigned long long)target << 31) / (unsigned long long)(long long)sum_in +
+                                 (unsigned long long)((1 << 30) / sum_in);
+        uint32_t big = 0;
+        int sum = 0;
+        big_at = 0;
+        for (uint32_t j = 0; j < cnt; j++) {
+            uint32_t f = F[j];
+            if (!f) continue;
+            if (big < f) { big = f; big_at = j; }
+            uint32_t s = (uint32_t)(((unsigned long long)f * mul) >> 31);
+            s = s ? s : 1;
+            F[j] = s;
+            sum += (int)s;
+        }
+        int slack = (int)(target - (uint32_t)sum);
+        if (slack > 0) { F[big_at] += (uint32_t)slack; break; }
+        if (slack == 0) break;
+        uint32_t need = (uint32_t)(-slack);
+        if (F[big_at] > need && (attempt == 1 || F[big_at] / 2 >= need)) { F[big_at] -= need; break; }
+        if (attempt < 1) { sum_in = sum; continue; }
+        slack += (int)F[big_at] - 1;
+        F[big_at] = 1;
+        for (uint32_t j = 0; slack && j < cnt; j++) {
+            if (F[j] < 2) continue;
+            int take = (F[j] > (uint32_t)(-slack)) ? slack : 1 - (int)F[j];
+            F[j] = (uint32_t)((int)F[j] + take);
+            slack -= take;
+        }
+        break;
+    }
+    return F[big_at] > 0 ? 0 : -1;
+}
+
+// RansEncSymbolInit, rANS_word.h:190-266
+__device__ __forceinline__ EncSym make_sym(uint32_t start, uint32_t freq, uint32_t bits) {
+    EncSym s;
+    s.x_max = (((1u << 15) >> bits) << 16) * freq;
+    uint32_t cmpl = ((1u << bits) - freq) & 0xffffu;
+    if (freq < 2) {
+        s.rcp_freq = ~0u;
+        s.bias = start + (1u << bits) - 1;
+        s.cmpl_shift = cmpl;                            // shift 0
+    } else {
+        uint32_t sh = 0;
+        while (freq > (1u << sh)) sh++;
+        s.rcp_freq = (uint32_t)(((1ull << (sh + 31)) + freq - 1) / freq);
+        s.bias = start;
+        s.cmpl_shift = cmpl | ((sh - 1) << 16);
+    }
+    return s;
+}
+
+// encode_alphabet, :182-206.  `present(j)` tells whether symbol j is in the alphabet.
+template <typename P>
+__device__ uint32_t put_alphabet(uint8_t* p, P present) {
+    uint8_t* p0 = p;
+    int implied = 0;
+    for (int j = 0; j < 256; j++) {
+        if (!present(j)) continue;
+        if (implied) { implied--; continue; }
+        *p++ = (uint8_t)j;
+        if (j && present(j - 1)) {
+            int e = j + 1;
+            while (e < 256 && present(e)) e++;
+            implied = e - (j + 1);
+            *p++ = (uint8_t)implied;
+        }
+    }
+    *p++ = 0;
+    return (uint32_t)(p - p0);
+}
+
+// ------------------------------------------------------------------------------------------
+// enc_stripe_kernel: transposed[at[j] + x] = in[x*N + j]   (:1168-1180)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) enc_stripe_kernel(EncWork* W) {
+    __shared__ uint32_t at[256];
+    for (uint32_t b = blockIdx.x; b < W->nblocks; b += gridDim.x) {
+        const EncBlock B = W->blocks[b];
+        if (B.mode != 1) continue;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t a = 0;
+            for (uint32_t j = 0; j < B.N; j++) { at[j] = a; a += B.n / B.N + ((B.n % B.N) > j); }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < B.n; i += blockDim.x) B.tr[at[i % B.N] + i / B.N] = B.in[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// enc_transform_kernel: PACK then RLE for one leaf per CTA
+// ------------------------------------------------------------------------------------------
+constexpr int TT = 256;
+
+template <typename T>
+__device__ __forceinline__ T cta_exscan(T v, T* warp_tot, T* total) {
+    uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    T x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { T y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    T pre = 0, tot = 0;
+    for (int k = 0; k < TT / 32; k++) { T t = warp_tot[k]; if (k < (int)w) pre += t; tot += t; }
+    __syncthreads();
+    *total = tot;
+    return pre + x - v;
+}
+// inclusive max-scan of int32 over the CTA
+__device__ __forceinline__ int cta_incl_maxscan(int v, int* warp_tot) {
+    uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x = max(x, y); }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    int pre = INT_MIN;
+    for (int k = 0; k < (int)w; k++) pre = max(pre, warp_tot[k]);
+    __syncthreads();
+    return max(pre, x);
+}
+
+__global__ void __launch_bounds__(TT) enc_transform_kernel(EncWork* W) {
+    __shared__ uint32_t seen[256];
+    __shared__ int code[256];
+    __shared__ int score[256];
+    __shared__ uint32_t wtot[TT / 32];
+    __shared__ int wmax[TT / 32];
+    __shared__ uint32_t s_n, s_cnt;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t li = blockIdx.x; li < W->nleaves; li += gridDim.x) {
+        EncLeaf& L = W->leaves[li];
+        if (!(L.flags & (F_PACK | F_RLE))) continue;
+        __syncthreads();
+        const uint8_t* cur = L.src;
+        uint32_t cur_n = L.n;
+        uint32_t out_flags = L.flags;
+
+        // ---------------- PACK, pack.c:56-151 + :1244-1267
+        if (L.flags & F_PACK) {
+            if (cur_n == 0) out_flags &= ~F_PACK;                    // :1265-1267
+            else {
+                seen[tid] = 0;
+                __syncthreads();
+                for (uint32_t i = tid; i < cur_n; i += TT) seen[cur[i]] = 1;
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t ns = 0;
+                    for (int s = 0; s < 256; s++) if (seen[s]) { code[s] = (int)ns; if (ns < 16) L.pmeta[1 + ns] = (uint8_t)s; ns++; }
+                    L.pmeta[0] = (uint8_t)ns;                        // 256 wraps to 0
+                    s_cnt = ns;
+                }
+                __syncthreads();
+                const uint32_t ns = s_cnt;
+                if (ns > 16 && ns != 256) {
+                    out_flags &= ~F_PACK;                            // :1249-1253
+                } else if (ns == 256) {                              // the wrap quirk: PACK kept, data copied, 1-byte meta
+                    for (uint32_t i = tid; i < cur_n; i += TT) L.packed[i] = cur[i];
+                    if (tid == 0) { L.pmeta_len = 1; L.packed_len = cur_n; }
+                    cur = L.packed;
+                } else {
+                    const uint32_t per = ns > 4 ? 2 : ns > 2 ? 4 : ns > 1 ? 8 : 0;
+                    uint32_t plen = 0;
+                    if (per) {
+                        const uint32_t bits = 8 / per;
+                        plen = (cur_n + per - 1) / per;
+                        for (uint32_t o = tid; o < plen; o += TT) {
+                            uint32_t v = 0;
+                            for (uint32_t k = 0; k < per && o * per + k < cur_n; k++) v |= (uint32_t)code[cur[o * per + k]] << (k * bits);
+                            L.packed[o] = (uint8_t)v;
+                        }
+                    }
+                    if (tid == 0) { L.pmeta_len = ns + 1; L.packed_len = plen; }
+                    cur = L.packed; cur_n = plen;
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---------------- RLE, rle.c:48-138 + :1269-1319
+        uint32_t rmeta_len = 0;
+        if (L.flags & F_RLE) {
+            if (cur_n == 0) out_flags &= ~F_RLE;                     // :1317-1319
+            else {
+                score[tid] = 0;
+                __syncthreads();
+                // rle_find_syms: +1 when a byte repeats its predecessor, -1 otherwise
+                for (uint32_t i = tid; i < cur_n; i += TT) {
+                    uint32_t b = cur[i];
+                    atomicAdd(&score[b], (i > 0 && cur[i - 1] == b) ? 1 : -1);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t nrs = 0;
+                    uint8_t* hdr = L.rmeta + 272;
+                    for (int s = 0; s < 256; s++) if (score[s] > 0) nrs++;
+                    uint8_t* m = hdr - 1 - nrs;
+                    m[0] = (uint8_t)nrs;
+                    uint32_t k = 0;
+                    for (int s = 0; s < 256; s++) if (score[s] > 0) m[1 + k++] = (uint8_t)s;
+                    s_cnt = nrs;
+                }
+                __syncthreads();
+                const uint32_t nrs = s_cnt;
+                uint8_t* runs = L.rmeta + 272;
+                // A byte starts a literal unless it continues a run of an RLE symbol.  A run's varint
+                // is emitted at the run's LAST byte (varints appear in literal order either way).
+                uint32_t lit_base = 0, run_base = 0;
+                int start_carry = -1;
+                for (uint32_t t0 = 0; t0 < cur_n; t0 += TT) {
+                    const uint32_t i = t0 + tid;
+                    uint32_t b = 0, isr = 0, is_start = 0, is_end = 0;
+                    if (i < cur_n) {
+                        b = cur[i];
+                        isr = score[b] > 0;
+                        is_start = !(isr && i > 0 && cur[i - 1] == b);
+                        is_end = isr && (i + 1 == cur_n || cur[i + 1] != b);
+                    }
+                    uint32_t tot;
+                    uint32_t lidx = cta_exscan<uint32_t>(is_start, wtot, &tot);
+                    int sp = cta_incl_maxscan(is_start ? (int)i : -1, wmax);
+                    sp = max(sp, start_carry);
+                    if (is_start) L.lits[lit_base + lidx] = (uint8_t)b;
+                    uint32_t vlen = 0, rl = 0;
+                    if (is_end) { rl = i - (uint32_t)sp; vlen = (uint32_t)var_len_u32(rl); }
+                    uint32_t vtot;
+                    uint32_t voff = cta_exscan<uint32_t>(vlen, wtot, &vtot);
+                    if (is_end) var_put_u32(runs + run_base + voff, rl);
+                    lit_base += tot;
+                    run_base += vtot;
+                    // carry the most recent literal start into the next tile
+                    if (tid == TT - 1) wmax[0] = sp;
+                    __syncthreads();
+                    start_carry = wmax[0];
+                    __syncthreads();
+                }
+                rmeta_len = 1 + nrs + run_base;
+                const uint32_t lit_len = lit_base;
+                if ((double)((unsigned long long)lit_len + rmeta_len) >= .99 * (double)cur_n) {   // :1287
+                    out_flags &= ~F_RLE;
+                    rmeta_len = 0;
+                } else {
+                    if (tid == 0) { L.rmeta_off = 272 - 1 - nrs; L.lit_len = lit_len; }
+                    cur = L.lits; cur_n = lit_len;
+                }
+            }
+        }
+        if (tid == 0) {
+            L.out_flags = out_flags;
+            L.rmeta_len = rmeta_len;
+            L.cur_n = cur_n;
+            EncStream& S = W->streams[L.body];
+            S.src = cur; S.n = cur_n;
+            if (L.meta != 0xffffffffu) {
+                EncStream& M = W->streams[L.meta];
+                M.src = L.rmeta + (rmeta_len ? L.rmeta_off : 0u);
+                M.n = rmeta_len;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// enc_hist_kernel: one CTA per stream
+// ------------------------------------------------------------------------------------------
+constexpr int HT = 256;
+constexpr uint32_t O1_SMEM_NS = 96;      // pair counts in shared memory up to this alphabet size (36 KB)
+
+__global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
+    __shared__ uint32_t h[256];
+    __shared__ uint8_t rank[256];
+    __shared__ uint32_t pair[O1_SMEM_NS * O1_SMEM_NS];
+    __shared__ uint32_t s_ns;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t si = blockIdx.x; si < W->nstreams; si += gridDim.x) {
+        EncStream& S = W->streams[si];
+        __syncthreads();
+        const uint8_t* in = S.src;
+        const uint32_t n = S.n, nway = S.nway;
+        uint32_t order = S.order;
+        if (order && (n < 8 || n < nway)) order = 0;                 // :1322-1325 (+ N-way analogue)
+        h[tid] = 0;
+        __syncthreads();
+        // hist8, utils.h:81-102: 16 bytes per thread per step, warp-aggregated by value runs
+        {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(in);
+            const uint32_t head = min(n, (uint32_t)((16 - (a & 15)) & 15));
+            for (uint32_t i = tid; i < head; i += HT) atomicAdd(&h[in[i]], 1u);
+            const uint32_t nv = (n - head) / 16;
+            const uint4* v = reinterpret_cast<const uint4*>(in + head);
+            for (uint32_t i = tid; i < nv; i += HT) {
+                uint4 q = v[i];
+                uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    atomicAdd(&h[w[k] & 0xff], 1u); atomicAdd(&h[(w[k] >> 8) & 0xff], 1u);
+                    atomicAdd(&h[(w[k] >> 16) & 0xff], 1u); atomicAdd(&h[w[k] >> 24], 1u);
+                }
+            }
+            for (uint32_t i = head + nv * 16 + tid; i < n; i += HT) atomicAdd(&h[in[i]], 1u);
+        }
+        __syncthreads();
+        S.F0[tid] = h[tid];
+        if (tid == 0) { S.order_eff = order; S.size = 0; S.tab_len = 0; S.pay_off = S.cap; }
+        if (!order || n == 0) continue;
+
+        // ---- order 1: alphabet = present symbols + symbol 0 (:729-731); ranks; pair counts
+        if (tid == 0) {
+            uint32_t ns = 0;
+            for (int s = 0; s < 256; s++) {
+                bool p = h[s] != 0 || s == 0;
+                rank[s] = (uint8_t)ns;
+                if (p) ns++;
+            }
+            s_ns = ns;
+            S.ns = ns;
+        }
+        __syncthreads();
+        const uint32_t ns = s_ns;
+        const bool in_smem = ns <= O1_SMEM_NS;
+        uint32_t* P = in_smem ? pair : S.F1;
+        for (uint32_t k = tid; k < ns * ns; k += HT) P[k] = 0;
+        __syncthreads();
+        // hist1_4, utils.h:137-202: every adjacent pair of the whole buffer, first context 0
+        for (uint32_t i = tid; i < n; i += HT) {
+            uint32_t c = i ? in[i - 1] : 0u, s = in[i];
+            atomicAdd(&P[rank[c] * ns + rank[s]], 1u);
+        }
+        // the segment starts are coded in context 0 (:720-723, with 4 -> nway)
+        const uint32_t seg = n / nway;
+        for (uint32_t k = 1 + tid; k < nway; k += HT) atomicAdd(&P[rank[0] * ns + rank[in[k * seg]]], 1u);
+        __syncthreads();
+        if (in_smem) for (uint32_t k = tid; k < ns * ns; k += HT) S.F1[k] = pair[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// enc_table_kernel: one CTA (128 threads) per stream
+// ------------------------------------------------------------------------------------------
+constexpr int KT = 128;
+
+// rans_compress_O0_4x16's table half (:408-435) for `n` symbols with histogram F (256 entries,
+// modified in place).  Writes the table to `tab`, the encoder symbols to `syms`; one thread.
+__device__ int build_o0_tables_enc(uint32_t* F, uint32_t n, uint8_t* tab, EncSym* syms, uint32_t* tab_len) {
+    uint32_t target = pow2_ceil(n);
+    if (target > 4096) target = 4096;
+    if (scale_freqs(F, 256, n, target) < 0) return -1;
+    uint8_t* p = tab;
+    p += put_alphabet(p, [&](int j) { return F[j] != 0; });
+    for (int j = 0; j < 256; j++) if (F[j]) p += var_put_u32(p, F[j]);
+    *tab_len = (uint32_t)(p - tab);
+    if (scale_freqs(F, 256, target, 4096) < 0) return -1;
+    uint32_t x = 0;
+    for (int j = 0; j < 256; j++) {
+        if (F[j]) { syms[j] = make_sym(x, F[j], 12); x += F[j]; }
+    }
+    return 0;
+}
+
+// One-thread rANS 4x16 order-0 encode of a short buffer (the order-1 table, :767-780).
+// F/syms are scratch (256 entries each); returns the stream length written to out, or 0.
+__device__ uint32_t nested_o0_encode(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, uint32_t* F, EncSym* syms) {
+    for (int j = 0; j < 256; j++) F[j] = 0;
+    for (uint32_t i = 0; i < n; i++) F[in[i]]++;
+    uint32_t tab = 0;
+    if (build_o0_tables_enc(F, n, out, syms, &tab) < 0) return 0;
+    uint8_t* end = out + (cap & ~1u);
+    uint8_t* p = end;
+    uint32_t R[4] = {1u << 15, 1u << 15, 1u << 15, 1u << 15};
+    for (uint32_t i = n; i-- > 0;) {
+        const EncSym s = syms[in[i]];
+        uint32_t x = R[i & 3];
+        if (x >= s.x_max) { p -= 2; p[0] = (uint8_t)x; p[1] = (uint8_t)(x >> 8); x >>= 16; }
+        uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift >> 16);
+        R[i & 3] = x + s.bias + q * (s.cmpl_shift & 0xffffu);
+    }
+    for (int z = 3; z >= 0; z--) { p -= 4; p[0] = (uint8_t)R[z]; p[1] = (uint8_t)(R[z] >> 8); p[2] = (uint8_t)(R[z] >> 16); p[3] = (uint8_t)(R[z] >> 24); }
+    uint32_t body = (uint32_t)(end - p);
+    for (uint32_t i = 0; i < body; i++) out[tab + i] = p[i];       // moves down, ascending copy is safe
+    return tab + body;
+}
+
+__device__ __forceinline__ double approx_log(int x) {              // fast_log, :620-623
+    double a = (double)x;
+    long long bits = __double_as_longlong(a);
+    return __dmul_rn(__ll2double_rn(bits - 4606921278410026770LL), 1.539095918623324e-16);
+}
+
+__global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
+    __shared__ uint32_t Fs[256];
+    __shared__ uint8_t unrank[256];
+    __shared__ int Sv[256];
+    __shared__ uint32_t Tv[256];
+    __shared__ uint32_t rowlen[256], rowoff[256];
+    __shared__ uint32_t s_shift, s_fail, s_alpha_len;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t si = blockIdx.x; si < W->nstreams; si += gridDim.x) {
+        EncStream& S = W->streams[si];
+        __syncthreads();
+        const uint32_t n = S.n;
+        if (n == 0) { if (tid == 0) { S.size = 0; S.tab_len = 0; } continue; }     // :405-406
+        if (S.order_eff == 0) {
+            if (tid == 0) {
+                uint32_t tab = 0;
+                for (int j = 0; j < 256; j++) Fs[j] = S.F0[j];
+                if (build_o0_tables_enc(Fs, n, S.out, S.syms, &tab) < 0) S.size = 0xffffffffu;
+                S.tab_len = tab;
+            }
+            continue;
+        }
+        // ================= order 1, :719-780 =================
+        const uint32_t ns = S.ns;
+        uint32_t* F1 = S.F1;
+        if (tid == 0) {
+            uint32_t r = 0;
+            for (int s = 0; s < 256; s++) if (S.F0[s] != 0 || s == 0) unrank[r++] = (uint8_t)s;
+            s_fail = 0;
+        }
+        __syncthreads();
+        // row totals T[i] (utils.h T0[] + the nway-1 segment starts)
+        for (uint32_t i = tid; i < ns; i += KT) {
+            uint32_t t = 0;
+            for (uint32_t j = 0; j < ns; j++) t += F1[i * ns + j];
+            Tv[i] = t;
+        }
+        __syncthreads();
+        // compute_shift, :629-691: ONE thread, reference accumulation order, no fused multiply-add
+        if (tid == 0) {
+            double e10 = 0, e12 = 0;
+            int max_tot = 0;
+            for (uint32_t i = 0; i < ns; i++) {
+                const uint32_t T = Tv[i];
+                int max_val = (int)pow2_ceil(T);
+                int nsym = 0, sm10 = 0, sm12 = 0;
+                for (uint32_t j = 0; j < ns; j++) {
+                    uint32_t f = F1[i * ns + j];
+                    if (f && (uint32_t)max_val / f > 1024) sm10++;
+                    if (f && (uint32_t)max_val / f > 4096) sm12++;
+                }
+                const double l10 = c_log10[sm10], l12 = c_log12[sm12];
+                const double Td = (double)T;
+                for (uint32_t j = 0; j < ns; j++) {
+                    uint32_t f = F1[i * ns + j];
+                    if (!f) continue;
+                    nsym++;
+                    const double fd = (double)f;
+                    int x = __double2int_rz(__ddiv_rn(__dmul_rn(1024.0, fd), Td));
+                    e10 = __dsub_rn(e10, __dmul_rn(fd, __dsub_rn(approx_log(x > 1 ? x : 1), l10)));
+                    x = __double2int_rz(__ddiv_rn(__dmul_rn(4096.0, fd), Td));
+                    e12 = __dsub_rn(e12, __dmul_rn(fd, __dsub_rn(approx_log(x > 1 ? x : 1), l12)));
+                    e10 = __dadd_rn(e10, 4.0);
+                    e12 = __dadd_rn(e12, 6.0);
+                }
+                if (nsym < 64 && max_val > 128) max_val /= 2;
+                if (max_val > 1024) max_val /= 2;
+                if (max_val > 4096) max_val = 4096;
+                Sv[i] = max_val;
+                if (max_tot < max_val) max_tot = max_val;
+            }
+            s_shift = (__ddiv_rn(e10, e12) < 1.01 || max_tot <= 1024) ? 10u : 12u;
+        }
+        __syncthreads();
+        const uint32_t shift = s_shift;
+        // normalise each row (:740-752), measure its serialised length (encode_freq_d :295-325)
+        for (uint32_t i = tid; i < ns; i += KT) {
+            uint32_t target = (uint32_t)Sv[i];
+            if (shift == 10 && target > 1024) target = 1024;
+            uint32_t* row = F1 + i * ns;
+            if (scale_freqs(row, ns, Tv[i], target) < 0) s_fail = 1;
+            Tv[i] = target;
+            uint32_t len = 0, z = 0;
+            for (uint32_t j = 0; j < ns; j++) {
+                if (row[j]) { if (z) { len += 2; z = 0; } len += (uint32_t)var_len_u32(row[j]); }
+                else z++;
+            }
+            if (z) len += 2;
+            rowlen[i] = len;
+        }
+        __syncthreads();
+        uint8_t* tab = S.out;
+        if (tid == 0) {
+            tab[0] = (uint8_t)(shift << 4);
+            uint32_t al = put_alphabet(tab + 1, [&](int j) { return S.F0[j] != 0 || j == 0; });
+            s_alpha_len = al;
+            uint32_t o = 1 + al;
+            for (uint32_t i = 0; i < ns; i++) { rowoff[i] = o; o += rowlen[i]; }
+            S.tab_len = o;
+            S.shift = shift;
+        }
+        __syncthreads();
+        // write the rows, shift them up to 1<<shift (:756), build the encoder symbols (:758-762)
+        for (uint32_t i = tid; i < ns; i += KT) {
+            uint32_t* row = F1 + i * ns;
+            uint8_t* p = tab + rowoff[i];
+            uint32_t z = 0;
+            for (uint32_t j = 0; j < ns; j++) {
+                if (row[j]) {
+                    if (z) { *p++ = 0; *p++ = (uint8_t)(z - 1); z = 0; }
+                    p += var_put_u32(p, row[j]);
+                } else z++;
+            }
+            if (z) { *p++ = 0; *p++ = (uint8_t)(z - 1); }
+            uint32_t sh = 0, t = Tv[i];
+            if (t != 0 && t != (1u << shift)) while ((t << sh) < (1u << shift)) sh++;
+            uint32_t x = 0;
+            EncSym* srow = S.syms + (size_t)i * ns;
+            for (uint32_t j = 0; j < ns; j++) {
+                uint32_t f = row[j] << sh;
+                srow[j] = make_sym(x, f, shift);
+                x += f;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (s_fail) S.size = 0xffffffffu;
+            else if (S.tab_len > 1000) {                             // :767-780
+                const uint32_t usz = S.tab_len - 1;
+                // scratch F / syms for the nested coder live behind the compressed bytes
+                const uint32_t ccap = ((usz + usz / 16 + 1024) & ~15u);
+                uint32_t* F = reinterpret_cast<uint32_t*>(S.ctab + ccap);
+                EncSym* ns_syms = reinterpret_cast<EncSym*>(S.ctab + ccap + 1024);
+                uint32_t csz = nested_o0_encode(tab + 1, usz, S.ctab, ccap, F, ns_syms);
+                if (csz && csz + 6 < S.tab_len) {
+                    uint8_t* op = tab;
+                    *op++ |= 1;
+                    op += var_put_u32(op, usz);
+                    op += var_put_u32(op, csz);
+                    for (uint32_t k = 0; k < csz; k++) op[k] = S.ctab[k];
+                    S.tab_len = (uint32_t)(op - tab) + csz;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// enc_rans_kernel: persistent, one warp per CTA, a group of NWAY lanes per stream
+// ------------------------------------------------------------------------------------------
+template <int NWAY> struct EGrp {
+    static constexpr int G = 32 / NWAY;
+    static constexpr uint32_t GM = (NWAY == 32) ? 0xffffffffu : ((1u << NWAY) - 1u);
+    uint32_t g, glane, gshift, gmask;
+    __device__ __forceinline__ EGrp() {
+        uint32_t lane = lane_id();
+        g = lane / NWAY; glane = lane % NWAY; gshift = g * NWAY; gmask = GM << gshift;
+    }
+};
+
+// RansEncPutSymbol (rANS_word.h:281-321) for all lanes of the warp at once.  `wp` is the group's
+// write pointer (moves down); emitting lanes store their low 16 bits in descending lane order.
+template <int NWAY>
+__device__ __forceinline__ uint32_t enc_put(uint32_t x, bool act, const EncSym s, uint8_t*& wp, const EGrp<NWAY>& G) {
+    const bool emit = act && x >= s.x_max;
+    const uint32_t m = (__ballot_sync(0xffffffffu, emit) >> G.gshift) & EGrp<NWAY>::GM;
+    if (emit) {
+        const uint32_t above = __popc((m >> G.glane) >> 1);          // emitting lanes with a higher index write first
+        uint8_t* p = wp - 2 * (above + 1);
+        *reinterpret_cast<uint16_t*>(p) = (uint16_t)x;
+        x >>= 16;
+    }
+    wp -= 2 * __popc(m);
+    if (act) {
+        const uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift >> 16);
+        x = x + s.bias + q * (s.cmpl_shift & 0xffffu);
+    }
+    return x;
+}
+
+constexpr int ENC_O0_SMEM_PER_GROUP = 256 * 16;                      // EncSym[256]
+constexpr uint32_t ENC_O1_SMEM_NS_32 = 48;                           // order-1 symbols in shared memory up to this ns (36 KB)
+constexpr uint32_t ENC_O1_SMEM_NS_4 = 16;                            // per 4-lane group (4 KB)
+
+template <int NWAY, int ORDER>
+__global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W) {
+    using EG = EGrp<NWAY>;
+    extern __shared__ __align__(16) uint8_t esm[];
+    const EG G;
+    constexpr uint32_t SMEM_NS = (NWAY == 32) ? ENC_O1_SMEM_NS_32 : ENC_O1_SMEM_NS_4;
+    constexpr uint32_t PER_GROUP = ORDER ? (SMEM_NS * SMEM_NS * 16 + 256) : ENC_O0_SMEM_PER_GROUP;
+    uint8_t* gsm = esm + G.g * PER_GROUP;
+    EncSym* ssym = reinterpret_cast<EncSym*>(gsm);
+    uint8_t* srank = gsm + SMEM_NS * SMEM_NS * 16;                  // order-1 only
+    uint32_t* cursor = &W->next_stream[NWAY == 32][ORDER];
+    const uint32_t nstreams = W->nstreams;
+
+    for (;;) {
+        // streams are claimed EG::G at a time; those of another nway/order are skipped by predicate
+        uint32_t s0 = 0;
+        if (lane_id() == 0) s0 = atomicAdd(cursor, (uint32_t)EG::G);
+        s0 = __shfl_sync(0xffffffffu, s0, 0);
+        if (s0 >= nstreams) break;
+        const uint32_t si = s0 + G.g;
+        bool act_s = si < nstreams;
+        EncStream* S = act_s ? &W->streams[si] : nullptr;
+        if (act_s && (S->nway != NWAY || S->order_eff != ORDER || S->n == 0 || S->size == 0xffffffffu)) act_s = false;
+        if (!__any_sync(0xffffffffu, act_s)) continue;
+
+        const uint8_t* in = act_s ? S->src : nullptr;
+        const uint32_t n = act_s ? S->n : 0;
+        uint32_t ns = 1;
+        const EncSym* syms = ssym;
+        if (ORDER == 0) {
+            if (act_s) for (uint32_t k = G.glane; k < 256; k += NWAY) ssym[k] = S->syms[k];
+        } else if (act_s) {
+            ns = S->ns;
+            // symbol -> rank
+            uint32_t r = 0;
+            if (G.glane == 0) for (int s = 0; s < 256; s++) { srank[s] = (uint8_t)r; if (S->F0[s] != 0 || s == 0) r++; }
+            if (ns <= SMEM_NS) for (uint32_t k = G.glane; k < ns * ns; k += NWAY) ssym[k] = S->syms[k];
+            else syms = S->syms;
+        }
+        __syncwarp();
+
+        uint8_t* wp = act_s ? S->out + S->cap : nullptr;             // payload grows down from the end
+        uint32_t x = 1u << 15;                                       // RansEncInit, rANS_word.h:69-72
+        if (ORDER == 0) {
+            // symbol i belongs to state i % NWAY; rows are coded from the last to the first (:442-480)
+            const uint32_t rows = (n + NWAY - 1) / NWAY;
+            const uint32_t maxrows = (NWAY == 32) ? rows : __reduce_max_sync(0xffffffffu, rows);
+            for (uint32_t k = 0; k < maxrows; k++) {
+                const bool in_rows = k < rows;
+                const uint32_t pos = in_rows ? (rows - 1 - k) * NWAY + G.glane : 0;
+                const bool act = in_rows && pos < n;
+                EncSym s = ssym[act ? in[pos] : 0];
+                x = enc_put<NWAY>(x, act, s, wp, G);
+            }
+        } else {
+            // state z owns in[z*seg, (z+1)*seg), the last state also the tail; coded last-to-first
+            // with the preceding byte as context, 0 at a segment start (:794-834)
+            const uint32_t seg = n / NWAY, tail = n - seg * NWAY;
+            const uint32_t steps = act_s ? seg + tail : 0;
+            const uint32_t maxsteps = __reduce_max_sync(0xffffffffu, steps);
+            const uint32_t skip = maxsteps - steps;                  // groups with fewer steps idle first
+            const uint32_t base = G.glane * seg;
+            for (uint32_t k = 0; k < maxsteps; k++) {
+                bool act = false;
+                uint32_t c = 0, sy = 0;
+                if (act_s && k >= skip) {
+                    const uint32_t kk = k - skip;                    // 0 .. steps-1
+                    if (kk < tail) {                                 // tail symbols, last lane only
+                        if (G.glane == NWAY - 1) { uint32_t pos = n - 1 - kk; act = true; sy = in[pos]; c = in[pos - 1]; }
+                    } else {
+                        uint32_t t = seg - 1 - (kk - tail);          // seg-1 .. 0
+                        uint32_t pos = base + t;
+                        act = true; sy = in[pos]; c = t ? in[pos - 1] : 0u;
+                    }
+                }
+                EncSym s;
+                s.x_max = 0xffffffffu; s.rcp_freq = 0; s.bias = 0; s.cmpl_shift = 0;
+                if (act) s = syms[(uint32_t)srank[c] * ns + srank[sy]];
+                x = enc_put<NWAY>(x, act, s, wp, G);
+            }
+        }
+        // RansEncFlush (rANS_word.h:104-116): states NWAY-1 .. 0, so state 0 ends lowest
+        if (act_s) {
+            uint8_t* p = wp - 4 * (NWAY - G.glane);
+            p[0] = (uint8_t)x; p[1] = (uint8_t)(x >> 8); p[2] = (uint8_t)(x >> 16); p[3] = (uint8_t)(x >> 24);
+            if (G.glane == 0) {
+                uint32_t pay_off = (uint32_t)(wp - 4 * NWAY - S->out);
+                S->pay_off = pay_off;
+                S->size = S->tab_len + (S->cap - pay_off);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// enc_finish_kernel: one CTA per leaf -- assemble the container (:1231-1342)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint32_t n) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) enc_finish_kernel(EncWork* W) {
+    __shared__ uint32_t s_hdr, s_fail, s_cat;
+    for (uint32_t li = blockIdx.x; li < W->nleaves; li += gridDim.x) {
+        EncLeaf& L = W->leaves[li];
+        __syncthreads();
+        const EncStream& B = W->streams[L.body];
+        uint8_t* out = L.out;
+        if (threadIdx.x == 0) {
+            uint32_t flags = L.out_flags;
+            uint32_t hdr = 1;
+            s_fail = 0;
+            if (!(L.flags & F_NOSZ)) hdr += var_put_u32(out + hdr, L.n);                     // :1234
+            if (flags & F_PACK) {                                                              // :1257-1262
+                for (uint32_t k = 0; k < L.pmeta_len; k++) out[hdr + k] = L.pmeta[k];
+                hdr += L.pmeta_len;
+                hdr += var_put_u32(out + hdr, L.packed_len);
+            }
+            if (flags & F_RLE) {                                                               // :1295-1310
+                const EncStream& M = W->streams[L.meta];
+                if (M.size == 0xffffffffu) s_fail = 1;
+                if (M.size < L.rmeta_len) {
+                    hdr += var_put_u32(out + hdr, L.rmeta_len * 2);
+                    hdr += var_put_u32(out + hdr, L.lit_len);
+                    hdr += var_put_u32(out + hdr, M.size);
+                } else {
+                    hdr += var_put_u32(out + hdr, L.rmeta_len * 2 + 1);
+                    hdr += var_put_u32(out + hdr, L.lit_len);
+                }
+            }
+            if (B.order_eff == 0) flags &= ~1u;                                                // :1322-1325
+            if (B.size == 0xffffffffu) s_fail = 1;
+            const uint32_t cur_n = L.cur_n;
+            s_cat = B.size >= cur_n;                                                           // :1332
+            if (s_cat) flags = (flags & ~3u) | F_CAT | (L.flags & F_NOSZ);
+            out[0] = (uint8_t)flags;
+            s_hdr = hdr;
+        }
+        __syncthreads();
+        uint32_t hdr = s_hdr;
+        const uint32_t flags = out[0];
+        if (flags & F_RLE) {
+            const EncStream& M = W->streams[L.meta];
+            if (M.size < L.rmeta_len) {
+                cta_copy(out + hdr, M.out, M.tab_len);
+                cta_copy(out + hdr + M.tab_len, M.out + M.pay_off, M.cap - M.pay_off);
+                hdr += M.size;
+            } else {
+                cta_copy(out + hdr, L.rmeta + L.rmeta_off, L.rmeta_len);
+                hdr += L.rmeta_len;
+            }
+        }
+        const uint32_t cur_n = L.cur_n;
+        uint32_t body;
+        if (s_cat) { cta_copy(out + hdr, B.src, cur_n); body = cur_n; }
+        else {
+            cta_copy(out + hdr, B.out, B.tab_len);
+            cta_copy(out + hdr + B.tab_len, B.out + B.pay_off, B.cap - B.pay_off);
+            body = B.size;
+        }
+        if (threadIdx.x == 0) { L.out_size = hdr + body; L.status = s_fail ? ST_INTERNAL : ST_OK; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// enc_block_kernel: one CTA per block -- stripe winner selection / X_CAT / result reporting
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) enc_block_kernel(EncWork* W, uint32_t* out_len, int32_t* status) {
+    __shared__ uint32_t win[256], woff[256];
+    __shared__ uint32_t s_hdr;
+    __shared__ int s_st;
+    for (uint32_t b = blockIdx.x; b < W->nblocks; b += gridDim.x) {
+        const EncBlock B = W->blocks[b];
+        __syncthreads();
+        if (B.mode == 3) { if (threadIdx.x == 0) { status[b] = ST_SIZE; out_len[b] = 0; } continue; }
+        if (B.mode == 2) {                                                                     // :1218-1225
+            if (threadIdx.x == 0) { B.out[0] = F_CAT; s_hdr = 1 + var_put_u32(B.out + 1, B.n); }
+            __syncthreads();
+            cta_copy(B.out + s_hdr, B.in, B.n);
+            if (threadIdx.x == 0) { out_len[b] = s_hdr + B.n; status[b] = ST_OK; }
+            continue;
+        }
+        if (B.mode == 0) {
+            if (threadIdx.x == 0) { const EncLeaf& L = W->leaves[B.leaf0]; out_len[b] = L.out_size; status[b] = L.status; }
+            continue;
+        }
+        // stripe, :1182-1215
+        if (threadIdx.x == 0) {
+            uint32_t hdr = 1;
+            int st = ST_OK;
+            B.out[0] = (uint8_t)(B.order & ~F_NOSZ);
+            hdr += var_put_u32(B.out + hdr, B.n);
+            B.out[hdr++] = (uint8_t)B.N;
+            uint32_t pay = 0;
+            for (uint32_t j = 0; j < B.N; j++) {
+                uint32_t best = B.n + 10, bi = 0;                    // strict '<' : the first smallest wins
+                for (uint32_t c = 0; c < B.ncand; c++) {
+                    const EncLeaf& L = W->leaves[B.leaf0 + j * B.ncand + c];
+                    if (L.status != ST_OK) st = L.status;
+                    if (best > L.out_size) { best = L.out_size; bi = c; }
+                }
+                win[j] = B.leaf0 + j * B.ncand + bi;
+                woff[j] = pay;
+                pay += best;
+                hdr += var_put_u32(B.out + hdr, best);
+            }
+            s_hdr = hdr; s_st = st;
+            out_len[b] = hdr + pay;
+            status[b] = st;
+        }
+        __syncthreads();
+        for (uint32_t j = 0; j < B.N; j++) {
+            const EncLeaf& L = W->leaves[win[j]];
+            cta_copy(B.out + s_hdr + woff[j], L.out, L.out_size);
+        }
+    }
+}
+
+// Patches the pointers that depend on the caller's device-resident offset arrays.
+__global__ void enc_fix_kernel(EncWork* W, const uint8_t* in_base, const uint64_t* in_off, uint8_t* out_base,
+                               const uint64_t* out_off) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= W->nblocks) return;
+    EncBlock& B = W->blocks[b];
+    B.in = in_base + in_off[b];
+    B.out = out_base + out_off[b];
+    if (B.mode == 0) {
+        EncLeaf& L = W->leaves[B.leaf0];
+        L.src = B.in; L.out = B.out;
+        W->streams[L.body].src = B.in;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct EncImpl {
+    uint8_t* d_scratch = nullptr; size_t scratch_cap = 0;
+    uint8_t* d_desc = nullptr; size_t desc_cap = 0;
+    uint8_t* h_desc = nullptr; size_t h_desc_cap = 0;          // pinned
+    cudaEvent_t uploaded = nullptr;
+    bool pending = false;
+    std::vector<uint32_t> h_len;
+    std::vector<int32_t> h_order;
+};
+
+int g_sms_enc = 0;
+int g_grid_enc[2][2];
+
+unsigned int host_bound(unsigned int size, int order) {        // rans_compress_bound_4x16, :360-372
+    int N = order >> 8;
+    if (!N) N = 4;
+    order &= 0xff;
+    double d = 1.05 * size;
+    d += (order == 0) ? (257 * 3 + 4) : (257 * 257 * 3 + 4 + 257 * 3 + 4);
+    d += (order & F_PACK) ? 1 : 0;
+    d += (order & F_RLE) ? (1 + 257 * 3 + 4) : 0;
+    d += 20;
+    d += (order & F_STRIPE) ? (1 + 5 * N) : 0;
+    int sz = (int)d;
+    return (unsigned int)(sz + (sz & 1) + 2);
+}
+
+size_t up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+template <typename K> int occ_grid(K kernel, int smem, int sms) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int per = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, 32, smem);
+    return std::max(per, 1) * sms;
+}
+
+constexpr int SM_O0_32 = ENC_O0_SMEM_PER_GROUP, SM_O0_4 = ENC_O0_SMEM_PER_GROUP * 8;
+constexpr int SM_O1_32 = ENC_O1_SMEM_NS_32 * ENC_O1_SMEM_NS_32 * 16 + 256;
+constexpr int SM_O1_4 = (ENC_O1_SMEM_NS_4 * ENC_O1_SMEM_NS_4 * 16 + 256) * 8;
+
+}  // namespace
+
+void EncSlot::release() {
+    EncImpl* I = static_cast<EncImpl*>(impl);
+    if (!I) return;
+    if (I->d_scratch) cudaFree(I->d_scratch);
+    if (I->d_desc) cudaFree(I->d_desc);
+    if (I->h_desc) cudaFreeHost(I->h_desc);
+    if (I->uploaded) cudaEventDestroy(I->uploaded);
+    delete I;
+    impl = nullptr;
+}
+
+int encode_init(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    g_sms_enc = prop.multiProcessorCount;
+    double l10[257], l12[257];
+    for (int k = 0; k <= 256; k++) { l10[k] = log((double)(1024 + k)); l12[k] = log((double)(4096 + k)); }
+    if (cudaMemcpyToSymbol(c_log10, l10, sizeof(l10)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(c_log12, l12, sizeof(l12)) != cudaSuccess) return -1;
+    g_grid_enc[0][0] = occ_grid(enc_rans_kernel<4, 0>, SM_O0_4, g_sms_enc);
+    g_grid_enc[0][1] = occ_grid(enc_rans_kernel<4, 1>, SM_O1_4, g_sms_enc);
+    g_grid_enc[1][0] = occ_grid(enc_rans_kernel<32, 0>, SM_O0_32, g_sms_enc);
+    g_grid_enc[1][1] = occ_grid(enc_rans_kernel<32, 1>, SM_O1_32, g_sms_enc);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, const int32_t* h_order,
+               cudaStream_t st, char* err, size_t errlen) {
+#define ECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, errlen, "encode.cu:%d %s", __LINE__, cudaGetErrorString(e_)); return -1; } } while (0)
+    if (!slot.impl) slot.impl = new EncImpl();
+    EncImpl* I = static_cast<EncImpl*>(slot.impl);
+    if (!I->uploaded) ECK(cudaEventCreateWithFlags(&I->uploaded, cudaEventDisableTiming));
+    const int nblk = b.nblk;
+    if (!h_in_len || !h_order) {                                  // device-resident API: fetch the two small arrays
+        I->h_len.resize(nblk); I->h_order.resize(nblk);
+        ECK(cudaMemcpyAsync(I->h_len.data(), b.in_len, 4 * (size_t)nblk, cudaMemcpyDeviceToHost, st));
+        ECK(cudaMemcpyAsync(I->h_order.data(), b.order, 4 * (size_t)nblk, cudaMemcpyDeviceToHost, st));
+        ECK(cudaStreamSynchronize(st));
+        h_in_len = I->h_len.data(); h_order = I->h_order.data();
+    }
+
+    // ---- expand blocks into leaves and streams; lay out the scratch arena (offsets first)
+    std::vector<EncBlock> blocks(nblk);
+    std::vector<EncLeaf> leaves;
+    std::vector<EncStream> streams;
+    std::vector<uint64_t> in_off_needed;                           // (unused: offsets are read on the device)
+    size_t scratch = 0;
+    auto take = [&](size_t bytes) { size_t at = scratch; scratch += up(bytes + 32); return at; };
+    // Device pointers are formed as (uint8_t*)offset + tag; fixed up in a tiny kernel-free way below:
+    // leaves/streams store offsets relative to scratch base (tag 1) or to the block's in/out (tag 2).
+    struct Fix { uint32_t kind; uint32_t idx; uint32_t field; uint32_t blk; };
+    (void)in_off_needed;
+
+    auto add_stream = [&](uint32_t leaf, uint32_t n_max, uint32_t order, uint32_t nway, bool is_meta) {
+        EncStream S;
+        memset(&S, 0, sizeof(S));
+        S.n = n_max; S.order = order; S.nway = nway; S.leaf = leaf;
+        uint32_t cap = (host_bound(n_max, order) + 4 * nway + 64) & ~1u;
+        S.cap = cap;
+        S.out = reinterpret_cast<uint8_t*>(take(cap));
+        S.F0 = reinterpret_cast<uint32_t*>(take(1024));
+        if (order) {
+            S.F1 = reinterpret_cast<uint32_t*>(take(256 * 256 * 4));
+            S.syms = reinterpret_cast<EncSym*>(take(256 * 256 * 16));
+            const size_t tmax = 257 * 257 * 3 + 16;
+            S.ctab = reinterpret_cast<uint8_t*>(take(((tmax + tmax / 16 + 1024) & ~15u) + 1024 + 4096 + 64));
+        } else {
+            S.syms = reinterpret_cast<EncSym*>(take(256 * 16));
+        }
+        (void)is_meta;
+        streams.push_back(S);
+        return (uint32_t)streams.size() - 1;
+    };
+    // src/out of leaves: encoded as offset | tag in the low bits is fragile; keep explicit side tables
+    std::vector<uint8_t> leaf_src_is_scratch, leaf_out_is_scratch;
+    std::vector<uint64_t> leaf_src_off, leaf_out_off;
+
+    auto add_leaf = [&](uint32_t blk, uint32_t n, uint32_t flags, bool src_scratch, uint64_t src_off, bool out_scratch,
+                        uint64_t out_off) {
+        EncLeaf L;
+        memset(&L, 0, sizeof(L));
+        L.n = n; L.flags = flags; L.blk = blk; L.out_flags = flags; L.cur_n = n;
+        if (flags & F_PACK) L.packed = reinterpret_cast<uint8_t*>(take((size_t)n + 16));
+        if (flags & F_RLE) {
+            L.lits = reinterpret_cast<uint8_t*>(take((size_t)n + 16));
+            L.rmeta = reinterpret_cast<uint8_t*>(take((size_t)n + 272 + 64));
+        }
+        const uint32_t li = (uint32_t)leaves.size();
+        const uint32_t nway = (flags & F_X32) ? 32 : 4;
+        L.body = add_stream(li, n, flags & 1, nway, false);
+        L.meta = (flags & F_RLE) ? add_stream(li, n + 272, 0, nway, true) : 0xffffffffu;
+        leaves.push_back(L);
+        leaf_src_is_scratch.push_back(src_scratch); leaf_src_off.push_back(src_off);
+        leaf_out_is_scratch.push_back(out_scratch); leaf_out_off.push_back(out_off);
+        return li;
+    };
+
+    std::vector<uint64_t> blk_tr_off(nblk, 0);
+    for (int i = 0; i < nblk; i++) {
+        EncBlock& B = blocks[i];
+        memset(&B, 0, sizeof(B));
+        uint32_t n = h_in_len[i];
+        int order = h_order[i];
+        B.n = n; B.order = (uint32_t)order;
+        B.cap = host_bound(n, order);
+        if (n <= 20) order &= ~(int)F_STRIPE;                      // :1151
+        if (order & F_STRIPE) {
+            int N = order >> 8;
+            if (N == 0) N = 4;
+            if (N > 255) { B.mode = 3; continue; }                 // :1158
+            B.mode = 1; B.N = (uint32_t)N;
+            blk_tr_off[i] = take((size_t)n + 16);
+            static const int cand[4] = {1, 64, 128, 0};            // :1192
+            uint32_t ncand = 0;
+            int use[4];
+            for (int c = 0; c < 4; c++) if ((order & cand[c]) == cand[c]) use[ncand++] = cand[c];
+            B.ncand = ncand;
+            B.leaf0 = (uint32_t)leaves.size();
+            uint64_t at = 0;
+            for (int j = 0; j < N; j++) {
+                uint32_t len = n / N + ((n % N) > (uint32_t)j);
+                for (uint32_t c = 0; c < ncand; c++) {
+                    uint32_t fl = (uint32_t)use[c] | F_NOSZ | ((uint32_t)order & F_X32);
+                    size_t o = take(host_bound(len, (int)fl) + 64);
+                    add_leaf(i, len, fl, true, blk_tr_off[i] + at, true, o);
+                }
+                at += len;
+            }
+        } else if (order & F_CAT) {
+            B.mode = 2;
+        } else {
+            B.mode = 0;
+            B.leaf0 = add_leaf(i, n, (uint32_t)order & 0xff, false, 0, false, 0);
+        }
+    }
+
+    // ---- device memory
+    const size_t desc_bytes = up(sizeof(EncWork)) + up(sizeof(EncBlock) * blocks.size()) + up(sizeof(EncLeaf) * leaves.size()) +
+                              up(sizeof(EncStream) * streams.size()) + 256;
+    if (I->pending) { ECK(cudaEventSynchronize(I->uploaded)); I->pending = false; }
+    if (scratch + 256 > I->scratch_cap) {
+        if (I->d_scratch) cudaFree(I->d_scratch);
+        I->d_scratch = nullptr; I->scratch_cap = 0;
+        size_t want = scratch + scratch / 8 + (1 << 20);
+        if (cudaMalloc(&I->d_scratch, want) != cudaSuccess) { cudaGetLastError(); snprintf(err, errlen, "out of device memory for encode scratch (%zu B)", want); return -1; }
+        I->scratch_cap = want;
+    }
+    if (desc_bytes > I->desc_cap) {
+        if (I->d_desc) cudaFree(I->d_desc);
+        if (I->h_desc) cudaFreeHost(I->h_desc);
+        I->d_desc = nullptr; I->h_desc = nullptr; I->desc_cap = 0;
+        size_t want = desc_bytes + desc_bytes / 4;
+        if (cudaMalloc(&I->d_desc, want) != cudaSuccess || cudaHostAlloc(&I->h_desc, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError(); snprintf(err, errlen, "out of memory for encode descriptors"); return -1;
+        }
+        I->desc_cap = want;
+    }
+    // ---- resolve offsets into device pointers.  Block in/out pointers need in_off/out_off, which
+    // live on the device: a fix-up kernel patches them (enc_fix_kernel below).
+    uint8_t* sb = I->d_scratch;
+    for (auto& S : streams) {
+        S.out = sb + (size_t)S.out; S.F0 = reinterpret_cast<uint32_t*>(sb + (size_t)S.F0);
+        S.syms = reinterpret_cast<EncSym*>(sb + (size_t)S.syms);
+        if (S.order) { S.F1 = reinterpret_cast<uint32_t*>(sb + (size_t)S.F1); S.ctab = sb + (size_t)S.ctab; }
+    }
+    for (size_t k = 0; k < leaves.size(); k++) {
+        EncLeaf& L = leaves[k];
+        if (L.flags & F_PACK) L.packed = sb + (size_t)L.packed;
+        if (L.flags & F_RLE) { L.lits = sb + (size_t)L.lits; L.rmeta = sb + (size_t)L.rmeta; }
+        L.src = leaf_src_is_scratch[k] ? sb + leaf_src_off[k] : nullptr;      // nullptr: patched from the block
+        L.out = leaf_out_is_scratch[k] ? sb + leaf_out_off[k] : nullptr;
+        streams[L.body].src = L.src;
+    }
+    for (int i = 0; i < nblk; i++) if (blocks[i].mode == 1) blocks[i].tr = sb + blk_tr_off[i];
+
+    size_t o = 0;
+    EncWork hw;
+    memset(&hw, 0, sizeof(hw));
+    const size_t o_work = o; o += up(sizeof(EncWork));
+    const size_t o_blocks = o; o += up(sizeof(EncBlock) * blocks.size());
+    const size_t o_leaves = o; o += up(sizeof(EncLeaf) * leaves.size());
+    const size_t o_streams = o; o += up(sizeof(EncStream) * streams.size());
+    hw.blocks = reinterpret_cast<EncBlock*>(I->d_desc + o_blocks);
+    hw.leaves = reinterpret_cast<EncLeaf*>(I->d_desc + o_leaves);
+    hw.streams = reinterpret_cast<EncStream*>(I->d_desc + o_streams);
+    hw.nblocks = (uint32_t)blocks.size(); hw.nleaves = (uint32_t)leaves.size(); hw.nstreams = (uint32_t)streams.size();
+    memcpy(I->h_desc + o_work, &hw, sizeof(hw));
+    memcpy(I->h_desc + o_blocks, blocks.data(), sizeof(EncBlock) * blocks.size());
+    if (!leaves.empty()) memcpy(I->h_desc + o_leaves, leaves.data(), sizeof(EncLeaf) * leaves.size());
+    if (!streams.empty()) memcpy(I->h_desc + o_streams, streams.data(), sizeof(EncStream) * streams.size());
+    ECK(cudaMemcpyAsync(I->d_desc, I->h_desc, o, cudaMemcpyHostToDevice, st));
+    ECK(cudaEventRecord(I->uploaded, st));
+    I->pending = true;
+
+    EncWork* dW = reinterpret_cast<EncWork*>(I->d_desc + o_work);
+    int launches = 0;
+    const int g = g_sms_enc * 4;
+    enc_fix_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(dW, b.in_base, b.in_off, b.out_base, b.out_off); launches++;
+    bool any_stripe = false, any_tr = false, any32[2] = {false, false}, any4[2] = {false, false};
+    for (auto& B : blocks) any_stripe |= B.mode == 1;
+    for (auto& L : leaves) any_tr |= (L.flags & (F_PACK | F_RLE)) != 0;
+    for (auto& S : streams) { if (S.nway == 32) { any32[0] = true; any32[1] |= S.order != 0; } else { any4[0] = true; any4[1] |= S.order != 0; } }
+    if (any_stripe) { enc_stripe_kernel<<<g, 256, 0, st>>>(dW); launches++; }
+    if (any_tr) { enc_transform_kernel<<<g, TT, 0, st>>>(dW); launches++; }
+    if (!streams.empty()) {
+        enc_hist_kernel<<<g, HT, 0, st>>>(dW); launches++;
+        enc_table_kernel<<<g * 2, KT, 0, st>>>(dW); launches++;
+        // an order-1 request can fall back to order 0 on the device, so the order-0 kernels always run
+        if (any4[0])  { enc_rans_kernel<4, 0><<<g_grid_enc[0][0], 32, SM_O0_4, st>>>(dW); launches++; }
+        if (any4[1])  { enc_rans_kernel<4, 1><<<g_grid_enc[0][1], 32, SM_O1_4, st>>>(dW); launches++; }
+        if (any32[0]) { enc_rans_kernel<32, 0><<<g_grid_enc[1][0], 32, SM_O0_32, st>>>(dW); launches++; }
+        if (any32[1]) { enc_rans_kernel<32, 1><<<g_grid_enc[1][1], 32, SM_O1_32, st>>>(dW); launches++; }
+        enc_finish_kernel<<<g, 256, 0, st>>>(dW); launches++;
+    }
+    enc_block_kernel<<<g, 256, 0, st>>>(dW, b.out_len, b.status); launches++;
+    ECK(cudaGetLastError());
+    return launches;
+#undef ECK
+}
+
 }  // namespace hb
