@@ -81,7 +81,10 @@ struct Stage {
     DecSlot dec;
     EncSlot enc;
     cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+    cudaStream_t s_compute = nullptr;   // one per stage: a block is decoded by ONE warp, so a chunk's kernels
+                                        // last as long as its slowest block; chunks must overlap on the SMs
     void release() {
+        if (s_compute) cudaStreamDestroy(s_compute);
         d_in.release(); d_out.release(); d_off.release(); d_u32.release(); d_method.release();
         h_off.release(); h_u32.release(); h_method.release(); dec.release(); enc.release();
         if (h2d_done) cudaEventDestroy(h2d_done);
@@ -136,6 +139,10 @@ extern "C" hts_b200_ctx* hts_b200_create(int device) {
         cudaEventCreateWithFlags(&ctx->stage[s].h2d_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->stage[s].compute_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->stage[s].d2h_done, cudaEventDisableTiming);
+        if (cudaStreamCreateWithFlags(&ctx->stage[s].s_compute, cudaStreamNonBlocking) != cudaSuccess) {
+            hts_b200_destroy(ctx);
+            return nullptr;
+        }
     }
     return ctx;
 }
@@ -285,8 +292,12 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
     if (!ctx || nblk < 0) return -1;
     if (nblk == 0) return 0;
     CK(cudaSetDevice(ctx->device));
-    // ---- chunking: ~64 MiB of (in + out) per chunk keeps three stages busy without hogging HBM
-    const uint64_t target = 96ull << 20;
+    // ---- chunking.  The entropy kernels give one warp (or 4 lanes) to a block, so a chunk's kernel time is
+    // its slowest block's time however few blocks it holds: chunks must be big enough to fill the SMs
+    // (hundreds of blocks) yet numerous enough (>= ~6) for the copies of one to hide behind the next.
+    uint64_t total_bytes = 0;
+    for (int i = 0; i < nblk; i++) total_bytes += (uint64_t)in_len[i] + out_len[i];
+    const uint64_t target = std::max<uint64_t>(32ull << 20, std::min<uint64_t>(384ull << 20, total_bytes / 8));
     std::vector<int> cuts{0};
     {
         uint64_t acc = 0;
@@ -336,7 +347,8 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
         if (method) CK(cudaMemcpyAsync(S.d_method.p, S.h_method.p, n, cudaMemcpyHostToDevice, ctx->s_in));
         CK(cudaEventRecord(S.h2d_done, ctx->s_in));
         // ---- kernels
-        CK(cudaStreamWaitEvent(ctx->stream, S.h2d_done, 0));
+        cudaStream_t cs = S.s_compute;
+        CK(cudaStreamWaitEvent(cs, S.h2d_done, 0));
         uint32_t* d_status = S.d_u32.p + 2 * (size_t)n;
         if (!enc) {
             if (dec_prepare(ctx, S.dec, n, std::max<size_t>(ctx->arena_hint, 64u << 20))) return -1;
@@ -359,7 +371,7 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
                 if (f & F_PACK) post |= 2u;
             }
             db.kinds = kinds; db.post = post;
-            if (dec_enqueue(ctx, S.dec, db, ctx->stream)) return -1;
+            if (dec_enqueue(ctx, S.dec, db, cs)) return -1;
         } else {
             EncodeBatch eb;
             eb.in_base = S.d_in.p; eb.in_off = S.d_off.p; eb.in_len = S.d_u32.p;
@@ -367,11 +379,11 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
             eb.status = reinterpret_cast<int32_t*>(d_status);
             eb.order = reinterpret_cast<const int32_t*>(S.d_u32.p + 3 * (size_t)n);
             eb.nblk = n;
-            int l = encode_run(S.enc, eb, h_in_len, reinterpret_cast<const int32_t*>(h_order), ctx->stream, ctx->err, sizeof(ctx->err));
+            int l = encode_run(S.enc, eb, h_in_len, reinterpret_cast<const int32_t*>(h_order), cs, ctx->err, sizeof(ctx->err));
             if (l < 0) return -1;
             ctx->launches += l;
         }
-        CK(cudaEventRecord(S.compute_done, ctx->stream));
+        CK(cudaEventRecord(S.compute_done, cs));
         // ---- D2H
         CK(cudaStreamWaitEvent(ctx->s_out, S.compute_done, 0));
         CK(cudaMemcpyAsync(S.h_u32.p + n, S.d_u32.p + n, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->s_out));   // out_len + status
