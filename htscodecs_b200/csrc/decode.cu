@@ -161,12 +161,16 @@ __device__ int32_t plan_chain(DecWork* W, const uint8_t* in, uint32_t in_len, ui
             if (t1_size > in_len || t1_size > osz) return ST_FORMAT;
             if (!push_job(W, JK_COPY, j)) return ST_ARENA;
         } else if (flags & F_ORDER1) {
-            if (in[0] & 1) {                                         // O0-compressed table: scratch for it
-                uint32_t usz;
-                var_get_u32(in + 1, end, &usz);
+            if (in_len >= 4 * (x32 ? 32u : 4u) && (in[0] & 1)) {     // O0-compressed table (:944-955): expanded by an
+                uint32_t usz, csz;                                   // order-0 job (always 4-way) ahead of the order-1 kernel
+                const uint8_t* p = in + 1;
+                p += var_get_u32(p, end, &usz);
+                p += var_get_u32(p, end, &csz);
                 if (usz > 257u * 257u * 3u + 1024u) return ST_FORMAT;
+                if ((int64_t)csz >= (int64_t)(end - p) - 16) return ST_FORMAT;   // :948 (quirk kept)
                 j.aux = arena_alloc(W, (uint64_t)usz + 16);
                 if (!j.aux) return ST_ARENA;
+                if (!push_job(W, JK_O0_4, make_job(p, csz, j.aux, usz, blk))) return ST_ARENA;
             }
             if (!push_job(W, x32 ? JK_O1_32 : JK_O1_4, j)) return ST_ARENA;
         } else {
@@ -669,78 +673,84 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
 // ------------------------------------------------------------------------------------------
 // order-1
 // ------------------------------------------------------------------------------------------
-// Tables are compacted over the alphabet: rank r = index of a symbol among the present ones.
-//   rows[r_ctx][m]        -> rank of the decoded symbol          (ns rows of 1<<shift bytes)
-//   fc[r_ctx * ns + r]    -> F << 16 | C
-// They live in shared memory when they fit (8 symbols at shift 10 need 8.3 KB), else in the arena
-// (global memory, L1/L2 cached).  Shared memory of one group: [0,256) rank -> symbol,
-// [256,512) symbol -> rank, [512,1536) frequency scratch, the word ring, then TAB table bytes.
+// Symbols are ranked over the stream's alphabet (rank r = index of a symbol among the present
+// ones).  Two table forms:
+//
+//  * compact (shared memory; Nx16 streams whose alphabet fits).  Per context a row of packed
+//    entries, one per symbol of non-zero frequency, in cumulative order,
+//        entry = (C + F - 1) | (F - 1) << 12 | rank << 24
+//    and a 64-bucket coarse index: coarse[ctx][m >> (shift - 6)] = index of the entry holding
+//    the bucket's first slot.  A lookup reads the coarse byte and three consecutive entries and
+//    steps forward while m lies beyond an entry's last slot (a fourth or later entry inside one
+//    bucket is reached by a short scan; rows end in sentinels whose last slot is 0xfff).  This
+//    takes ns * (64 + 4 * (ns + 3)) bytes whatever the table precision: 1 KB for binned
+//    qualities, 12 KB for 46 symbols -- where byte-per-slot rows need 9-184 KB.
+//  * LUT (global memory, from the arena; 4x8 streams and alphabets that do not fit):
+//    rows[ctx][m] -> rank, fc[ctx * ns + rank] = F << 16 | C, as in the reference
+//    (rANS_static4x16pr.c:922-930).
+//
+// Shared memory of one group: [0,256) rank -> symbol, [256,512) symbol -> rank, [512,1536)
+// frequency scratch, the word ring, then TAB bytes of compact tables.
 template <int NWAY> struct O1Smem {
     static constexpr int UNRANK = 0, RANK = 256, FTMP = 512, RINGO = 1536;
     static constexpr int TABO = 1536 + GroupCfg<NWAY>::RING;
-    static constexpr int TAB = (NWAY == 32) ? 16896 : 6144;          // >= 6144: the nested O0 decoder's scratch
+    static constexpr int TAB = (NWAY == 32) ? 11968 : 3072;          // X_32: 15 warps / SM; 4-way: 40 groups / SM
     static constexpr int STRIDE = TABO + TAB;                        // multiple of 16
     static constexpr int TOTAL = STRIDE * GroupCfg<NWAY>::G;
 };
-
-// Scalar rANS 4x16 order-0 decode of a short stream (the compressed order-1 table,
-// …4x16pr.c:944-955) by ONE lane.  `scr` = 6144 bytes of shared scratch.
-__device__ bool nested_o0_decode(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t n, uint32_t scr) {
-    if (in_len < 16) return false;                                   // :503
-    const uint32_t F = scr, lut = scr + 1024, fq = scr + 5120;       // F: 256 x u32 (+ presence in the lut area)
-    for (uint32_t k = 0; k < 256; k++) { sts_u32(F + 4 * k, 0u); sts_u8(lut + k, 0u); }
-    GRd r{in, in + in_len - 8};                                      // :516
-    if (!read_alphabet(r, lut, 1u)) return false;
-    uint32_t tot = 0;
-    for (uint32_t s = 0; s < 256; s++) {
-        if (!lds_u8(lut + s)) continue;
-        uint32_t f = r.varint();
-        sts_u32(F + 4 * s, f);
-        tot += f;
-    }
-    uint32_t sh = 0;
-    if (tot != 0 && tot < 4096) while ((tot << sh) < 4096) sh++;
-    uint32_t x = 0;
-    for (uint32_t s = 0; s < 256; s++) {
-        uint32_t f = lds_u32(F + 4 * s) << sh;
-        if (!f) continue;
-        if (f > 4096 - x) return false;
-        sts_u32(fq + 4 * s, (f << 16) | x);
-        for (uint32_t y = 0; y < f; y++) sts_u8(lut + x + y, s);
-        x += f;
-    }
-    if (x != 4096) return false;
-    const uint8_t* p = r.p;
-    const uint8_t* lim = in + in_len;
-    if (p + 16 > lim) return false;
-    uint32_t R[4];
-    for (int z = 0; z < 4; z++) { R[z] = ld_u32_le(p); p += 4; if (R[z] < (1u << 15)) return false; }
-    for (uint32_t i = 0; i < n; i += 4) {
-#pragma unroll
-        for (int z = 0; z < 4; z++) {
-            if (i + z < n) {
-                uint32_t m = R[z] & 0xfff, s = lds_u8(lut + m), e = lds_u32(fq + 4 * s);
-                out[i + z] = (uint8_t)s;
-                R[z] = (e >> 16) * (R[z] >> 12) + m - (e & 0xffff);
-                if (R[z] < (1u << 15) && p + 1 < lim) { R[z] = (R[z] << 16) | p[0] | (p[1] << 8); p += 2; }
-            }
-        }
-    }
-    return true;
-}
+constexpr uint32_t O1_SENTINEL = 0x00ffffffu;                        // last slot 0xfff, F 4096, rank 0
 
 struct O1Tables {
-    uint8_t* rows;          // generic pointer: shared or global
-    uint32_t* fc;
+    uint32_t compact;       // 1: compact form in shared memory
+    uint32_t coarse, rows;  // compact: shared addresses
+    uint32_t rstride;       // compact: bytes per row, 4 * (ns + 3)
+    uint8_t* g_rows;        // LUT form
+    uint32_t* g_fc;
     uint32_t ns, shift;
 };
 
-// Group-cooperative: frequencies of one context (shared u32 array F, indexed by rank, `nsr`
-// entries used, all 256 zero-initialised) -> fc row + symbol row.  Returns false if they do not
-// sum to M after the power-of-two shift (…4x16pr.c:982-997); sums of M-1 are accepted for 4x8.
+// Group-cooperative: frequencies of one context (shared u32 array F, indexed by rank, `ns`
+// entries used) -> compact row + coarse index.  Returns false if they do not sum to 1 << shift
+// after the power-of-two shift (…4x16pr.c:982-997).
 template <int NWAY>
-__device__ bool build_o1_row(const Grp<NWAY>& G, uint32_t F, const O1Tables& T, uint32_t ctx, uint32_t Tsum,
-                             bool allow_4095) {
+__device__ bool build_o1_row_compact(const Grp<NWAY>& G, uint32_t F, const O1Tables& T, uint32_t ctx, uint32_t Tsum) {
+    const uint32_t M = 1u << T.shift, ns = T.ns, bs = T.shift - 6;
+    uint32_t sh = 0;
+    if (Tsum < M) while ((Tsum << sh) < M) sh++;
+    const uint32_t K = (ns + NWAY - 1) / NWAY, r0 = G.glane * K;     // each lane owns K consecutive ranks
+    uint32_t mine = 0, nz = 0;
+    bool bad = false;
+    for (uint32_t k = 0; k < K; k++) {
+        const uint32_t r = r0 + k;
+        const uint32_t f = (r < ns) ? (lds_u32(F + 4 * r) << sh) : 0u;
+        if (f > M) bad = true;
+        mine += f;
+        nz += (f != 0);
+    }
+    uint32_t total, nzt;
+    uint32_t c = G.exscan(bad ? 2 * M : mine, &total);
+    uint32_t idx = G.exscan(nz, &nzt);
+    if (total != M) return false;
+    const uint32_t row = T.rows + ctx * T.rstride, crs = T.coarse + ctx * 64;
+    for (uint32_t k = 0; k < K; k++) {
+        const uint32_t r = r0 + k;
+        if (r >= ns) break;
+        const uint32_t f = lds_u32(F + 4 * r) << sh;
+        if (!f) continue;
+        const uint32_t last = c + f - 1;
+        sts_u32(row + 4 * idx, last | ((f - 1) << 12) | (r << 24));
+        for (uint32_t q = (c + (1u << bs) - 1) >> bs; q <= (last >> bs); q++) sts_u8(crs + q, idx);
+        idx++;
+        c += f;
+    }
+    G.sync();
+    return true;
+}
+
+// LUT form of one context row (global memory).  Sums of M - 1 are accepted for 4x8.
+template <int NWAY>
+__device__ bool build_o1_row_lut(const Grp<NWAY>& G, uint32_t F, const O1Tables& T, uint32_t ctx, uint32_t Tsum,
+                                 bool allow_4095) {
     constexpr int K = 256 / NWAY;
     const uint32_t M = 1u << T.shift;
     uint32_t sh = 0;
@@ -758,17 +768,19 @@ __device__ bool build_o1_row(const Grp<NWAY>& G, uint32_t F, const O1Tables& T, 
     for (int k = 0; k < K; k++) {
         uint32_t sj = G.glane * K + k;
         uint32_t f = lds_u32(F + 4 * sj) << sh;
-        if (sj < T.ns) T.fc[ctx * T.ns + sj] = (f << 16) | c;
+        if (sj < T.ns) T.g_fc[ctx * T.ns + sj] = (f << 16) | c;
         sts_u32(F + 4 * sj, (f << 16) | c);
         c += f;
     }
     G.sync();
+    uint8_t* rowp = T.g_rows + (size_t)ctx * M;
     for (uint32_t sj = 0; sj < T.ns; sj++) {
         uint32_t e = lds_u32(F + 4 * sj);
         uint32_t f = e >> 16, cs = e & 0xffffu;
-        for (uint32_t k = G.glane; k < f; k += NWAY) T.rows[(size_t)ctx * M + cs + k] = (uint8_t)sj;
+        for (uint32_t k = G.glane; k < f; k += NWAY) rowp[cs + k] = (uint8_t)sj;
     }
-    if (total == M - 1 && G.glane == 0) T.rows[(size_t)ctx * M + M - 1] = T.rows[(size_t)ctx * M + M - 2];   // rANS_static.c:799
+    G.sync();
+    if (total == M - 1 && G.glane == 0) rowp[M - 1] = rowp[M - 2];   // rANS_static.c:799
     G.sync();
     return true;
 }
@@ -798,13 +810,12 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
             uint32_t h = job.in[0];
             shift = h >> 4;
             if (shift != 10 && shift != 12) err = 1;         // the reference has loops for 12 and 10 only
-            if (h & 1) {                                     // :944-955
-                uint32_t usz, csz;
+            if (h & 1) {                                     // :944-955: the planner had the table expanded into aux
+                uint32_t usz, csz;                           // by an order-0 job (and applied the :948 check)
                 const uint8_t* p = job.in + 1;
                 p += var_get_u32(p, in_end, &usz);
                 p += var_get_u32(p, in_end, &csz);
-                if ((int64_t)csz >= (int64_t)(in_end - p) - 16 || !job.aux) err = 1;      // :948 (quirk kept)
-                else if (!nested_o0_decode(p, csz, job.aux, usz, tabs)) err = 1;
+                if (!job.aux || (int64_t)csz >= (int64_t)(in_end - p) - 16) err = 1;
                 rd.p = job.aux; rd.end = job.aux + usz;
                 body = p + csz;
             } else {
@@ -830,24 +841,28 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     // ---- table storage
     O1Tables T;
     T.ns = ns; T.shift = shift;
-    const uint64_t rows_bytes = ((uint64_t)ns * M + 15) & ~15ull;
-    const uint64_t need = rows_bytes + (uint64_t)ns * ns * 4;
-    if (need <= (uint64_t)S::TAB) {
-        T.rows = gsm + S::TABO;
+    T.g_rows = nullptr; T.g_fc = nullptr;
+    T.rstride = 4 * (ns + 3);
+    T.coarse = tabs; T.rows = tabs + ns * 64;
+    T.compact = (!BYTE && ns * 64 + ns * T.rstride <= (uint32_t)S::TAB) ? 1u : 0u;
+    if (T.compact) {
+        for (uint32_t k = G.glane; k < ns * 16; k += NWAY) sts_u32(T.coarse + 4 * k, 0u);
+        for (uint32_t k = G.glane; k < ns * (ns + 3); k += NWAY) sts_u32(T.rows + 4 * k, O1_SENTINEL);
     } else {
+        const uint64_t rows_bytes = ((uint64_t)ns * M + 15) & ~15ull;
         uint8_t* a = nullptr;
-        if (G.glane == 0) a = arena_alloc(W, need);
-        T.rows = const_cast<uint8_t*>(G.bcast_ptr(a));
-        if (!T.rows) return ST_ARENA;
+        if (G.glane == 0) a = arena_alloc(W, rows_bytes + (uint64_t)ns * ns * 4);
+        T.g_rows = const_cast<uint8_t*>(G.bcast_ptr(a));
+        if (!T.g_rows) return ST_ARENA;
+        T.g_fc = reinterpret_cast<uint32_t*>(T.g_rows + rows_bytes);
+        for (uint32_t k = G.glane; k < ns * ns; k += NWAY) T.g_fc[k] = 0u;       // absent (ctx,sym) pairs: F = 0
     }
-    T.fc = reinterpret_cast<uint32_t*>(T.rows + rows_bytes);
-    for (uint32_t k = G.glane; k < ns * ns; k += NWAY) T.fc[k] = 0u;   // absent (ctx,sym) pairs: F = 0
     G.sync();
 
     // ---- phase 2: one row per context; lane 0 parses, the group fills
     if (!BYTE) {
         for (uint32_t ci = 0; ci < ns; ci++) {               // :967-998 (ascending symbol == ascending rank)
-            for (uint32_t k = G.glane; k < 256; k += NWAY) sts_u32(Ftmp + 4 * k, 0u);
+            for (uint32_t k = G.glane; k < (T.compact ? ns : 256u); k += NWAY) sts_u32(Ftmp + 4 * k, 0u);
             G.sync();
             uint32_t Tsum = 0;
             if (G.glane == 0) {                              // decode_freq_d :327-358
@@ -868,7 +883,8 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
             err = G.bcast(err); Tsum = G.bcast(Tsum);
             if (err) return ST_FORMAT;
             if (!Tsum) continue;                             // :977-980
-            if (!build_o1_row<NWAY>(G, Ftmp, T, ci, Tsum, false)) return ST_FORMAT;
+            if (T.compact ? !build_o1_row_compact<NWAY>(G, Ftmp, T, ci, Tsum)
+                          : !build_o1_row_lut<NWAY>(G, Ftmp, T, ci, Tsum, false)) return ST_FORMAT;
         }
     } else {
         // rANS_static.c:748-813: outer "sym [run]" list of contexts, one 4x8 table each
@@ -885,7 +901,7 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
             G.sync();
             err = G.bcast(err); ctx = G.bcast(ctx); x = G.bcast(x);
             if (err) return ST_FORMAT;
-            if (!build_o1_row<NWAY>(G, Ftmp, T, ctx, 4096u, true)) return ST_FORMAT;
+            if (!build_o1_row_lut<NWAY>(G, Ftmp, T, ctx, 4096u, true)) return ST_FORMAT;
             uint32_t more = 0;
             if (G.glane == 0) {
                 if (!run_i && ctx + 1 == rd.peek()) { rd.get(); ctx++; run_i = rd.get(); }
@@ -915,30 +931,90 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     return ST_OK;
 }
 
+// Per-lane output sink of the order-1 loop.  A lane writes its own contiguous segment, so a
+// plain byte store per symbol would cost one memory transaction per lane per step; instead the
+// last 16 bytes ride in registers and leave as one 128-bit store whenever the lane's address
+// crosses a 16-byte line.  The partial lines at either end of the segment are written bytewise
+// (the neighbouring lanes' segments share those lines).
+struct ByteSink {
+    uint8_t* p;                  // address of the next byte
+    uint32_t w0, w1, w2, w3;     // the newest 16 bytes, newest in the top byte of w3
+    uint32_t cnt;                // bytes gathered since the last store
+    __device__ __forceinline__ void init(uint8_t* q) { p = q; w0 = w1 = w2 = w3 = 0; cnt = 0; }
+    __device__ __forceinline__ void drain() {                // write the newest `cnt` bytes one by one
+        uint8_t* q = p;
+        for (uint32_t k = 0; k < cnt; k++) {
+            *--q = (uint8_t)(w3 >> 24);
+            w3 = __funnelshift_l(w2, w3, 8); w2 = __funnelshift_l(w1, w2, 8); w1 = __funnelshift_l(w0, w1, 8); w0 <<= 8;
+        }
+        cnt = 0;
+    }
+    __device__ __forceinline__ void put(uint32_t s) {
+        w0 = __funnelshift_r(w0, w1, 8); w1 = __funnelshift_r(w1, w2, 8); w2 = __funnelshift_r(w2, w3, 8);
+        w3 = (w3 >> 8) | (s << 24);
+        p++; cnt++;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            if (cnt == 16) { *reinterpret_cast<uint4*>(p - 16) = make_uint4(w0, w1, w2, w3); cnt = 0; }
+            else drain();
+        }
+    }
+};
+
+// One decode step of a lane (rANS_static4x16pr.c:1033-1047 / rANS_static.c:850-878): returns the
+// decoded rank and updates R.
+__device__ __forceinline__ uint32_t o1_symbol(uint32_t& R, uint32_t ctx, const O1Tables& T, uint32_t mask) {
+    const uint32_t m = R & mask;
+    if (T.compact) {
+        const uint32_t ci = lds_u8(T.coarse + ctx * 64 + (m >> (T.shift - 6)));
+        uint32_t ea = T.rows + ctx * T.rstride + 4 * ci;
+        const uint32_t e0 = lds_u32(ea), e1 = lds_u32(ea + 4), e2 = lds_u32(ea + 8);
+        const bool a = m > (e0 & 0xfffu), b = m > (e1 & 0xfffu);
+        uint32_t e = b ? e2 : (a ? e1 : e0);
+        if (b && m > (e2 & 0xfffu)) {                        // >= 4 symbols share the bucket: scan on (sentinel-bounded)
+            ea += 12;
+            do { e = lds_u32(ea); ea += 4; } while (m > (e & 0xfffu));
+        }
+        const uint32_t fm1 = (e >> 12) & 0xfffu;
+        R = (fm1 + 1u) * (R >> T.shift) + m - ((e & 0xfffu) - fm1);
+        return e >> 24;
+    }
+    uint32_t sr = T.g_rows[(size_t)ctx * (mask + 1u) + m];
+    sr = min(sr, T.ns - 1u);                                 // rows of never-seen contexts are uninitialised
+    const uint32_t e = T.g_fc[ctx * T.ns + sr];
+    R = (e >> 16) * (R >> T.shift) + m - (e & 0xffffu);
+    return sr;
+}
+
 template <int NWAY, bool BYTE>
 __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const O1Tables T, uint32_t unrank,
                                         uint32_t ctx0, uint8_t* out, uint32_t seg, uint32_t tail, uint32_t maxit,
                                         const Grp<NWAY>& G) {
     const uint32_t lt = (NWAY == 32) ? lanemask_lt() : ((1u << G.glane) - 1u);
-    const uint32_t shift = T.shift, mask = (1u << shift) - 1u, ns = T.ns;
+    const uint32_t mask = (1u << T.shift) - 1u;
     const uint32_t mine = seg + ((G.glane == NWAY - 1) ? tail : 0u);   // symbols this lane decodes
     const uint32_t group_steps = seg + tail;
-    uint8_t* op = out + (size_t)G.glane * seg;
+    ByteSink sink;
+    sink.init(out + (size_t)G.glane * seg);
     uint32_t ctx = ctx0;
-    for (uint32_t i = 0; i < maxit; i++) {
+    uint32_t i = 0;
+    if (NWAY == 32) {                                        // every lane is active for the first `seg` steps
+        for (; i < seg; i++) {
+            ctx = o1_symbol(R, ctx, T, mask);
+            sink.put(lds_u8(unrank + ctx));
+            R = renorm_step<NWAY, BYTE, false>(R, true, ring, lt, G.gshift);
+            ring.advance(G.glane, true);
+        }
+    }
+    for (; i < maxit; i++) {
         const bool act = i < mine;
-        if (act) {                                           // :1033-1047 / rANS_static.c:850-878
-            uint32_t m = R & mask;
-            uint32_t sr = T.rows[(size_t)ctx * (mask + 1u) + m];
-            sr = min(sr, ns - 1u);                           // rows of never-seen contexts are uninitialised
-            uint32_t e = T.fc[ctx * ns + sr];
-            R = (e >> 16) * (R >> shift) + m - (e & 0xffffu);
-            *op++ = (uint8_t)lds_u8(unrank + sr);
-            ctx = sr;
+        if (act) {
+            ctx = o1_symbol(R, ctx, T, mask);
+            sink.put(lds_u8(unrank + ctx));
         }
         R = renorm_step<NWAY, BYTE, false>(R, act, ring, lt, G.gshift);
         ring.advance(G.glane, i < group_steps);
     }
+    sink.drain();
 }
 
 template <int NWAY, bool BYTE>
@@ -961,13 +1037,16 @@ __global__ void __launch_bounds__(32) dec_o1_kernel(DecWork* W, int32_t* status,
         const bool active = ji < njobs;
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         O1Tables T;
-        T.rows = nullptr; T.fc = nullptr; T.ns = 1; T.shift = 12;
+        T.compact = 1; T.coarse = T.rows = base + S::TABO; T.rstride = 0;
+        T.g_rows = nullptr; T.g_fc = nullptr; T.ns = 1; T.shift = 12;
         uint32_t R = 0, ctx0 = 0;
         const uint8_t* first_word = nullptr;
         bool ok = false;
         if (active) {
             job = jobs[ji];
-            int32_t st = o1_setup<NWAY, BYTE>(G, W, job, gsm, &T, &R, &first_word, &ctx0);
+            // an order-0 job may have been expanding this stream's table: skip if that (or anything else) failed
+            int32_t st = (job.aux && status[job.blk] != ST_OK) ? ST_FORMAT
+                                                               : o1_setup<NWAY, BYTE>(G, W, job, gsm, &T, &R, &first_word, &ctx0);
             ok = st == ST_OK;
             if (!ok && G.glane == 0) set_status(status, job.blk, st);
         }
