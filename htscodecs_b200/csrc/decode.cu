@@ -528,16 +528,17 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 // ------------------------------------------------------------------------------------------
 // Shared memory of dec_o0_kernel: G symbol LUTs (4096 B each; during set-up a LUT doubles as
 // header staging [0,1040), presence bytes [1280,1536) and frequency scratch [2048,3072)),
-// then G fc tables (256 x {F, -C}), then G word rings.
+// then G fc tables (256 x u32, F << 16 | C), then G word rings.  7 KB per X_32 warp with the
+// per-CTA reserve: 32 resident warps per SM.
 template <int NWAY> struct O0Smem {
     static constexpr int G = GroupCfg<NWAY>::G;
-    static constexpr int LUT = 0, FC = G * 4096, RINGO = G * 6144;
-    static constexpr int TOTAL = G * (6144 + GroupCfg<NWAY>::RING);
+    static constexpr int LUT = 0, FC = G * 4096, RINGO = G * 5120;
+    static constexpr int TOTAL = G * (5120 + GroupCfg<NWAY>::RING);
 };
 constexpr int HDR_STAGE = 1040;     // bytes of stream head staged for the table parser
 
 // Turn 256 frequencies (shared u32 array F) into the decode tables of one group:
-//   fc[s]  = { F[s], -C[s] }       so that   x' = F*(x>>12) + (m - C)
+//   fc[s]  = F[s] << 16 | C[s]     so that   x' = F*(x>>12) + m - C
 //   lut[m] = s                     for C[s] <= m < C[s]+F[s]
 // Group-synchronous.  Returns false unless the frequencies sum to `want` (or `want_alt`).
 template <int NWAY>
@@ -557,13 +558,13 @@ __device__ bool build_o0_tables(const Grp<NWAY>& G, uint32_t F, uint32_t fc, uin
     for (int k = 0; k < K; k++) {
         uint32_t s = G.glane * K + k;
         uint32_t f = lds_u32(F + 4 * s);
-        sts_v2(fc + 8 * s, make_uint2(f, 0u - c));
+        sts_u32(fc + 4 * s, (f << 16) | c);
         c += f;
     }
     G.sync();
     for (uint32_t s = 0; s < 256; s++) {                             // :538-549, the group fills one symbol at a time
-        uint2 e = lds_v2(fc + 8 * s);
-        uint32_t f = e.x, cs = 0u - e.y;
+        uint32_t e = lds_u32(fc + 4 * s);
+        uint32_t f = e >> 16, cs = e & 0xffffu;
         for (uint32_t k = G.glane; k < f; k += NWAY) sts_u8(lut + cs + k, s);
     }
     G.sync();
@@ -612,19 +613,37 @@ __device__ bool o0_setup(const Grp<NWAY>& G, const DecJob& job, uint32_t lut, ui
     return build_o0_tables<NWAY>(G, Ftmp, fc, lut, 4096u, BYTE ? 4095u : 4096u); // 4x8 tables may sum to 4095 (:305)
 }
 
+// One decode step (rANS_static4x16pr.c:576-597 / rANS_static.c:318-344) for every lane.
+template <int NWAY, bool BYTE, bool ALIGNED, bool ALLACT>
+__device__ __forceinline__ uint32_t o0_step(uint32_t R, bool act, WordRing<NWAY>& ring, uint32_t lut, uint32_t fc,
+                                            uint8_t* op, uint32_t lt, uint32_t gshift) {
+    const uint32_t m = R & 0xfffu;
+    const uint32_t s = lds_u8(lut + m);
+    const uint32_t e = lds_u32(fc + s * 4);
+    const uint32_t Rn = (e >> 16) * (R >> 12) + m - (e & 0xffffu);
+    if (ALLACT || act) { R = Rn; *op = (uint8_t)s; }
+    return renorm_step<NWAY, BYTE, ALIGNED>(R, ALLACT || act, ring, lt, gshift);
+}
+
+// `minit` (warp-uniform) = steps for which every lane of the warp is active: they run four to a
+// ring check (four steps consume at most half of a half ring).
 template <int NWAY, bool BYTE, bool ALIGNED>
 __device__ __forceinline__ void o0_loop(uint32_t R, WordRing<NWAY>& ring, uint32_t lut, uint32_t fc, uint8_t* out,
-                                        uint32_t iters, uint32_t rem, uint32_t maxit, const Grp<NWAY>& G) {
+                                        uint32_t iters, uint32_t rem, uint32_t minit, uint32_t maxit, const Grp<NWAY>& G) {
     const uint32_t lt = (NWAY == 32) ? lanemask_lt() : ((1u << G.glane) - 1u);
     uint8_t* op = out + G.glane;
-    for (uint32_t i = 0; i < maxit; i++) {
-        const bool act = (NWAY == 32) ? true : (i < iters);
-        uint32_t m = R & 0xfffu;
-        uint32_t s = lds_u8(lut + m);
-        uint2 e = lds_v2(fc + s * 8);
-        uint32_t Rn = e.x * (R >> 12) + (m + e.y);
-        if (act) { R = Rn; *op = (uint8_t)s; op += NWAY; }
-        R = renorm_step<NWAY, BYTE, ALIGNED>(R, act, ring, lt, G.gshift);
+    uint32_t i = 0;
+    for (; i + 4 <= minit; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            R = o0_step<NWAY, BYTE, ALIGNED, true>(R, true, ring, lut, fc, op + u * NWAY, lt, G.gshift);
+        op += 4 * NWAY;
+        ring.advance(G.glane, true);
+    }
+    for (; i < maxit; i++) {
+        const bool act = i < iters;
+        R = o0_step<NWAY, BYTE, ALIGNED, false>(R, act, ring, lut, fc, op, lt, G.gshift);
+        if (act) op += NWAY;
         ring.advance(G.glane, act);
     }
     // the last n % NWAY symbols: peek only (rANS_static.c:346-355; for Nx16 nothing follows them)
@@ -637,8 +656,9 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
     using S = O0Smem<NWAY>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const Grp<NWAY> G;
-    const uint32_t base = smem_addr(smem_raw);
-    const uint32_t lut = base + S::LUT + G.g * 4096, fc = base + S::FC + G.g * 2048;
+    uint32_t base = smem_addr(smem_raw);
+    asm volatile("" : "+r"(base));                      // keep the window base in a register (no re-derivation per step)
+    const uint32_t lut = base + S::LUT + G.g * 4096, fc = base + S::FC + G.g * 1024;
     const uint32_t ringa = base + S::RINGO + G.g * C::RING;
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
@@ -662,10 +682,10 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
         ring.init(job.in + first_word, job.in + job.in_len, ringa, G, ok);
         __syncwarp();
         const uint32_t iters = ok ? job.out_len / NWAY : 0, rem = ok ? job.out_len % NWAY : 0;
-        const uint32_t maxit = (NWAY == 32) ? iters : __reduce_max_sync(0xffffffffu, iters);
-        const bool aligned = (NWAY == 32) && !BYTE && ((ring.head & 1u) == 0);
-        if (aligned) o0_loop<NWAY, BYTE, true >(R, ring, lut, fc, job.out, iters, rem, maxit, G);
-        else         o0_loop<NWAY, BYTE, false>(R, ring, lut, fc, job.out, iters, rem, maxit, G);
+        const uint32_t maxit = __reduce_max_sync(0xffffffffu, iters), minit = __reduce_min_sync(0xffffffffu, iters);
+        const bool aligned = !BYTE && __all_sync(0xffffffffu, (ring.head & 1u) == 0);
+        if (aligned) o0_loop<NWAY, BYTE, true >(R, ring, lut, fc, job.out, iters, rem, minit, maxit, G);
+        else         o0_loop<NWAY, BYTE, false>(R, ring, lut, fc, job.out, iters, rem, minit, maxit, G);
         __syncwarp();
     }
 }
@@ -787,10 +807,9 @@ __device__ bool build_o1_row_lut(const Grp<NWAY>& G, uint32_t F, const O1Tables&
 
 // Per-group order-1 set-up.  Returns 0 ok, ST_FORMAT or ST_ARENA (group-uniform).
 template <int NWAY, bool BYTE>
-__device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, uint8_t* gsm, O1Tables* Tout,
-                            uint32_t* R, const uint8_t** first_word, uint32_t* ctx0) {
+__device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, uint8_t* gsm, uint32_t base,
+                            O1Tables* Tout, uint32_t* R, const uint8_t** first_word, uint32_t* ctx0) {
     using S = O1Smem<NWAY>;
-    const uint32_t base = smem_addr(gsm);
     const uint32_t unrank = base + S::UNRANK, rank = base + S::RANK, Ftmp = base + S::FTMP, tabs = base + S::TABO;
     const uint8_t* in_end = job.in + job.in_len;
 
@@ -933,38 +952,45 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
 
 // Per-lane output sink of the order-1 loop.  A lane writes its own contiguous segment, so a
 // plain byte store per symbol would cost one memory transaction per lane per step; instead the
-// last 16 bytes ride in registers and leave as one 128-bit store whenever the lane's address
-// crosses a 16-byte line.  The partial lines at either end of the segment are written bytewise
-// (the neighbouring lanes' segments share those lines).
+// newest 16 bytes ride in registers and leave as one 128-bit store each time a 16-byte line is
+// complete.  The partial lines at either end of a segment are written bytewise (neighbouring
+// lanes' segments share those lines).
+__device__ __noinline__ void sink_drain(uint8_t* line, uint32_t k, uint32_t skip, uint32_t w0, uint32_t w1, uint32_t w2,
+                                        uint32_t w3) {
+    // the newest (k - skip) bytes sit at the top of the window; they belong at line[skip .. k)
+    for (uint32_t q = k; q > skip; q--) {
+        line[q - 1] = (uint8_t)(w3 >> 24);
+        w3 = __funnelshift_l(w2, w3, 8); w2 = __funnelshift_l(w1, w2, 8); w1 = __funnelshift_l(w0, w1, 8); w0 <<= 8;
+    }
+}
+
 struct ByteSink {
-    uint8_t* p;                  // address of the next byte
+    uint8_t* line;               // 16-byte aligned address of the line being gathered
     uint32_t w0, w1, w2, w3;     // the newest 16 bytes, newest in the top byte of w3
-    uint32_t cnt;                // bytes gathered since the last store
-    __device__ __forceinline__ void init(uint8_t* q) { p = q; w0 = w1 = w2 = w3 = 0; cnt = 0; }
-    __device__ __forceinline__ void drain() {                // write the newest `cnt` bytes one by one
-        uint8_t* q = p;
-        for (uint32_t k = 0; k < cnt; k++) {
-            *--q = (uint8_t)(w3 >> 24);
-            w3 = __funnelshift_l(w2, w3, 8); w2 = __funnelshift_l(w1, w2, 8); w1 = __funnelshift_l(w0, w1, 8); w0 <<= 8;
-        }
-        cnt = 0;
+    uint32_t k;                  // bytes of this line accounted for (including `skip`)
+    uint32_t skip;               // leading bytes of the first line that belong to the previous segment
+    __device__ __forceinline__ void init(uint8_t* q) {
+        const uint32_t lo = (uint32_t)(reinterpret_cast<uintptr_t>(q) & 15);
+        line = q - lo; k = skip = lo; w0 = w1 = w2 = w3 = 0;
     }
     __device__ __forceinline__ void put(uint32_t s) {
         w0 = __funnelshift_r(w0, w1, 8); w1 = __funnelshift_r(w1, w2, 8); w2 = __funnelshift_r(w2, w3, 8);
         w3 = (w3 >> 8) | (s << 24);
-        p++; cnt++;
-        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-            if (cnt == 16) { *reinterpret_cast<uint4*>(p - 16) = make_uint4(w0, w1, w2, w3); cnt = 0; }
-            else drain();
+        if (++k == 16) {
+            if (skip == 0) *reinterpret_cast<uint4*>(line) = make_uint4(w0, w1, w2, w3);
+            else { sink_drain(line, 16, skip, w0, w1, w2, w3); skip = 0; }
+            line += 16; k = 0;
         }
     }
+    __device__ __forceinline__ void finish() { if (k > skip) sink_drain(line, k, skip, w0, w1, w2, w3); }
 };
 
 // One decode step of a lane (rANS_static4x16pr.c:1033-1047 / rANS_static.c:850-878): returns the
-// decoded rank and updates R.
+// decoded rank and updates R.  COMPACT: the warp holds compact tables only (no per-step test).
+template <bool COMPACT>
 __device__ __forceinline__ uint32_t o1_symbol(uint32_t& R, uint32_t ctx, const O1Tables& T, uint32_t mask) {
     const uint32_t m = R & mask;
-    if (T.compact) {
+    if (COMPACT || T.compact) {
         const uint32_t ci = lds_u8(T.coarse + ctx * 64 + (m >> (T.shift - 6)));
         uint32_t ea = T.rows + ctx * T.rstride + 4 * ci;
         const uint32_t e0 = lds_u32(ea), e1 = lds_u32(ea + 4), e2 = lds_u32(ea + 8);
@@ -985,10 +1011,12 @@ __device__ __forceinline__ uint32_t o1_symbol(uint32_t& R, uint32_t ctx, const O
     return sr;
 }
 
-template <int NWAY, bool BYTE>
+// `minit` (warp-uniform) = steps for which every lane of the warp is active; they run four to a
+// ring check.
+template <int NWAY, bool BYTE, bool ALIGNED, bool COMPACT>
 __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const O1Tables T, uint32_t unrank,
-                                        uint32_t ctx0, uint8_t* out, uint32_t seg, uint32_t tail, uint32_t maxit,
-                                        const Grp<NWAY>& G) {
+                                        uint32_t ctx0, uint8_t* out, uint32_t seg, uint32_t tail, uint32_t minit,
+                                        uint32_t maxit, const Grp<NWAY>& G) {
     const uint32_t lt = (NWAY == 32) ? lanemask_lt() : ((1u << G.glane) - 1u);
     const uint32_t mask = (1u << T.shift) - 1u;
     const uint32_t mine = seg + ((G.glane == NWAY - 1) ? tail : 0u);   // symbols this lane decodes
@@ -997,24 +1025,25 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
     sink.init(out + (size_t)G.glane * seg);
     uint32_t ctx = ctx0;
     uint32_t i = 0;
-    if (NWAY == 32) {                                        // every lane is active for the first `seg` steps
-        for (; i < seg; i++) {
-            ctx = o1_symbol(R, ctx, T, mask);
+    for (; i + 4 <= minit; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            ctx = o1_symbol<COMPACT>(R, ctx, T, mask);
             sink.put(lds_u8(unrank + ctx));
-            R = renorm_step<NWAY, BYTE, false>(R, true, ring, lt, G.gshift);
-            ring.advance(G.glane, true);
+            R = renorm_step<NWAY, BYTE, ALIGNED>(R, true, ring, lt, G.gshift);
         }
+        ring.advance(G.glane, true);
     }
     for (; i < maxit; i++) {
         const bool act = i < mine;
         if (act) {
-            ctx = o1_symbol(R, ctx, T, mask);
+            ctx = o1_symbol<COMPACT>(R, ctx, T, mask);
             sink.put(lds_u8(unrank + ctx));
         }
-        R = renorm_step<NWAY, BYTE, false>(R, act, ring, lt, G.gshift);
+        R = renorm_step<NWAY, BYTE, ALIGNED>(R, act, ring, lt, G.gshift);
         ring.advance(G.glane, i < group_steps);
     }
-    sink.drain();
+    sink.finish();
 }
 
 template <int NWAY, bool BYTE>
@@ -1024,7 +1053,8 @@ __global__ void __launch_bounds__(32) dec_o1_kernel(DecWork* W, int32_t* status,
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const Grp<NWAY> G;
     uint8_t* gsm = smem_raw + G.g * S::STRIDE;
-    const uint32_t base = smem_addr(gsm);
+    uint32_t base = smem_addr(gsm);
+    asm volatile("" : "+r"(base));                      // keep the window base in a register
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
 
@@ -1046,7 +1076,7 @@ __global__ void __launch_bounds__(32) dec_o1_kernel(DecWork* W, int32_t* status,
             job = jobs[ji];
             // an order-0 job may have been expanding this stream's table: skip if that (or anything else) failed
             int32_t st = (job.aux && status[job.blk] != ST_OK) ? ST_FORMAT
-                                                               : o1_setup<NWAY, BYTE>(G, W, job, gsm, &T, &R, &first_word, &ctx0);
+                                                               : o1_setup<NWAY, BYTE>(G, W, job, gsm, base, &T, &R, &first_word, &ctx0);
             ok = st == ST_OK;
             if (!ok && G.glane == 0) set_status(status, job.blk, st);
         }
@@ -1054,8 +1084,14 @@ __global__ void __launch_bounds__(32) dec_o1_kernel(DecWork* W, int32_t* status,
         ring.init(first_word, job.in + job.in_len, base + S::RINGO, G, ok);
         __syncwarp();
         const uint32_t seg = ok ? job.out_len / NWAY : 0, tail = ok ? job.out_len - seg * NWAY : 0;
-        const uint32_t maxit = __reduce_max_sync(0xffffffffu, seg + tail);
-        o1_loop<NWAY, BYTE>(R, ring, T, base + S::UNRANK, ctx0, job.out, seg, tail, maxit, G);
+        const uint32_t maxit = __reduce_max_sync(0xffffffffu, seg + tail), minit = __reduce_min_sync(0xffffffffu, seg);
+        const bool aligned = !BYTE && __all_sync(0xffffffffu, (ring.head & 1u) == 0);
+        const bool compact = !BYTE && __all_sync(0xffffffffu, T.compact != 0);
+        const uint32_t unrank = base + S::UNRANK;
+        if (BYTE)                    o1_loop<NWAY, BYTE, false, false>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
+        else if (compact && aligned) o1_loop<NWAY, false, true, true>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
+        else if (compact)            o1_loop<NWAY, false, false, true>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
+        else                         o1_loop<NWAY, false, false, false>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
         __syncwarp();
     }
 }
