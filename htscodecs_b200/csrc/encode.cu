@@ -97,8 +97,7 @@ struct EncBlock {
 struct EncWork {
     EncLeaf* leaves; EncStream* streams; EncBlock* blocks;
     uint32_t nleaves, nstreams, nblocks;
-    uint32_t next_stream[2][2];    // persistent-kernel cursors: [nway32][order]
-    uint32_t next_misc[8];
+    uint32_t next_misc[8];         // persistent-kernel cursors, one per enc_rans_kernel launch
 };
 
 __constant__ double c_log10[257];   // log(1024 + k)  (host libm, see encode_init)
@@ -386,17 +385,51 @@ __global__ void __launch_bounds__(TT) enc_transform_kernel(EncWork* W) {
 }
 
 // ------------------------------------------------------------------------------------------
-// enc_hist_kernel: one CTA per stream
+// enc_hist_kernel: one CTA (4 warps) per stream
 // ------------------------------------------------------------------------------------------
-constexpr int HT = 256;
-constexpr uint32_t O1_SMEM_NS = 96;      // pair counts in shared memory up to this alphabet size (36 KB)
+// Counting is done without atomics: every lane owns a private column of 16-bit counters,
+// cnt[warp][slot][lane] (16 KB per warp for 256 slots: conflict-free, lane l only ever touches
+// bank l/2), which are folded into 32-bit totals after at most HT_TILE bytes per lane.  Slots are
+// byte values for the order-0 histogram (utils.h:81-102) and rank pairs ctx * ns + sym for
+// order-1 statistics over alphabets of up to 16 symbols (utils.h:137-202); larger alphabets use
+// shared-memory atomics on a 96 x 96 table, or global atomics beyond that.
+constexpr int HT = 128;
+constexpr int HT_WARPS = HT / 32;
+constexpr uint32_t HT_TILE = 32768;                     // bytes per lane between folds (< 65536)
+constexpr uint32_t O1_PRIV_NS = 16;                     // lane-private pair counters up to this alphabet size
+constexpr uint32_t O1_SMEM_NS = 96;                     // shared-memory atomics up to this alphabet size
+constexpr int HIST_SMEM = HT_WARPS * 256 * 64;          // 64 KB of private counters (reused as the 96 x 96 table)
+
+// Fold the private counters of `nslots` slots into tot[] (u32, shared) and clear them.
+__device__ __forceinline__ void hist_fold(uint16_t* cnt, uint32_t* tot, uint32_t nslots) {
+    __syncthreads();
+    for (uint32_t sl = threadIdx.x; sl < nslots; sl += HT) {
+        uint32_t sum = 0;
+        for (int w = 0; w < HT_WARPS; w++) {
+            uint32_t* col = reinterpret_cast<uint32_t*>(cnt + ((size_t)w * 256 + sl) * 32);
+            for (uint32_t j = 0; j < 16; j++) {
+                const uint32_t jj = (j + sl) & 15;     // rotate: neighbouring slots start in different banks
+                const uint32_t v = col[jj];
+                sum += (v & 0xffffu) + (v >> 16);
+                col[jj] = 0;
+            }
+        }
+        tot[sl] += sum;
+    }
+    __syncthreads();
+}
 
 __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
+    extern __shared__ __align__(16) uint8_t hsm[];
     __shared__ uint32_t h[256];
+    __shared__ uint32_t ptot[O1_PRIV_NS * O1_PRIV_NS];
     __shared__ uint8_t rank[256];
-    __shared__ uint32_t pair[O1_SMEM_NS * O1_SMEM_NS];
     __shared__ uint32_t s_ns;
-    const uint32_t tid = threadIdx.x;
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(hsm);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint16_t* mycol = cnt + (size_t)warp * 256 * 32 + lane;          // + slot * 32
+
+    for (uint32_t k = tid; k < HIST_SMEM / 16; k += HT) reinterpret_cast<uint4*>(hsm)[k] = make_uint4(0, 0, 0, 0);
     for (uint32_t si = blockIdx.x; si < W->nstreams; si += gridDim.x) {
         EncStream& S = W->streams[si];
         __syncthreads();
@@ -404,28 +437,34 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
         const uint32_t n = S.n, nway = S.nway;
         uint32_t order = S.order;
         if (order && (n < 8 || n < nway)) order = 0;                 // :1322-1325 (+ N-way analogue)
-        h[tid] = 0;
+        for (uint32_t k = tid; k < 256; k += HT) h[k] = 0;
         __syncthreads();
-        // hist8, utils.h:81-102: 16 bytes per thread per step, warp-aggregated by value runs
+        // ---- hist8, utils.h:81-102: aligned 16-byte chunks, one per thread per step
+        const uintptr_t a = reinterpret_cast<uintptr_t>(in);
+        const uint32_t head = min(n, (uint32_t)((16 - (a & 15)) & 15));
+        const uint32_t nv = (n - head) / 16;
+        const uint4* v = reinterpret_cast<const uint4*>(in + head);
         {
-            const uintptr_t a = reinterpret_cast<uintptr_t>(in);
-            const uint32_t head = min(n, (uint32_t)((16 - (a & 15)) & 15));
             for (uint32_t i = tid; i < head; i += HT) atomicAdd(&h[in[i]], 1u);
-            const uint32_t nv = (n - head) / 16;
-            const uint4* v = reinterpret_cast<const uint4*>(in + head);
-            for (uint32_t i = tid; i < nv; i += HT) {
-                uint4 q = v[i];
-                uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    atomicAdd(&h[w[k] & 0xff], 1u); atomicAdd(&h[(w[k] >> 8) & 0xff], 1u);
-                    atomicAdd(&h[(w[k] >> 16) & 0xff], 1u); atomicAdd(&h[w[k] >> 24], 1u);
-                }
-            }
             for (uint32_t i = head + nv * 16 + tid; i < n; i += HT) atomicAdd(&h[in[i]], 1u);
+            uint32_t since = 0;
+            for (uint32_t i0 = 0; i0 < nv; i0 += HT) {
+                const uint32_t i = i0 + tid;
+                if (i < nv) {
+                    const uint4 q = __ldg(v + i);
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+#pragma unroll
+                        for (int bb = 0; bb < 4; bb++) mycol[((w[k] >> (8 * bb)) & 0xffu) * 32]++;
+                    }
+                }
+                since += 16;
+                if (since >= HT_TILE) { hist_fold(cnt, h, 256); since = 0; }          // block-uniform
+            }
+            hist_fold(cnt, h, 256);
         }
-        __syncthreads();
-        S.F0[tid] = h[tid];
+        for (uint32_t k = tid; k < 256; k += HT) S.F0[k] = h[k];
         if (tid == 0) { S.order_eff = order; S.size = 0; S.tab_len = 0; S.pay_off = S.cap; }
         if (!order || n == 0) continue;
 
@@ -442,20 +481,52 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
         }
         __syncthreads();
         const uint32_t ns = s_ns;
-        const bool in_smem = ns <= O1_SMEM_NS;
-        uint32_t* P = in_smem ? pair : S.F1;
-        for (uint32_t k = tid; k < ns * ns; k += HT) P[k] = 0;
-        __syncthreads();
-        // hist1_4, utils.h:137-202: every adjacent pair of the whole buffer, first context 0
-        for (uint32_t i = tid; i < n; i += HT) {
-            uint32_t c = i ? in[i - 1] : 0u, s = in[i];
-            atomicAdd(&P[rank[c] * ns + rank[s]], 1u);
-        }
-        // the segment starts are coded in context 0 (:720-723, with 4 -> nway)
         const uint32_t seg = n / nway;
-        for (uint32_t k = 1 + tid; k < nway; k += HT) atomicAdd(&P[rank[0] * ns + rank[in[k * seg]]], 1u);
-        __syncthreads();
-        if (in_smem) for (uint32_t k = tid; k < ns * ns; k += HT) S.F1[k] = pair[k];
+        if (ns <= O1_PRIV_NS) {
+            // hist1_4, utils.h:137-202: every adjacent pair of the whole buffer, first context 0
+            for (uint32_t k = tid; k < ns * ns; k += HT) ptot[k] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < head; i += HT) atomicAdd(&ptot[rank[i ? in[i - 1] : 0u] * ns + rank[in[i]]], 1u);
+            for (uint32_t i = head + nv * 16 + tid; i < n; i += HT) atomicAdd(&ptot[rank[i ? in[i - 1] : 0u] * ns + rank[in[i]]], 1u);
+            // the segment starts are coded in context 0 (:720-723, with 4 -> nway)
+            for (uint32_t k = 1 + tid; k < nway; k += HT) atomicAdd(&ptot[rank[0] * ns + rank[in[k * seg]]], 1u);
+            uint32_t since = 0;
+            for (uint32_t i0 = 0; i0 < nv; i0 += HT) {
+                const uint32_t i = i0 + tid;
+                if (i < nv) {
+                    const uint4 q = __ldg(v + i);
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                    const uint32_t at = head + i * 16;
+                    uint32_t rc = rank[at ? in[at - 1] : 0u] * ns;   // context of the chunk's first byte
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+#pragma unroll
+                        for (int bb = 0; bb < 4; bb++) {
+                            const uint32_t r = rank[(w[k] >> (8 * bb)) & 0xffu];
+                            mycol[(rc + r) * 32]++;
+                            rc = r * ns;
+                        }
+                    }
+                }
+                since += 16;
+                if (since >= HT_TILE) { hist_fold(cnt, ptot, ns * ns); since = 0; }
+            }
+            hist_fold(cnt, ptot, ns * ns);
+            for (uint32_t k = tid; k < ns * ns; k += HT) S.F1[k] = ptot[k];
+        } else {
+            // the private-counter area doubles as the 96 x 96 atomic table (it is all zeros here)
+            const bool in_smem = ns <= O1_SMEM_NS;
+            uint32_t* P = in_smem ? reinterpret_cast<uint32_t*>(hsm) : S.F1;
+            if (!in_smem) for (uint32_t k = tid; k < ns * ns; k += HT) P[k] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < n; i += HT) {
+                uint32_t c = i ? in[i - 1] : 0u, s = in[i];
+                atomicAdd(&P[rank[c] * ns + rank[s]], 1u);
+            }
+            for (uint32_t k = 1 + tid; k < nway; k += HT) atomicAdd(&P[rank[0] * ns + rank[in[k * seg]]], 1u);
+            __syncthreads();
+            if (in_smem) for (uint32_t k = tid; k < ns * ns; k += HT) { S.F1[k] = P[k]; P[k] = 0; }
+        }
     }
 }
 
@@ -692,24 +763,55 @@ __device__ __forceinline__ uint32_t enc_put(uint32_t x, bool act, const EncSym s
 }
 
 constexpr int ENC_O0_SMEM_PER_GROUP = 256 * 16;                      // EncSym[256]
-constexpr uint32_t ENC_O1_SMEM_NS_32 = 48;                           // order-1 symbols in shared memory up to this ns (36 KB)
-constexpr uint32_t ENC_O1_SMEM_NS_4 = 16;                            // per 4-lane group (4 KB)
 
-template <int NWAY, int ORDER>
-__global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W) {
+// Per-lane backward byte reader of the order-1 loop.  A lane walks its own segment from the end,
+// so a plain byte load per symbol would cost one memory transaction per lane per step; instead
+// a lane pulls the aligned 16-byte line it is in once and shifts bytes out of registers.
+struct ByteSrc {
+    const uint8_t* line;         // aligned line currently held
+    uint32_t w0, w1, w2, w3;     // its bytes; the next byte to hand out is the top byte of w3
+    uint32_t k;                  // bytes left in the window
+    __device__ __forceinline__ void load() {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(line));
+        w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w;
+    }
+    // `end` = one past the first byte to hand out (bytes are handed out at descending addresses)
+    __device__ __forceinline__ void init(const uint8_t* end) {
+        const uint32_t lo = (uint32_t)(reinterpret_cast<uintptr_t>(end) & 15);
+        if (lo == 0) { line = end; k = 0; w0 = w1 = w2 = w3 = 0; return; }
+        line = end - lo;
+        load();                                               // 16-byte aligned: never leaves the page of end[-1]
+        for (uint32_t q = lo; q < 16; q++) {                  // drop the bytes at and above `end`
+            w3 = __funnelshift_l(w2, w3, 8); w2 = __funnelshift_l(w1, w2, 8); w1 = __funnelshift_l(w0, w1, 8); w0 <<= 8;
+        }
+        k = lo;
+    }
+    __device__ __forceinline__ uint32_t get() {
+        if (k == 0) { line -= 16; load(); k = 16; }
+        const uint32_t b = w3 >> 24;
+        w3 = __funnelshift_l(w2, w3, 8); w2 = __funnelshift_l(w1, w2, 8); w1 = __funnelshift_l(w0, w1, 8); w0 <<= 8;
+        k--;
+        return b;
+    }
+};
+
+// Order-1 symbol tables live in shared memory when the alphabet has at most NSCAP symbols; two
+// kernel variants (NSCAP 16: 4 KB per group, many resident warps; NSCAP 48: 36 KB) split the
+// streams between them by alphabet size, larger alphabets read the table from global memory.
+template <int NWAY, int ORDER, int NSCAP>
+__global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t cursor_id, uint32_t ns_lo, uint32_t ns_hi) {
     using EG = EGrp<NWAY>;
     extern __shared__ __align__(16) uint8_t esm[];
     const EG G;
-    constexpr uint32_t SMEM_NS = (NWAY == 32) ? ENC_O1_SMEM_NS_32 : ENC_O1_SMEM_NS_4;
-    constexpr uint32_t PER_GROUP = ORDER ? (SMEM_NS * SMEM_NS * 16 + 256) : ENC_O0_SMEM_PER_GROUP;
+    constexpr uint32_t PER_GROUP = ORDER ? (NSCAP * NSCAP * 16 + 256) : ENC_O0_SMEM_PER_GROUP;
     uint8_t* gsm = esm + G.g * PER_GROUP;
     EncSym* ssym = reinterpret_cast<EncSym*>(gsm);
-    uint8_t* srank = gsm + SMEM_NS * SMEM_NS * 16;                  // order-1 only
-    uint32_t* cursor = &W->next_stream[NWAY == 32][ORDER];
+    uint8_t* srank = gsm + NSCAP * NSCAP * 16;                      // order-1 only
+    uint32_t* cursor = &W->next_misc[cursor_id];
     const uint32_t nstreams = W->nstreams;
 
     for (;;) {
-        // streams are claimed EG::G at a time; those of another nway/order are skipped by predicate
+        // streams are claimed EG::G at a time; those of another nway/order/size class are skipped by predicate
         uint32_t s0 = 0;
         if (lane_id() == 0) s0 = atomicAdd(cursor, (uint32_t)EG::G);
         s0 = __shfl_sync(0xffffffffu, s0, 0);
@@ -718,6 +820,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W) {
         bool act_s = si < nstreams;
         EncStream* S = act_s ? &W->streams[si] : nullptr;
         if (act_s && (S->nway != NWAY || S->order_eff != ORDER || S->n == 0 || S->size == 0xffffffffu)) act_s = false;
+        if (ORDER && act_s && (S->ns <= ns_lo || S->ns > ns_hi)) act_s = false;    // another variant's alphabet class
         if (!__any_sync(0xffffffffu, act_s)) continue;
 
         const uint8_t* in = act_s ? S->src : nullptr;
@@ -731,7 +834,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W) {
             // symbol -> rank
             uint32_t r = 0;
             if (G.glane == 0) for (int s = 0; s < 256; s++) { srank[s] = (uint8_t)r; if (S->F0[s] != 0 || s == 0) r++; }
-            if (ns <= SMEM_NS) for (uint32_t k = G.glane; k < ns * ns; k += NWAY) ssym[k] = S->syms[k];
+            if (ns <= NSCAP) for (uint32_t k = G.glane; k < ns * ns; k += NWAY) ssym[k] = S->syms[k];
             else syms = S->syms;
         }
         __syncwarp();
@@ -751,29 +854,40 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W) {
             }
         } else {
             // state z owns in[z*seg, (z+1)*seg), the last state also the tail; coded last-to-first
-            // with the preceding byte as context, 0 at a segment start (:794-834)
+            // with the preceding byte as context, 0 at a segment start (:794-834).  Lanes with fewer
+            // symbols idle first, so every state finishes on the last step.
             const uint32_t seg = n / NWAY, tail = n - seg * NWAY;
-            const uint32_t steps = act_s ? seg + tail : 0;
-            const uint32_t maxsteps = __reduce_max_sync(0xffffffffu, steps);
-            const uint32_t skip = maxsteps - steps;                  // groups with fewer steps idle first
-            const uint32_t base = G.glane * seg;
-            for (uint32_t k = 0; k < maxsteps; k++) {
-                bool act = false;
-                uint32_t c = 0, sy = 0;
-                if (act_s && k >= skip) {
-                    const uint32_t kk = k - skip;                    // 0 .. steps-1
-                    if (kk < tail) {                                 // tail symbols, last lane only
-                        if (G.glane == NWAY - 1) { uint32_t pos = n - 1 - kk; act = true; sy = in[pos]; c = in[pos - 1]; }
-                    } else {
-                        uint32_t t = seg - 1 - (kk - tail);          // seg-1 .. 0
-                        uint32_t pos = base + t;
-                        act = true; sy = in[pos]; c = t ? in[pos - 1] : 0u;
-                    }
+            const uint32_t my_n = act_s ? seg + ((G.glane == NWAY - 1) ? tail : 0u) : 0u;
+            const uint32_t maxsteps = __reduce_max_sync(0xffffffffu, my_n);
+            const uint32_t minsteps = __reduce_min_sync(0xffffffffu, my_n);
+            const uint32_t idle = maxsteps - my_n;
+            ByteSrc src;
+            src.init(in + (size_t)G.glane * seg + my_n);
+            uint32_t rs = 0;                                         // rank of the symbol to code next
+            if (my_n) rs = srank[src.get()];
+            uint32_t left = my_n;                                    // symbols this lane still has to code
+            uint32_t k = 0;
+            EncSym idle_sym;
+            idle_sym.x_max = 0xffffffffu; idle_sym.rcp_freq = 0; idle_sym.bias = 0; idle_sym.cmpl_shift = 0;
+            for (; k < maxsteps - minsteps; k++) {                   // ragged start: some lanes idle
+                const bool act = k >= idle;
+                EncSym s = idle_sym;
+                if (act) {
+                    const uint32_t rc = (left > 1) ? (uint32_t)srank[src.get()] : (uint32_t)srank[0];
+                    s = syms[rc * ns + rs];
+                    rs = rc; left--;
                 }
-                EncSym s;
-                s.x_max = 0xffffffffu; s.rcp_freq = 0; s.bias = 0; s.cmpl_shift = 0;
-                if (act) s = syms[(uint32_t)srank[c] * ns + srank[sy]];
                 x = enc_put<NWAY>(x, act, s, wp, G);
+            }
+            for (; k + 1 < maxsteps; k++) {                          // every lane active, a context byte exists
+                const uint32_t rc = srank[src.get()];
+                const EncSym s = syms[rc * ns + rs];
+                rs = rc;
+                x = enc_put<NWAY>(x, true, s, wp, G);
+            }
+            if (k < maxsteps && minsteps) {                          // segment starts: context 0
+                const EncSym s = syms[(uint32_t)srank[0] * ns + rs];
+                x = enc_put<NWAY>(x, true, s, wp, G);
             }
         }
         // RansEncFlush (rANS_word.h:104-116): states NWAY-1 .. 0, so state 0 ends lowest
@@ -971,8 +1085,9 @@ template <typename K> int occ_grid(K kernel, int smem, int sms) {
 }
 
 constexpr int SM_O0_32 = ENC_O0_SMEM_PER_GROUP, SM_O0_4 = ENC_O0_SMEM_PER_GROUP * 8;
-constexpr int SM_O1_32 = ENC_O1_SMEM_NS_32 * ENC_O1_SMEM_NS_32 * 16 + 256;
-constexpr int SM_O1_4 = (ENC_O1_SMEM_NS_4 * ENC_O1_SMEM_NS_4 * 16 + 256) * 8;
+constexpr int SM_O1_32_S = 16 * 16 * 16 + 256, SM_O1_32_L = 48 * 48 * 16 + 256;     // small / large alphabet variants
+constexpr int SM_O1_4_S = (16 * 16 * 16 + 256) * 8;                                  // 4-way: small only (larger: global)
+int g_grid_o1_32_s = 0, g_grid_o1_32_l = 0, g_grid_o1_4_s = 0;
 
 }  // namespace
 
@@ -995,10 +1110,12 @@ int encode_init(int device) {
     for (int k = 0; k <= 256; k++) { l10[k] = log((double)(1024 + k)); l12[k] = log((double)(4096 + k)); }
     if (cudaMemcpyToSymbol(c_log10, l10, sizeof(l10)) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(c_log12, l12, sizeof(l12)) != cudaSuccess) return -1;
-    g_grid_enc[0][0] = occ_grid(enc_rans_kernel<4, 0>, SM_O0_4, g_sms_enc);
-    g_grid_enc[0][1] = occ_grid(enc_rans_kernel<4, 1>, SM_O1_4, g_sms_enc);
-    g_grid_enc[1][0] = occ_grid(enc_rans_kernel<32, 0>, SM_O0_32, g_sms_enc);
-    g_grid_enc[1][1] = occ_grid(enc_rans_kernel<32, 1>, SM_O1_32, g_sms_enc);
+    cudaFuncSetAttribute(enc_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM);
+    g_grid_enc[0][0] = occ_grid(enc_rans_kernel<4, 0, 16>, SM_O0_4, g_sms_enc);
+    g_grid_enc[1][0] = occ_grid(enc_rans_kernel<32, 0, 16>, SM_O0_32, g_sms_enc);
+    g_grid_o1_4_s = occ_grid(enc_rans_kernel<4, 1, 16>, SM_O1_4_S, g_sms_enc);
+    g_grid_o1_32_s = occ_grid(enc_rans_kernel<32, 1, 16>, SM_O1_32_S, g_sms_enc);
+    g_grid_o1_32_l = occ_grid(enc_rans_kernel<32, 1, 48>, SM_O1_32_L, g_sms_enc);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1181,13 +1298,16 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     if (any_stripe) { enc_stripe_kernel<<<g, 256, 0, st>>>(dW); launches++; }
     if (any_tr) { enc_transform_kernel<<<g, TT, 0, st>>>(dW); launches++; }
     if (!streams.empty()) {
-        enc_hist_kernel<<<g, HT, 0, st>>>(dW); launches++;
+        enc_hist_kernel<<<g_sms_enc * 3, HT, HIST_SMEM, st>>>(dW); launches++;
         enc_table_kernel<<<g * 2, KT, 0, st>>>(dW); launches++;
         // an order-1 request can fall back to order 0 on the device, so the order-0 kernels always run
-        if (any4[0])  { enc_rans_kernel<4, 0><<<g_grid_enc[0][0], 32, SM_O0_4, st>>>(dW); launches++; }
-        if (any4[1])  { enc_rans_kernel<4, 1><<<g_grid_enc[0][1], 32, SM_O1_4, st>>>(dW); launches++; }
-        if (any32[0]) { enc_rans_kernel<32, 0><<<g_grid_enc[1][0], 32, SM_O0_32, st>>>(dW); launches++; }
-        if (any32[1]) { enc_rans_kernel<32, 1><<<g_grid_enc[1][1], 32, SM_O1_32, st>>>(dW); launches++; }
+        // cursors: next_misc[0..4]; order-1 streams go to the small-alphabet variant (ns <= 16, tables in
+        // shared memory at high occupancy) or the large one (ns > 16: shared up to 48 symbols, else global)
+        if (any4[0])  { enc_rans_kernel<4, 0, 16><<<g_grid_enc[0][0], 32, SM_O0_4, st>>>(dW, 0, 0, 256); launches++; }
+        if (any4[1])  { enc_rans_kernel<4, 1, 16><<<g_grid_o1_4_s, 32, SM_O1_4_S, st>>>(dW, 1, 0, 256); launches++; }
+        if (any32[0]) { enc_rans_kernel<32, 0, 16><<<g_grid_enc[1][0], 32, SM_O0_32, st>>>(dW, 2, 0, 256); launches++; }
+        if (any32[1]) { enc_rans_kernel<32, 1, 16><<<g_grid_o1_32_s, 32, SM_O1_32_S, st>>>(dW, 3, 0, 16); launches++;
+                        enc_rans_kernel<32, 1, 48><<<g_grid_o1_32_l, 32, SM_O1_32_L, st>>>(dW, 4, 16, 256); launches++; }
         enc_finish_kernel<<<g, 256, 0, st>>>(dW); launches++;
     }
     enc_block_kernel<<<g, 256, 0, st>>>(dW, b.out_len, b.status); launches++;
