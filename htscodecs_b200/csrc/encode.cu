@@ -842,15 +842,48 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
         uint8_t* wp = act_s ? S->out + S->cap : nullptr;             // payload grows down from the end
         uint32_t x = 1u << 15;                                       // RansEncInit, rANS_word.h:69-72
         if (ORDER == 0) {
-            // symbol i belongs to state i % NWAY; rows are coded from the last to the first (:442-480)
+            // symbol i belongs to state i % NWAY; rows are coded from the last to the first (:442-480).
+            // The symbol bytes do not depend on the coder state, so they are fetched a batch of rows
+            // ahead (non-coherent loads, free to move above the payload stores) while the serial
+            // state updates of the previous batch run.
             const uint32_t rows = (n + NWAY - 1) / NWAY;
             const uint32_t maxrows = (NWAY == 32) ? rows : __reduce_max_sync(0xffffffffu, rows);
-            for (uint32_t k = 0; k < maxrows; k++) {
-                const bool in_rows = k < rows;
-                const uint32_t pos = in_rows ? (rows - 1 - k) * NWAY + G.glane : 0;
+            // rows of this group that are complete and that every other group of the warp also has
+            const uint32_t full = __reduce_min_sync(0xffffffffu, act_s ? n / NWAY : 0u);
+            uint32_t k = 0;
+            for (; k < maxrows - full; k++) {                        // ragged part (partial last row, shorter groups)
+                const bool in_rows = k + rows >= maxrows;            // groups with fewer rows idle first
+                const uint32_t kk = k - (maxrows - rows);
+                const uint32_t pos = in_rows ? (rows - 1 - kk) * NWAY + G.glane : 0;
                 const bool act = in_rows && pos < n;
-                EncSym s = ssym[act ? in[pos] : 0];
+                EncSym s = ssym[act ? __ldg(in + pos) : 0];
                 x = enc_put<NWAY>(x, act, s, wp, G);
+            }
+            // from here on every lane of the warp codes rows full-1 .. 0 of its stream
+            constexpr int B = 8;
+            const uint8_t* ip = in + G.glane;
+            uint32_t r = full;                                       // rows left
+            uint32_t nb[B];
+#pragma unroll
+            for (int u = 0; u < B; u++) nb[u] = (r > (uint32_t)u) ? __ldg(ip + (size_t)(r - 1 - u) * NWAY) : 0u;
+            while (r >= B) {
+                uint32_t b[B];
+#pragma unroll
+                for (int u = 0; u < B; u++) b[u] = nb[u];
+                r -= B;
+#pragma unroll
+                for (int u = 0; u < B; u++) nb[u] = (r > (uint32_t)u) ? __ldg(ip + (size_t)(r - 1 - u) * NWAY) : 0u;
+                EncSym sy[B];
+#pragma unroll
+                for (int u = 0; u < B; u++) sy[u] = ssym[b[u]];
+#pragma unroll
+                for (int u = 0; u < B; u++) x = enc_put<NWAY>(x, true, sy[u], wp, G);
+            }
+            for (uint32_t u = 0; u < r; u++) {                       // fewer than B rows left (already fetched)
+                uint32_t bsel = nb[0];
+#pragma unroll
+                for (int q = 1; q < B; q++) if (u == (uint32_t)q) bsel = nb[q];
+                x = enc_put<NWAY>(x, true, ssym[bsel], wp, G);
             }
         } else {
             // state z owns in[z*seg, (z+1)*seg), the last state also the tail; coded last-to-first
@@ -907,8 +940,27 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
 // ------------------------------------------------------------------------------------------
 // enc_finish_kernel: one CTA per leaf -- assemble the container (:1231-1342)
 // ------------------------------------------------------------------------------------------
+// CTA-wide copy with arbitrary mutual alignment: 16-byte aligned stores, the source read as
+// aligned 32-bit words and realigned with funnel shifts.  src and dst must not overlap.
 __device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint32_t n) {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+    for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
+    const uint32_t nv = (n - head) / 16;
+    const uint8_t* s0 = src + head;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s0) & 3) * 8;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - (sh >> 3));
+    uint4* dv = reinterpret_cast<uint4*>(dst + head);
+    for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
+        const uint32_t* w = sw + 4 * (size_t)i;
+        uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3];
+        if (sh) {                                            // block-uniform
+            const uint32_t a4 = w[4];                        // inside the source: the chunk ends sh/8 bytes into it
+            a0 = __funnelshift_r(a0, a1, sh); a1 = __funnelshift_r(a1, a2, sh);
+            a2 = __funnelshift_r(a2, a3, sh); a3 = __funnelshift_r(a3, a4, sh);
+        }
+        dv[i] = make_uint4(a0, a1, a2, a3);
+    }
+    for (uint32_t i = head + nv * 16 + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
 __global__ void __launch_bounds__(256) enc_finish_kernel(EncWork* W) {
