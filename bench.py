@@ -153,6 +153,62 @@ def run_reference(args, rank, world):
     }))
 
 
+def path_sweep(ctx, torch, hb, blocks, nblk, reps=3):
+    """Device-resident GB/s (uncompressed) of the other hot-path legs on the same 1 MiB quality
+    blocks: encode and decode x order-0/1 x X_32/4-way.  Decode inputs come from the encoder under
+    test; every leg is checked by a device-side round-trip comparison."""
+    import numpy as np
+    n, distinct = BLOCK, len(blocks)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    d_raw = torch.from_numpy(np.concatenate([blocks[i % distinct] for i in range(nblk)])).cuda()
+    raw_off = torch.arange(nblk, dtype=torch.int64, device="cuda") * n
+    raw_len = torch.full((nblk,), n, dtype=torch.int32, device="cuda")
+    status = torch.zeros(nblk, dtype=torch.int32, device="cuda")
+    d_out = torch.empty(nblk * n, dtype=torch.uint8, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = {}
+    for name, f in (("o0_x32", 4), ("o1_x32", 5), ("o0_4way", 0), ("o1_4way", 1)):
+        cap = (hb.rans_compress_bound_4x16(n, f) + 15) // 16 * 16
+        d_comp = torch.empty(nblk * cap, dtype=torch.uint8, device="cuda")
+        comp_off = torch.arange(nblk, dtype=torch.int64, device="cuda") * cap
+        comp_len = torch.full((nblk,), cap, dtype=torch.int32, device="cuda")
+        order = torch.full((nblk,), f, dtype=torch.int32, device="cuda")
+        out_len = torch.full((nblk,), n, dtype=torch.int32, device="cuda")
+
+        def enc():
+            comp_len.fill_(cap)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            ctx.compress_batch_dev(nblk, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=False)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+
+        enc()
+        assert int((status != 0).sum()) == 0, "encode failed"
+        t_enc = min(enc() for _ in range(reps))
+        in_len = comp_len.clone()
+        csz = int(in_len.to(torch.int64).sum())
+
+        def dec():
+            out_len.fill_(n)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, sync=False)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+
+        dec()
+        assert int((status != 0).sum()) == 0 and torch.equal(d_out, d_raw), "round trip mismatch"
+        t_dec = min(dec() for _ in range(reps))
+        gb = nblk * n / 1e9
+        res[name] = {"encode_GBs": round(gb / (t_enc * 1e-3), 1), "decode_GBs": round(gb / (t_dec * 1e-3), 1),
+                     "ratio": round(csz / (nblk * n), 4)}
+        del d_comp
+    return res
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import htscodecs_b200 as hb
@@ -266,7 +322,19 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = world * u_bytes / e2e_s / 1e9
+    # host-side gather of the per-block results of every rank (the only cross-rank step of the path)
+    from htscodecs_b200 import shard
+    ranges = shard.partition_blocks([BLOCK] * (world * nblk), world)
+    assert ranges[rank] == (rank * nblk, (rank + 1) * nblk)
+    all_len, all_status = shard.gather_results(d_out_len.cpu().numpy().view(np.uint32), d_status.cpu().numpy(),
+                                               ranges, rank, world, dist, torch.device("cuda", local_rank))
+    assert (all_status == 0).all() and (all_len == BLOCK).all(), "a rank reported decode errors"
     clocks = sampler.stop()
+    paths = None
+    if rank == 0 and not args.skip_paths:
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        paths = path_sweep(ctx, torch, hb, blocks, min(nblk, 4096))
 
     if rank != 0:
         if dist is not None:
@@ -313,6 +381,7 @@ def run_ours(args, rank, world, local_rank):
                      "note": "algorithmic bytes = compressed read + uncompressed write per step; duration = "
                              "CUDA-event step time (plan_kernel + decode kernel), so frac is a lower bound"},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": cpu_kind, "sample": cpu_sample},
+        "paths": paths,
     }))
     if dist is not None:
         dist.destroy_process_group()
@@ -328,6 +397,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=64, help="distinct blocks generated, tiled to --blocks")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the CPU baseline leg")
+    ap.add_argument("--skip-paths", action="store_true", help="skip the extra encode / order-1 / 4-way legs")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget for the reference leg")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
