@@ -365,7 +365,7 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
                 if (f & F_STRIPE) { kinds |= ~((1u << JK_R8_O0) | (1u << JK_R8_O1)); post |= 7u; continue; }
                 bool x32 = f & F_X32;
                 if (f & F_CAT) kinds |= 1u << JK_COPY;
-                else if (f & F_ORDER1) kinds |= (1u << (x32 ? JK_O1_32 : JK_O1_4)) | (1u << JK_O0_4);   // O0_4: compressed tables
+                else if (f & F_ORDER1) kinds |= (x32 ? (1u << JK_O1_32) | (1u << JK_O1_32S) : (1u << JK_O1_4)) | (1u << JK_O0_4);   // O0_4: compressed tables
                 else kinds |= 1u << (x32 ? JK_O0_32 : JK_O0_4);
                 if (f & F_RLE) { post |= 1u; kinds |= 1u << (x32 ? JK_O0_32 : JK_O0_4); }
                 if (f & F_PACK) post |= 2u;

@@ -22,7 +22,9 @@ enum : int32_t {
 
 // decode job kinds: one persistent kernel instantiation per kind
 enum JobKind : uint32_t {
-    JK_O0_4 = 0, JK_O0_32, JK_O1_4, JK_O1_32, JK_R8_O0, JK_R8_O1, JK_COPY, JK_NKINDS
+    JK_O0_4 = 0, JK_O0_32, JK_O1_4, JK_O1_32, JK_R8_O0, JK_R8_O1, JK_COPY,
+    JK_O1_32S,             // X_32 order-1 streams with a small alphabet: the high-occupancy kernel variant
+    JK_NKINDS
 };
 
 struct DecJob {

@@ -74,6 +74,54 @@ __device__ int unpack_meta(const uint8_t* d, uint32_t len, uint8_t* map, uint32_
     return c < ns ? 0 : (int)j;
 }
 
+// compact order-1 tables (see the order-1 section): bytes needed for `ns` symbols, and the table
+// budget of the small-alphabet X_32 kernel variant
+__host__ __device__ constexpr uint32_t o1_compact_bytes(uint32_t ns) { return ns * 64 + ns * 4 * (ns + 3); }
+constexpr uint32_t O1_SMALL_TAB = 4608;
+
+// bounded reader over global-memory bytes
+struct GRd {
+    const uint8_t* p; const uint8_t* end;
+    __device__ __forceinline__ bool more() const { return p < end; }
+    __device__ __forceinline__ uint32_t peek() const { return p < end ? *p : 0u; }
+    __device__ __forceinline__ uint32_t get() { uint32_t v = peek(); p++; return v; }
+    __device__ __forceinline__ uint32_t varint() {
+        uint32_t x = 0;
+        if (p >= end) return 0;
+        for (;;) {
+            uint32_t c = get();
+            x = (x << 7) | (c & 0x7f);
+            if (!(c & 0x80) || p >= end) break;
+        }
+        return x;
+    }
+};
+
+// decode_alphabet (rANS_static4x16pr.c:208-255) as a counter: number of symbols listed (an upper
+// bound on distinct symbols; exact for streams whose list is strictly increasing, as written by
+// the encoder).  Returns false when the bytes run out.
+__device__ bool count_alphabet(GRd& r, uint32_t* ns) {
+    if (!r.more()) return false;
+    uint32_t run = 0, j = r.get(), n = 0;
+    do {
+        n++;
+        if (!r.more()) return false;
+        if (!run && j + 1 == r.peek()) {
+            r.get();
+            if (!r.more()) return false;
+            j++;
+            run = r.get();
+        } else if (run) {
+            run--;
+            if (++j > 255) return false;
+        } else {
+            j = r.get();
+        }
+    } while (j && r.more() && n < 512);
+    *ns = n;
+    return true;
+}
+
 // One non-striped container, rANS_static4x16pr.c:1435-1629, turned into a plan.  `cap` is the
 // caller's capacity (the exact size for X_NOSZ); expect != 0xffffffff marks a stripe sub-stream
 // that must produce exactly that many bytes.  `ci` is the chain slot reserved by the caller.
@@ -172,7 +220,13 @@ __device__ int32_t plan_chain(DecWork* W, const uint8_t* in, uint32_t in_len, ui
                 if (!j.aux) return ST_ARENA;
                 if (!push_job(W, JK_O0_4, make_job(p, csz, j.aux, usz, blk))) return ST_ARENA;
             }
-            if (!push_job(W, x32 ? JK_O1_32 : JK_O1_4, j)) return ST_ARENA;
+            uint32_t kind = x32 ? JK_O1_32 : JK_O1_4;
+            if (x32 && !j.aux && in_len > 1) {                       // uncompressed table: count the alphabet to pick
+                GRd ar{in + 1, end};                                 // the kernel variant (small alphabets run at
+                uint32_t ns = 0;                                     // twice the occupancy)
+                if (count_alphabet(ar, &ns) && o1_compact_bytes(ns) <= O1_SMALL_TAB) kind = JK_O1_32S;
+            }
+            if (!push_job(W, kind, j)) return ST_ARENA;
         } else {
             if (!push_job(W, x32 ? JK_O0_32 : JK_O0_4, j)) return ST_ARENA;
         }
@@ -439,24 +493,6 @@ struct SRd {
     }
 };
 
-// bounded reader over global-memory bytes
-struct GRd {
-    const uint8_t* p; const uint8_t* end;
-    __device__ __forceinline__ bool more() const { return p < end; }
-    __device__ __forceinline__ uint32_t peek() const { return p < end ? *p : 0u; }
-    __device__ __forceinline__ uint32_t get() { uint32_t v = peek(); p++; return v; }
-    __device__ __forceinline__ uint32_t varint() {
-        uint32_t x = 0;
-        if (p >= end) return 0;
-        for (;;) {
-            uint32_t c = get();
-            x = (x << 7) | (c & 0x7f);
-            if (!(c & 0x80) || p >= end) break;
-        }
-        return x;
-    }
-};
-
 // decode_alphabet (rANS_static4x16pr.c:208-255): marks present symbols by storing `mark` into
 // the byte table at shared address `tab`.  Returns false when the bytes run out.
 template <typename RD>
@@ -709,12 +745,16 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
 //    rows[ctx][m] -> rank, fc[ctx * ns + rank] = F << 16 | C, as in the reference
 //    (rANS_static4x16pr.c:922-930).
 //
-// Shared memory of one group: [0,256) rank -> symbol, [256,512) symbol -> rank, [512,1536)
-// frequency scratch, the word ring, then TAB bytes of compact tables.
-template <int NWAY> struct O1Smem {
-    static constexpr int UNRANK = 0, RANK = 256, FTMP = 512, RINGO = 1536;
-    static constexpr int TABO = 1536 + GroupCfg<NWAY>::RING;
-    static constexpr int TAB = (NWAY == 32) ? 11968 : 3072;          // X_32: 15 warps / SM; 4-way: 40 groups / SM
+// Shared memory of one group: [0,256) rank -> symbol, [256,512) symbol -> rank, frequency
+// scratch, the word ring, then TAB bytes of compact tables.
+template <int NWAY, bool SMALL = false> struct O1Smem {
+    static constexpr int UNRANK = 0, RANK = 256;
+    // X_32: the frequency scratch is only live during set-up and shares its 1 KB with the word ring
+    static constexpr int FTMP = 512, RINGO = (NWAY == 32) ? 512 : 1536;
+    static constexpr int TABO = RINGO + GroupCfg<NWAY>::RING;
+    // X_32: 12992 B (<= 48 symbols, 15 warps / SM) or, SMALL, 4608 B (<= 25 symbols, 32 warps / SM);
+    // 4-way: 3072 B per group (<= 19 symbols, 40 groups / SM)
+    static constexpr int TAB = (NWAY == 32) ? (SMALL ? (int)O1_SMALL_TAB : 12992) : 3072;
     static constexpr int STRIDE = TABO + TAB;                        // multiple of 16
     static constexpr int TOTAL = STRIDE * GroupCfg<NWAY>::G;
 };
@@ -806,10 +846,10 @@ __device__ bool build_o1_row_lut(const Grp<NWAY>& G, uint32_t F, const O1Tables&
 }
 
 // Per-group order-1 set-up.  Returns 0 ok, ST_FORMAT or ST_ARENA (group-uniform).
-template <int NWAY, bool BYTE>
+template <int NWAY, bool BYTE, bool SMALL>
 __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, uint8_t* gsm, uint32_t base,
                             O1Tables* Tout, uint32_t* R, const uint8_t** first_word, uint32_t* ctx0) {
-    using S = O1Smem<NWAY>;
+    using S = O1Smem<NWAY, SMALL>;
     const uint32_t unrank = base + S::UNRANK, rank = base + S::RANK, Ftmp = base + S::FTMP, tabs = base + S::TABO;
     const uint8_t* in_end = job.in + job.in_len;
 
@@ -863,7 +903,7 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     T.g_rows = nullptr; T.g_fc = nullptr;
     T.rstride = 4 * (ns + 3);
     T.coarse = tabs; T.rows = tabs + ns * 64;
-    T.compact = (!BYTE && ns * 64 + ns * T.rstride <= (uint32_t)S::TAB) ? 1u : 0u;
+    T.compact = (!BYTE && o1_compact_bytes(ns) <= (uint32_t)S::TAB) ? 1u : 0u;
     if (T.compact) {
         for (uint32_t k = G.glane; k < ns * 16; k += NWAY) sts_u32(T.coarse + 4 * k, 0u);
         for (uint32_t k = G.glane; k < ns * (ns + 3); k += NWAY) sts_u32(T.rows + 4 * k, O1_SENTINEL);
@@ -1046,10 +1086,10 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
     sink.finish();
 }
 
-template <int NWAY, bool BYTE>
-__global__ void __launch_bounds__(32) dec_o1_kernel(DecWork* W, int32_t* status, uint32_t kind) {
+template <int NWAY, bool BYTE, bool SMALL>
+__global__ void __launch_bounds__(32, SMALL ? 28 : 1) dec_o1_kernel(DecWork* W, int32_t* status, uint32_t kind) {
     using C = GroupCfg<NWAY>;
-    using S = O1Smem<NWAY>;
+    using S = O1Smem<NWAY, SMALL>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const Grp<NWAY> G;
     uint8_t* gsm = smem_raw + G.g * S::STRIDE;
@@ -1076,7 +1116,7 @@ __global__ void __launch_bounds__(32) dec_o1_kernel(DecWork* W, int32_t* status,
             job = jobs[ji];
             // an order-0 job may have been expanding this stream's table: skip if that (or anything else) failed
             int32_t st = (job.aux && status[job.blk] != ST_OK) ? ST_FORMAT
-                                                               : o1_setup<NWAY, BYTE>(G, W, job, gsm, base, &T, &R, &first_word, &ctx0);
+                                                               : o1_setup<NWAY, BYTE, SMALL>(G, W, job, gsm, base, &T, &R, &first_word, &ctx0);
             ok = st == ST_OK;
             if (!ok && G.glane == 0) set_status(status, job.blk, st);
         }
@@ -1329,9 +1369,10 @@ int decode_init(int device) {
     g_grid[JK_O0_32] = persistent_grid(dec_o0_kernel<32, false>, O0Smem<32>::TOTAL, 32, g_sms);
     g_grid[JK_O0_4]  = persistent_grid(dec_o0_kernel<4, false>,  O0Smem<4>::TOTAL, 32, g_sms);
     g_grid[JK_R8_O0] = persistent_grid(dec_o0_kernel<4, true>,   O0Smem<4>::TOTAL, 32, g_sms);
-    g_grid[JK_O1_32] = persistent_grid(dec_o1_kernel<32, false>, O1Smem<32>::TOTAL, 32, g_sms);
-    g_grid[JK_O1_4]  = persistent_grid(dec_o1_kernel<4, false>,  O1Smem<4>::TOTAL, 32, g_sms);
-    g_grid[JK_R8_O1] = persistent_grid(dec_o1_kernel<4, true>,   O1Smem<4>::TOTAL, 32, g_sms);
+    g_grid[JK_O1_32] = persistent_grid(dec_o1_kernel<32, false, false>, O1Smem<32>::TOTAL, 32, g_sms);
+    g_grid[JK_O1_32S] = persistent_grid(dec_o1_kernel<32, false, true>, O1Smem<32, true>::TOTAL, 32, g_sms);
+    g_grid[JK_O1_4]  = persistent_grid(dec_o1_kernel<4, false, false>,  O1Smem<4>::TOTAL, 32, g_sms);
+    g_grid[JK_R8_O1] = persistent_grid(dec_o1_kernel<4, true, false>,   O1Smem<4>::TOTAL, 32, g_sms);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1351,10 +1392,11 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     auto want = [&](uint32_t k) { return (b.kinds >> k) & 1u; };
     if (want(JK_O0_32)) { dec_o0_kernel<32, false><<<g_grid[JK_O0_32], 32, O0Smem<32>::TOTAL, st>>>(b.work, b.status, JK_O0_32); launches++; }
     if (want(JK_O0_4))  { dec_o0_kernel<4, false><<<g_grid[JK_O0_4], 32, O0Smem<4>::TOTAL, st>>>(b.work, b.status, JK_O0_4); launches++; }
-    if (want(JK_O1_32)) { dec_o1_kernel<32, false><<<g_grid[JK_O1_32], 32, O1Smem<32>::TOTAL, st>>>(b.work, b.status, JK_O1_32); launches++; }
-    if (want(JK_O1_4))  { dec_o1_kernel<4, false><<<g_grid[JK_O1_4], 32, O1Smem<4>::TOTAL, st>>>(b.work, b.status, JK_O1_4); launches++; }
+    if (want(JK_O1_32S)) { dec_o1_kernel<32, false, true><<<g_grid[JK_O1_32S], 32, O1Smem<32, true>::TOTAL, st>>>(b.work, b.status, JK_O1_32S); launches++; }
+    if (want(JK_O1_32)) { dec_o1_kernel<32, false, false><<<g_grid[JK_O1_32], 32, O1Smem<32>::TOTAL, st>>>(b.work, b.status, JK_O1_32); launches++; }
+    if (want(JK_O1_4))  { dec_o1_kernel<4, false, false><<<g_grid[JK_O1_4], 32, O1Smem<4>::TOTAL, st>>>(b.work, b.status, JK_O1_4); launches++; }
     if (want(JK_R8_O0)) { dec_o0_kernel<4, true><<<g_grid[JK_R8_O0], 32, O0Smem<4>::TOTAL, st>>>(b.work, b.status, JK_R8_O0); launches++; }
-    if (want(JK_R8_O1)) { dec_o1_kernel<4, true><<<g_grid[JK_R8_O1], 32, O1Smem<4>::TOTAL, st>>>(b.work, b.status, JK_R8_O1); launches++; }
+    if (want(JK_R8_O1)) { dec_o1_kernel<4, true, false><<<g_grid[JK_R8_O1], 32, O1Smem<4>::TOTAL, st>>>(b.work, b.status, JK_R8_O1); launches++; }
     if (want(JK_COPY))  { copy_kernel<<<g_sms * 4, 256, 0, st>>>(b.work); launches++; }
     if (b.post & 1u) { rle_kernel<<<g_sms * 4, RLE_T, 0, st>>>(b.work, b.status, b.out_len); launches++; }
     if (b.post & 2u) { unpack_kernel<<<g_sms * 4, 256, 0, st>>>(b.work, b.status, b.out_len); launches++; }
