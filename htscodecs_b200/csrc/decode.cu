@@ -734,8 +734,8 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
 //
 //  * compact (shared memory; Nx16 streams whose alphabet fits).  Per context a row of packed
 //    entries, one per symbol of non-zero frequency, in cumulative order,
-//        entry = (C + F - 1) | (F - 1) << 12 | rank << 24
-//    and a 64-bucket coarse index: coarse[ctx][m >> (shift - 6)] = index of the entry holding
+//        entry = (C + F - 1) << 20 | (F - 1) << 8 | rank
+//    preceded by a 64-bucket coarse index: coarse[m >> (shift - 6)] = index of the entry holding
 //    the bucket's first slot.  A lookup reads the coarse byte and three consecutive entries and
 //    steps forward while m lies beyond an entry's last slot (a fourth or later entry inside one
 //    bucket is reached by a short scan; rows end in sentinels whose last slot is 0xfff).  This
@@ -758,12 +758,12 @@ template <int NWAY, bool SMALL = false> struct O1Smem {
     static constexpr int STRIDE = TABO + TAB;                        // multiple of 16
     static constexpr int TOTAL = STRIDE * GroupCfg<NWAY>::G;
 };
-constexpr uint32_t O1_SENTINEL = 0x00ffffffu;                        // last slot 0xfff, F 4096, rank 0
+constexpr uint32_t O1_SENTINEL = 0xffffff00u;                        // last slot 0xfff, F 4096, rank 0
 
 struct O1Tables {
     uint32_t compact;       // 1: compact form in shared memory
-    uint32_t coarse, rows;  // compact: shared addresses
-    uint32_t rstride;       // compact: bytes per row, 4 * (ns + 3)
+    uint32_t tabs;          // compact: shared address of context 0's block [64 B coarse | 4 * (ns + 3) B entries]
+    uint32_t bstride;       // compact: bytes per context block
     uint8_t* g_rows;        // LUT form
     uint32_t* g_fc;
     uint32_t ns, shift;
@@ -791,14 +791,14 @@ __device__ bool build_o1_row_compact(const Grp<NWAY>& G, uint32_t F, const O1Tab
     uint32_t c = G.exscan(bad ? 2 * M : mine, &total);
     uint32_t idx = G.exscan(nz, &nzt);
     if (total != M) return false;
-    const uint32_t row = T.rows + ctx * T.rstride, crs = T.coarse + ctx * 64;
+    const uint32_t crs = T.tabs + ctx * T.bstride, row = crs + 64;
     for (uint32_t k = 0; k < K; k++) {
         const uint32_t r = r0 + k;
         if (r >= ns) break;
         const uint32_t f = lds_u32(F + 4 * r) << sh;
         if (!f) continue;
         const uint32_t last = c + f - 1;
-        sts_u32(row + 4 * idx, last | ((f - 1) << 12) | (r << 24));
+        sts_u32(row + 4 * idx, (last << 20) | ((f - 1) << 8) | r);
         for (uint32_t q = (c + (1u << bs) - 1) >> bs; q <= (last >> bs); q++) sts_u8(crs + q, idx);
         idx++;
         c += f;
@@ -901,12 +901,12 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     O1Tables T;
     T.ns = ns; T.shift = shift;
     T.g_rows = nullptr; T.g_fc = nullptr;
-    T.rstride = 4 * (ns + 3);
-    T.coarse = tabs; T.rows = tabs + ns * 64;
+    T.bstride = 64 + 4 * (ns + 3);
+    T.tabs = tabs;
     T.compact = (!BYTE && o1_compact_bytes(ns) <= (uint32_t)S::TAB) ? 1u : 0u;
     if (T.compact) {
-        for (uint32_t k = G.glane; k < ns * 16; k += NWAY) sts_u32(T.coarse + 4 * k, 0u);
-        for (uint32_t k = G.glane; k < ns * (ns + 3); k += NWAY) sts_u32(T.rows + 4 * k, O1_SENTINEL);
+        for (uint32_t k = G.glane; k < ns * (T.bstride / 4); k += NWAY)     // coarse: 0, entries: sentinels
+            sts_u32(tabs + 4 * k, (k % (T.bstride / 4)) < 16 ? 0u : O1_SENTINEL);
     } else {
         const uint64_t rows_bytes = ((uint64_t)ns * M + 15) & ~15ull;
         uint8_t* a = nullptr;
@@ -1022,37 +1022,52 @@ struct ByteSink {
             line += 16; k = 0;
         }
     }
+    // four bytes at once (oldest in the low byte); requires k % 4 == 0
+    __device__ __forceinline__ void put4(uint32_t v) {
+        w0 = w1; w1 = w2; w2 = w3; w3 = v;
+        k += 4;
+        if (k == 16) {
+            if (skip == 0) *reinterpret_cast<uint4*>(line) = make_uint4(w0, w1, w2, w3);
+            else { sink_drain(line, 16, skip, w0, w1, w2, w3); skip = 0; }
+            line += 16; k = 0;
+        }
+    }
     __device__ __forceinline__ void finish() { if (k > skip) sink_drain(line, k, skip, w0, w1, w2, w3); }
 };
 
-// One decode step of a lane (rANS_static4x16pr.c:1033-1047 / rANS_static.c:850-878): returns the
-// decoded rank and updates R.  COMPACT: the warp holds compact tables only (no per-step test).
+// One decode step of a lane (rANS_static4x16pr.c:1033-1047 / rANS_static.c:850-878): updates R
+// and the lane's context `cs` (COMPACT: shared address of the context's table block; LUT form:
+// the rank) and returns the decoded rank.  COMPACT: the warp holds compact tables only.
 template <bool COMPACT>
-__device__ __forceinline__ uint32_t o1_symbol(uint32_t& R, uint32_t ctx, const O1Tables& T, uint32_t mask) {
+__device__ __forceinline__ uint32_t o1_symbol(uint32_t& R, uint32_t& cs, const O1Tables& T, uint32_t mask) {
     const uint32_t m = R & mask;
     if (COMPACT || T.compact) {
-        const uint32_t ci = lds_u8(T.coarse + ctx * 64 + (m >> (T.shift - 6)));
-        uint32_t ea = T.rows + ctx * T.rstride + 4 * ci;
+        const uint32_t blk = COMPACT ? cs : T.tabs + cs * T.bstride;
+        const uint32_t ci = lds_u8(blk + (m >> (T.shift - 6)));
+        uint32_t ea = blk + 64 + 4 * ci;
         const uint32_t e0 = lds_u32(ea), e1 = lds_u32(ea + 4), e2 = lds_u32(ea + 8);
-        const bool a = m > (e0 & 0xfffu), b = m > (e1 & 0xfffu);
-        uint32_t e = b ? e2 : (a ? e1 : e0);
-        if (b && m > (e2 & 0xfffu)) {                        // >= 4 symbols share the bucket: scan on (sentinel-bounded)
+        const uint32_t mk = m << 20;                         // mk > e  <=>  m > last slot of e (top 12 bits)
+        uint32_t e = (mk > e1) ? e2 : ((mk > e0) ? e1 : e0);
+        if (mk > e) {                                        // >= 4 symbols share the bucket: scan on (sentinel-bounded)
             ea += 12;
-            do { e = lds_u32(ea); ea += 4; } while (m > (e & 0xfffu));
+            do { e = lds_u32(ea); ea += 4; } while (mk > e);
         }
-        const uint32_t fm1 = (e >> 12) & 0xfffu;
-        R = (fm1 + 1u) * (R >> T.shift) + m - ((e & 0xfffu) - fm1);
-        return e >> 24;
+        const uint32_t fm1 = (e >> 8) & 0xfffu, r = e & 0xffu;
+        R = (fm1 + 1u) * (R >> T.shift) + m - ((e >> 20) - fm1);
+        cs = COMPACT ? T.tabs + r * T.bstride : r;
+        return r;
     }
-    uint32_t sr = T.g_rows[(size_t)ctx * (mask + 1u) + m];
+    uint32_t sr = T.g_rows[(size_t)cs * (mask + 1u) + m];
     sr = min(sr, T.ns - 1u);                                 // rows of never-seen contexts are uninitialised
-    const uint32_t e = T.g_fc[ctx * T.ns + sr];
+    const uint32_t e = T.g_fc[cs * T.ns + sr];
     R = (e >> 16) * (R >> T.shift) + m - (e & 0xffffu);
+    cs = sr;
     return sr;
 }
 
 // `minit` (warp-uniform) = steps for which every lane of the warp is active; they run four to a
-// ring check.
+// ring check and, when every lane's segment starts 4-byte aligned (AL4, warp-uniform), four
+// symbols to one sink operation.
 template <int NWAY, bool BYTE, bool ALIGNED, bool COMPACT>
 __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const O1Tables T, uint32_t unrank,
                                         uint32_t ctx0, uint8_t* out, uint32_t seg, uint32_t tail, uint32_t minit,
@@ -1062,23 +1077,39 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
     const uint32_t mine = seg + ((G.glane == NWAY - 1) ? tail : 0u);   // symbols this lane decodes
     const uint32_t group_steps = seg + tail;
     ByteSink sink;
-    sink.init(out + (size_t)G.glane * seg);
-    uint32_t ctx = ctx0;
+    uint8_t* const op0 = out + (size_t)G.glane * seg;
+    sink.init(op0);
+    uint32_t cs = COMPACT ? T.tabs + ctx0 * T.bstride : ctx0;
     uint32_t i = 0;
-    for (; i + 4 <= minit; i += 4) {
+    const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(op0) & 3) == 0);
+    if (al4) {
+        for (; i + 4 <= minit; i += 4) {
+            uint32_t pack = 0;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            ctx = o1_symbol<COMPACT>(R, ctx, T, mask);
-            sink.put(lds_u8(unrank + ctx));
-            R = renorm_step<NWAY, BYTE, ALIGNED>(R, true, ring, lt, G.gshift);
+            for (int u = 0; u < 4; u++) {
+                const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
+                pack |= lds_u8(unrank + r) << (8 * u);
+                R = renorm_step<NWAY, BYTE, ALIGNED>(R, true, ring, lt, G.gshift);
+            }
+            sink.put4(pack);
+            ring.advance(G.glane, true);
         }
-        ring.advance(G.glane, true);
+    } else {
+        for (; i + 4 <= minit; i += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
+                sink.put(lds_u8(unrank + r));
+                R = renorm_step<NWAY, BYTE, ALIGNED>(R, true, ring, lt, G.gshift);
+            }
+            ring.advance(G.glane, true);
+        }
     }
     for (; i < maxit; i++) {
         const bool act = i < mine;
         if (act) {
-            ctx = o1_symbol<COMPACT>(R, ctx, T, mask);
-            sink.put(lds_u8(unrank + ctx));
+            const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
+            sink.put(lds_u8(unrank + r));
         }
         R = renorm_step<NWAY, BYTE, ALIGNED>(R, act, ring, lt, G.gshift);
         ring.advance(G.glane, i < group_steps);
@@ -1107,7 +1138,7 @@ __global__ void __launch_bounds__(32, SMALL ? 28 : 1) dec_o1_kernel(DecWork* W, 
         const bool active = ji < njobs;
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         O1Tables T;
-        T.compact = 1; T.coarse = T.rows = base + S::TABO; T.rstride = 0;
+        T.compact = 1; T.tabs = base + S::TABO; T.bstride = 0;
         T.g_rows = nullptr; T.g_fc = nullptr; T.ns = 1; T.shift = 12;
         uint32_t R = 0, ctx0 = 0;
         const uint8_t* first_word = nullptr;
