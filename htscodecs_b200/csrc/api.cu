@@ -221,7 +221,8 @@ static int dec_enqueue(hts_b200_ctx* ctx, DecSlot& s, const DecodeBatch& b, cuda
 static bool dec_needs_retry(DecSlot& s, size_t* arena_bytes) {
     const DecWork& r = s.h_work.p[1];
     bool retry = false;
-    if (r.arena_used > r.arena_cap) { *arena_bytes = (size_t)(r.arena_used + r.arena_used / 4 + (1 << 20)); retry = true; }
+    // blocks that found the arena full stopped asking, so the reported need is a lower bound: over-provision
+    if (r.arena_used > r.arena_cap) { *arena_bytes = (size_t)(2 * r.arena_used + (16 << 20)); retry = true; }
     if (r.overflow) {
         uint32_t mj = 0;
         for (int k = 0; k < JK_NKINDS; k++) mj = std::max(mj, r.njobs[k]);
@@ -246,7 +247,7 @@ extern "C" int hts_b200_uncompress_batch_dev(hts_b200_ctx* ctx, int nblk, const 
     b.work = nullptr; b.hdr = nullptr; b.in_base = in_base; b.in_off = in_off; b.in_len = in_len;
     b.out_base = out_base; b.out_off = out_off; b.out_len = out_len; b.status = status; b.method = method;
     b.nblk = nblk; b.kinds = method ? ~0u : ~((1u << JK_R8_O0) | (1u << JK_R8_O1)); b.post = 7u;
-    for (int attempt = 0; attempt < 4; attempt++) {
+    for (int attempt = 0; attempt < 8; attempt++) {
         if (dec_prepare(ctx, s, nblk, arena_bytes)) return -1;
         if (sync) {
             if (attempt == 0) CK(cudaMemcpyAsync(s.cap_save.p, out_len, 4 * (size_t)nblk, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -423,7 +424,7 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
         if (collect_chunk(k, S)) return -1;
     }
     // ---- rare: chunks whose scratch overflowed are redone one at a time with the grown arena
-    for (int attempt = 0; !redo.empty() && attempt < 3; attempt++) {
+    for (int attempt = 0; !redo.empty() && attempt < 8; attempt++) {
         std::vector<int> again;
         again.swap(redo);
         for (int k : again) {

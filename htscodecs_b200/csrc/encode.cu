@@ -531,6 +531,39 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
 }
 
 // ------------------------------------------------------------------------------------------
+// lane groups and the encoder step (shared by enc_table_kernel's nested coder and enc_rans_kernel)
+// ------------------------------------------------------------------------------------------
+template <int NWAY> struct EGrp {
+    static constexpr int G = 32 / NWAY;
+    static constexpr uint32_t GM = (NWAY == 32) ? 0xffffffffu : ((1u << NWAY) - 1u);
+    uint32_t g, glane, gshift, gmask;
+    __device__ __forceinline__ EGrp() {
+        uint32_t lane = lane_id();
+        g = lane / NWAY; glane = lane % NWAY; gshift = g * NWAY; gmask = GM << gshift;
+    }
+};
+
+// RansEncPutSymbol (rANS_word.h:281-321) for all lanes of the warp at once.  `wp` is the group's
+// write pointer (moves down); emitting lanes store their low 16 bits in descending lane order.
+template <int NWAY>
+__device__ __forceinline__ uint32_t enc_put(uint32_t x, bool act, const EncSym s, uint8_t*& wp, const EGrp<NWAY>& G) {
+    const bool emit = act && x >= s.x_max;
+    const uint32_t m = (__ballot_sync(0xffffffffu, emit) >> G.gshift) & EGrp<NWAY>::GM;
+    if (emit) {
+        const uint32_t above = __popc((m >> G.glane) >> 1);          // emitting lanes with a higher index write first
+        uint8_t* p = wp - 2 * (above + 1);
+        *reinterpret_cast<uint16_t*>(p) = (uint16_t)x;
+        x >>= 16;
+    }
+    wp -= 2 * __popc(m);
+    if (act) {
+        const uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift >> 16);
+        x = x + s.bias + q * (s.cmpl_shift & 0xffffu);
+    }
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------
 // enc_table_kernel: one CTA (128 threads) per stream
 // ------------------------------------------------------------------------------------------
 constexpr int KT = 128;
@@ -553,27 +586,59 @@ __device__ int build_o0_tables_enc(uint32_t* F, uint32_t n, uint8_t* tab, EncSym
     return 0;
 }
 
-// One-thread rANS 4x16 order-0 encode of a short buffer (the order-1 table, :767-780).
-// F/syms are scratch (256 entries each); returns the stream length written to out, or 0.
-__device__ uint32_t nested_o0_encode(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, uint32_t* F, EncSym* syms) {
-    for (int j = 0; j < 256; j++) F[j] = 0;
-    for (uint32_t i = 0; i < n; i++) F[in[i]]++;
-    uint32_t tab = 0;
-    if (build_o0_tables_enc(F, n, out, syms, &tab) < 0) return 0;
-    uint8_t* end = out + (cap & ~1u);
-    uint8_t* p = end;
-    uint32_t R[4] = {1u << 15, 1u << 15, 1u << 15, 1u << 15};
-    for (uint32_t i = n; i-- > 0;) {
-        const EncSym s = syms[in[i]];
-        uint32_t x = R[i & 3];
-        if (x >= s.x_max) { p -= 2; p[0] = (uint8_t)x; p[1] = (uint8_t)(x >> 8); x >>= 16; }
-        uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift >> 16);
-        R[i & 3] = x + s.bias + q * (s.cmpl_shift & 0xffffu);
+// rANS 4x16 order-0 encode of the serialised order-1 table (:767-780) by one CTA: histogram by all
+// threads, table by thread 0, the 4-way coder by lanes 0-3 of warp 0 (lane = state).  hist/syms
+// are shared scratch (256 entries each).  Returns the stream length written to out (0 = failed);
+// the value is CTA-uniform.
+__device__ uint32_t nested_o0_encode(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, uint32_t* hist,
+                                     EncSym* syms, uint32_t* s_res) {
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t k = tid; k < 256; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += blockDim.x) atomicAdd(&hist[in[i]], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t tab = 0;
+        s_res[0] = build_o0_tables_enc(hist, n, out, syms, &tab) < 0 ? 0xffffffffu : tab;
     }
-    for (int z = 3; z >= 0; z--) { p -= 4; p[0] = (uint8_t)R[z]; p[1] = (uint8_t)(R[z] >> 8); p[2] = (uint8_t)(R[z] >> 16); p[3] = (uint8_t)(R[z] >> 24); }
-    uint32_t body = (uint32_t)(end - p);
-    for (uint32_t i = 0; i < body; i++) out[tab + i] = p[i];       // moves down, ascending copy is safe
-    return tab + body;
+    __syncthreads();
+    const uint32_t tab = s_res[0];
+    __syncthreads();
+    if (tab == 0xffffffffu) return 0;
+    if (tid < 32) {
+        const EGrp<4> G;
+        const bool mine = tid < 4;
+        uint8_t* const end = out + (cap & ~1u);
+        uint8_t* wp = end;
+        uint32_t x = 1u << 15;
+        const uint32_t rows = (n + 3) / 4;
+        for (uint32_t k = 0; k < rows; k++) {
+            const uint32_t pos = (rows - 1 - k) * 4 + G.glane;
+            const bool act = mine && pos < n;
+            const EncSym sy = syms[act ? in[pos] : 0];
+            x = enc_put<4>(x, act, sy, wp, G);
+        }
+        if (mine) {
+            uint8_t* p = wp - 4 * (4 - tid);
+            p[0] = (uint8_t)x; p[1] = (uint8_t)(x >> 8); p[2] = (uint8_t)(x >> 16); p[3] = (uint8_t)(x >> 24);
+        }
+        wp = reinterpret_cast<uint8_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)wp, 0)) - 16;
+        __syncwarp();
+        const uint32_t body = (uint32_t)(end - wp);
+        // move the payload down behind the table; ascending 32-byte steps never overtake unread bytes
+        for (uint32_t i0 = 0; i0 < body; i0 += 32) {
+            uint8_t v = 0;
+            if (i0 + tid < body) v = wp[i0 + tid];
+            __syncwarp();
+            if (i0 + tid < body) out[tab + i0 + tid] = v;
+            __syncwarp();
+        }
+        if (tid == 0) s_res[0] = tab + body;
+    }
+    __syncthreads();
+    const uint32_t r = s_res[0];
+    __syncthreads();
+    return r;
 }
 
 __device__ __forceinline__ double approx_log(int x) {              // fast_log, :620-623
@@ -588,7 +653,10 @@ __global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
     __shared__ int Sv[256];
     __shared__ uint32_t Tv[256];
     __shared__ uint32_t rowlen[256], rowoff[256];
-    __shared__ uint32_t s_shift, s_fail, s_alpha_len;
+    __shared__ uint32_t s_shift, s_fail, s_alpha_len, s_res[2];
+    __shared__ int s_maxtot;
+    __shared__ double rl10[256], rl12[256];
+    __shared__ __align__(16) EncSym nsyms[256];
     const uint32_t tid = threadIdx.x;
     for (uint32_t si = blockIdx.x; si < W->nstreams; si += gridDim.x) {
         EncStream& S = W->streams[si];
@@ -620,40 +688,58 @@ __global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
             Tv[i] = t;
         }
         __syncthreads();
-        // compute_shift, :629-691: ONE thread, reference accumulation order, no fused multiply-add
+        // compute_shift, :629-691.  The per-pair terms are computed in parallel; the two running sums
+        // are then accumulated by ONE thread in the reference's index order (double addition does
+        // not commute with reordering), with no fused multiply-add anywhere.
+        if (tid == 0) s_maxtot = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < ns; i += KT) {
+            const uint32_t T = Tv[i];
+            int max_val = (int)pow2_ceil(T);
+            int nsym = 0, sm10 = 0, sm12 = 0;
+            for (uint32_t j = 0; j < ns; j++) {
+                const uint32_t f = F1[i * ns + j];
+                if (!f) continue;
+                nsym++;
+                const uint32_t q = (uint32_t)max_val / f;
+                if (q > 1024) sm10++;
+                if (q > 4096) sm12++;
+            }
+            rl10[i] = c_log10[sm10]; rl12[i] = c_log12[sm12];
+            if (nsym < 64 && max_val > 128) max_val /= 2;
+            if (max_val > 1024) max_val /= 2;
+            if (max_val > 4096) max_val = 4096;
+            Sv[i] = max_val;
+            atomicMax(&s_maxtot, max_val);
+        }
+        __syncthreads();
+        double2* terms = reinterpret_cast<double2*>(S.syms);        // ns x ns x 16 B: not yet in use
+        for (uint32_t k = tid; k < ns * ns; k += KT) {
+            const uint32_t i = k / ns, f = F1[k];
+            double2 t;
+            t.x = t.y = __longlong_as_double(0x7ff8000000000000LL);  // NaN marks an absent pair
+            if (f) {
+                const double fd = (double)f, Td = (double)Tv[i];
+                int x = __double2int_rz(__ddiv_rn(__dmul_rn(1024.0, fd), Td));
+                t.x = __dmul_rn(fd, __dsub_rn(approx_log(x > 1 ? x : 1), rl10[i]));
+                x = __double2int_rz(__ddiv_rn(__dmul_rn(4096.0, fd), Td));
+                t.y = __dmul_rn(fd, __dsub_rn(approx_log(x > 1 ? x : 1), rl12[i]));
+            }
+            terms[k] = t;
+        }
+        __syncthreads();
         if (tid == 0) {
             double e10 = 0, e12 = 0;
-            int max_tot = 0;
-            for (uint32_t i = 0; i < ns; i++) {
-                const uint32_t T = Tv[i];
-                int max_val = (int)pow2_ceil(T);
-                int nsym = 0, sm10 = 0, sm12 = 0;
-                for (uint32_t j = 0; j < ns; j++) {
-                    uint32_t f = F1[i * ns + j];
-                    if (f && (uint32_t)max_val / f > 1024) sm10++;
-                    if (f && (uint32_t)max_val / f > 4096) sm12++;
+            const uint32_t np = ns * ns;
+#pragma unroll 8
+            for (uint32_t k = 0; k < np; k++) {
+                const double2 t = terms[k];
+                if (t.x == t.x) {
+                    e10 = __dadd_rn(__dsub_rn(e10, t.x), 4.0);
+                    e12 = __dadd_rn(__dsub_rn(e12, t.y), 6.0);
                 }
-                const double l10 = c_log10[sm10], l12 = c_log12[sm12];
-                const double Td = (double)T;
-                for (uint32_t j = 0; j < ns; j++) {
-                    uint32_t f = F1[i * ns + j];
-                    if (!f) continue;
-                    nsym++;
-                    const double fd = (double)f;
-                    int x = __double2int_rz(__ddiv_rn(__dmul_rn(1024.0, fd), Td));
-                    e10 = __dsub_rn(e10, __dmul_rn(fd, __dsub_rn(approx_log(x > 1 ? x : 1), l10)));
-                    x = __double2int_rz(__ddiv_rn(__dmul_rn(4096.0, fd), Td));
-                    e12 = __dsub_rn(e12, __dmul_rn(fd, __dsub_rn(approx_log(x > 1 ? x : 1), l12)));
-                    e10 = __dadd_rn(e10, 4.0);
-                    e12 = __dadd_rn(e12, 6.0);
-                }
-                if (nsym < 64 && max_val > 128) max_val /= 2;
-                if (max_val > 1024) max_val /= 2;
-                if (max_val > 4096) max_val = 4096;
-                Sv[i] = max_val;
-                if (max_tot < max_val) max_tot = max_val;
             }
-            s_shift = (__ddiv_rn(e10, e12) < 1.01 || max_tot <= 1024) ? 10u : 12u;
+            s_shift = (__ddiv_rn(e10, e12) < 1.01 || s_maxtot <= 1024) ? 10u : 12u;
         }
         __syncthreads();
         const uint32_t shift = s_shift;
@@ -709,21 +795,28 @@ __global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
         __syncthreads();
         if (tid == 0) {
             if (s_fail) S.size = 0xffffffffu;
-            else if (S.tab_len > 1000) {                             // :767-780
-                const uint32_t usz = S.tab_len - 1;
-                // scratch F / syms for the nested coder live behind the compressed bytes
-                const uint32_t ccap = ((usz + usz / 16 + 1024) & ~15u);
-                uint32_t* F = reinterpret_cast<uint32_t*>(S.ctab + ccap);
-                EncSym* ns_syms = reinterpret_cast<EncSym*>(S.ctab + ccap + 1024);
-                uint32_t csz = nested_o0_encode(tab + 1, usz, S.ctab, ccap, F, ns_syms);
-                if (csz && csz + 6 < S.tab_len) {
+            s_res[1] = (!s_fail && S.tab_len > 1000) ? S.tab_len : 0u;               // :767-780
+        }
+        __syncthreads();
+        const uint32_t tlen = s_res[1];
+        if (tlen) {                                                  // CTA-uniform
+            const uint32_t usz = tlen - 1;
+            const uint32_t ccap = ((usz + usz / 16 + 1024) & ~15u);
+            const uint32_t csz = nested_o0_encode(tab + 1, usz, S.ctab, ccap, Fs, nsyms, s_res);
+            if (csz && csz + 6 < tlen) {
+                uint32_t hdr = 0;
+                if (tid == 0) {
                     uint8_t* op = tab;
                     *op++ |= 1;
                     op += var_put_u32(op, usz);
                     op += var_put_u32(op, csz);
-                    for (uint32_t k = 0; k < csz; k++) op[k] = S.ctab[k];
-                    S.tab_len = (uint32_t)(op - tab) + csz;
+                    hdr = (uint32_t)(op - tab);
+                    S.tab_len = hdr + csz;
+                    s_res[0] = hdr;
                 }
+                __syncthreads();
+                hdr = s_res[0];
+                for (uint32_t k = tid; k < csz; k += KT) tab[hdr + k] = S.ctab[k];
             }
         }
     }
@@ -732,36 +825,6 @@ __global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
 // ------------------------------------------------------------------------------------------
 // enc_rans_kernel: persistent, one warp per CTA, a group of NWAY lanes per stream
 // ------------------------------------------------------------------------------------------
-template <int NWAY> struct EGrp {
-    static constexpr int G = 32 / NWAY;
-    static constexpr uint32_t GM = (NWAY == 32) ? 0xffffffffu : ((1u << NWAY) - 1u);
-    uint32_t g, glane, gshift, gmask;
-    __device__ __forceinline__ EGrp() {
-        uint32_t lane = lane_id();
-        g = lane / NWAY; glane = lane % NWAY; gshift = g * NWAY; gmask = GM << gshift;
-    }
-};
-
-// RansEncPutSymbol (rANS_word.h:281-321) for all lanes of the warp at once.  `wp` is the group's
-// write pointer (moves down); emitting lanes store their low 16 bits in descending lane order.
-template <int NWAY>
-__device__ __forceinline__ uint32_t enc_put(uint32_t x, bool act, const EncSym s, uint8_t*& wp, const EGrp<NWAY>& G) {
-    const bool emit = act && x >= s.x_max;
-    const uint32_t m = (__ballot_sync(0xffffffffu, emit) >> G.gshift) & EGrp<NWAY>::GM;
-    if (emit) {
-        const uint32_t above = __popc((m >> G.glane) >> 1);          // emitting lanes with a higher index write first
-        uint8_t* p = wp - 2 * (above + 1);
-        *reinterpret_cast<uint16_t*>(p) = (uint16_t)x;
-        x >>= 16;
-    }
-    wp -= 2 * __popc(m);
-    if (act) {
-        const uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift >> 16);
-        x = x + s.bias + q * (s.cmpl_shift & 0xffffu);
-    }
-    return x;
-}
-
 constexpr int ENC_O0_SMEM_PER_GROUP = 256 * 16;                      // EncSym[256]
 
 // Per-lane backward byte reader of the order-1 loop.  A lane walks its own segment from the end,
@@ -769,25 +832,37 @@ constexpr int ENC_O0_SMEM_PER_GROUP = 256 * 16;                      // EncSym[2
 // a lane pulls the aligned 16-byte line it is in once and shifts bytes out of registers.
 struct ByteSrc {
     const uint8_t* line;         // aligned line currently held
+    const uint8_t* lo_line;      // aligned line of the lane's first byte: nothing below it is touched
     uint32_t w0, w1, w2, w3;     // its bytes; the next byte to hand out is the top byte of w3
+    uint4 pre;                   // the line below, already on its way
     uint32_t k;                  // bytes left in the window
-    __device__ __forceinline__ void load() {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(line));
-        w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w;
+    __device__ __forceinline__ uint4 fetch(const uint8_t* l) const {
+        return (l >= lo_line) ? __ldg(reinterpret_cast<const uint4*>(l)) : make_uint4(0, 0, 0, 0);
     }
-    // `end` = one past the first byte to hand out (bytes are handed out at descending addresses)
-    __device__ __forceinline__ void init(const uint8_t* end) {
+    // [begin, end): the lane's bytes, handed out from end - 1 down to begin
+    __device__ __forceinline__ void init(const uint8_t* begin, const uint8_t* end) {
+        lo_line = begin - (reinterpret_cast<uintptr_t>(begin) & 15);
         const uint32_t lo = (uint32_t)(reinterpret_cast<uintptr_t>(end) & 15);
-        if (lo == 0) { line = end; k = 0; w0 = w1 = w2 = w3 = 0; return; }
+        w0 = w1 = w2 = w3 = 0; k = 0;
+        pre = make_uint4(0, 0, 0, 0);
+        if (begin == end) { line = end; return; }
+        if (lo == 0) { line = end; pre = fetch(line - 16); return; }
         line = end - lo;
-        load();                                               // 16-byte aligned: never leaves the page of end[-1]
+        const uint4 v = fetch(line);                          // 16-byte aligned: never leaves the page of end[-1]
+        w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w;
+        pre = fetch(line - 16);
         for (uint32_t q = lo; q < 16; q++) {                  // drop the bytes at and above `end`
             w3 = __funnelshift_l(w2, w3, 8); w2 = __funnelshift_l(w1, w2, 8); w1 = __funnelshift_l(w0, w1, 8); w0 <<= 8;
         }
         k = lo;
     }
     __device__ __forceinline__ uint32_t get() {
-        if (k == 0) { line -= 16; load(); k = 16; }
+        if (k == 0) {
+            w0 = pre.x; w1 = pre.y; w2 = pre.z; w3 = pre.w;
+            line -= 16;
+            pre = fetch(line - 16);
+            k = 16;
+        }
         const uint32_t b = w3 >> 24;
         w3 = __funnelshift_l(w2, w3, 8); w2 = __funnelshift_l(w1, w2, 8); w1 = __funnelshift_l(w0, w1, 8); w0 <<= 8;
         k--;
@@ -895,7 +970,8 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
             const uint32_t minsteps = __reduce_min_sync(0xffffffffu, my_n);
             const uint32_t idle = maxsteps - my_n;
             ByteSrc src;
-            src.init(in + (size_t)G.glane * seg + my_n);
+            src.init(in + (size_t)G.glane * seg, in + (size_t)G.glane * seg + my_n);
+            const bool sm_syms = (syms == ssym);                     // this group's symbols are in shared memory
             uint32_t rs = 0;                                         // rank of the symbol to code next
             if (my_n) rs = srank[src.get()];
             uint32_t left = my_n;                                    // symbols this lane still has to code
@@ -912,7 +988,25 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                 }
                 x = enc_put<NWAY>(x, act, s, wp, G);
             }
-            for (; k + 1 < maxsteps; k++) {                          // every lane active, a context byte exists
+            // every lane active, a context byte exists.  Table look-ups do not depend on the coder
+            // state: four steps' symbols are gathered first, then the four serial state updates run.
+            for (; k + 5 <= maxsteps; k += 4) {
+                EncSym sy[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t rc = srank[src.get()];
+                    const EncSym* sp = syms + rc * ns + rs;
+                    if (sm_syms) sy[u] = *sp;
+                    else {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(sp));
+                        sy[u].x_max = v.x; sy[u].rcp_freq = v.y; sy[u].bias = v.z; sy[u].cmpl_shift = v.w;
+                    }
+                    rs = rc;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) x = enc_put<NWAY>(x, true, sy[u], wp, G);
+            }
+            for (; k + 1 < maxsteps; k++) {
                 const uint32_t rc = srank[src.get()];
                 const EncSym s = syms[rc * ns + rs];
                 rs = rc;
