@@ -301,10 +301,14 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
     const uint64_t target = std::max<uint64_t>(32ull << 20, std::min<uint64_t>(384ull << 20, total_bytes / 8));
     std::vector<int> cuts{0};
     {
+        // the first chunks are smaller (1/8, 1/4, 1/2 of the target) so that the device->host stream,
+        // the bottleneck of a decode, starts early instead of waiting for a full-size chunk
         uint64_t acc = 0;
+        int ramp = total_bytes > 4 * target ? 3 : 0;
         for (int i = 0; i < nblk; i++) {
             uint64_t w = (uint64_t)in_len[i] + out_len[i];
-            if (acc && acc + w > target) { cuts.push_back(i); acc = 0; }
+            const uint64_t lim = std::max<uint64_t>(32ull << 20, target >> ramp);
+            if (acc && acc + w > lim) { cuts.push_back(i); acc = 0; if (ramp) ramp--; }
             acc += w;
         }
         cuts.push_back(nblk);

@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
 //
 //  * compact (shared memory; Nx16 streams whose alphabet fits).  Per context a row of packed
 //    entries, one per symbol of non-zero frequency, in cumulative order,
-//        entry = (C + F - 1) << 20 | (F - 1) << 8 | rank
+//        entry = (C + F - 1) << 20 | rank << 12 | (F - 1)
 //    preceded by a 64-bucket coarse index: coarse[m >> (shift - 6)] = index of the entry holding
 //    the bucket's first slot.  A lookup reads the coarse byte and three consecutive entries and
 //    steps forward while m lies beyond an entry's last slot (a fourth or later entry inside one
@@ -758,7 +758,7 @@ template <int NWAY, bool SMALL = false> struct O1Smem {
     static constexpr int STRIDE = TABO + TAB;                        // multiple of 16
     static constexpr int TOTAL = STRIDE * GroupCfg<NWAY>::G;
 };
-constexpr uint32_t O1_SENTINEL = 0xffffff00u;                        // last slot 0xfff, F 4096, rank 0
+constexpr uint32_t O1_SENTINEL = 0xfff00fffu;                        // last slot 0xfff, rank 0, F 4096
 
 struct O1Tables {
     uint32_t compact;       // 1: compact form in shared memory
@@ -798,7 +798,7 @@ __device__ bool build_o1_row_compact(const Grp<NWAY>& G, uint32_t F, const O1Tab
         const uint32_t f = lds_u32(F + 4 * r) << sh;
         if (!f) continue;
         const uint32_t last = c + f - 1;
-        sts_u32(row + 4 * idx, (last << 20) | ((f - 1) << 8) | r);
+        sts_u32(row + 4 * idx, (last << 20) | (r << 12) | (f - 1));
         for (uint32_t q = (c + (1u << bs) - 1) >> bs; q <= (last >> bs); q++) sts_u8(crs + q, idx);
         idx++;
         c += f;
@@ -1048,12 +1048,15 @@ __device__ __forceinline__ uint32_t o1_symbol(uint32_t& R, uint32_t& cs, const O
         const uint32_t e0 = lds_u32(ea), e1 = lds_u32(ea + 4), e2 = lds_u32(ea + 8);
         const uint32_t mk = m << 20;                         // mk > e  <=>  m > last slot of e (top 12 bits)
         uint32_t e = (mk > e1) ? e2 : ((mk > e0) ? e1 : e0);
+        const uint32_t q = R >> T.shift, qm = q + m;
+        // x' = F * q + m - C with F - 1 = e[11:0] and C + F - 1 = e[31:20]
+        R = (e & 0xfffu) * (q + 1u) + (qm - (e >> 20));
         if (mk > e) {                                        // >= 4 symbols share the bucket: scan on (sentinel-bounded)
             ea += 12;
             do { e = lds_u32(ea); ea += 4; } while (mk > e);
+            R = (e & 0xfffu) * (q + 1u) + (qm - (e >> 20));
         }
-        const uint32_t fm1 = (e >> 8) & 0xfffu, r = e & 0xffu;
-        R = (fm1 + 1u) * (R >> T.shift) + m - ((e >> 20) - fm1);
+        const uint32_t r = (e >> 12) & 0xffu;
         cs = COMPACT ? T.tabs + r * T.bstride : r;
         return r;
     }

@@ -387,9 +387,10 @@ __global__ void __launch_bounds__(TT) enc_transform_kernel(EncWork* W) {
 // ------------------------------------------------------------------------------------------
 // enc_hist_kernel: one CTA (4 warps) per stream
 // ------------------------------------------------------------------------------------------
-// Counting is done without atomics: every lane owns a private column of 16-bit counters,
-// cnt[warp][slot][lane] (16 KB per warp for 256 slots: conflict-free, lane l only ever touches
-// bank l/2), which are folded into 32-bit totals after at most HT_TILE bytes per lane.  Slots are
+// Counting is done without atomics: every lane owns a private column of 16-bit counters -- word
+// `lane` of a 128-byte row holds the lane's counters for slots 2r (low half) and 2r+1 (high
+// half), so lane l only ever touches bank l: no conflicts, no lost updates -- 16 KB per warp for
+// 256 slots, folded into 32-bit totals after at most HT_TILE bytes per lane.  Slots are
 // byte values for the order-0 histogram (utils.h:81-102) and rank pairs ctx * ns + sym for
 // order-1 statistics over alphabets of up to 16 symbols (utils.h:137-202); larger alphabets use
 // shared-memory atomics on a 96 x 96 table, or global atomics beyond that.
@@ -400,21 +401,29 @@ constexpr uint32_t O1_PRIV_NS = 16;                     // lane-private pair cou
 constexpr uint32_t O1_SMEM_NS = 96;                     // shared-memory atomics up to this alphabet size
 constexpr int HIST_SMEM = HT_WARPS * 256 * 64;          // 64 KB of private counters (reused as the 96 x 96 table)
 
-// Fold the private counters of `nslots` slots into tot[] (u32, shared) and clear them.
+// Address of lane `lane`'s counter for `slot` inside one warp's 16 KB area.
+__device__ __forceinline__ uint16_t* hist_ctr(uint16_t* warp_area, uint32_t slot, uint32_t lane) {
+    return warp_area + (slot >> 1) * 64 + lane * 2 + (slot & 1);
+}
+
+// Fold the private counters of `nslots` slots into tot[] (u32, shared) and clear them.  One
+// thread per slot pair (one 128-byte row per warp area).
 __device__ __forceinline__ void hist_fold(uint16_t* cnt, uint32_t* tot, uint32_t nslots) {
     __syncthreads();
-    for (uint32_t sl = threadIdx.x; sl < nslots; sl += HT) {
-        uint32_t sum = 0;
+    const uint32_t nrows = (nslots + 1) / 2;
+    for (uint32_t r = threadIdx.x; r < nrows; r += HT) {
+        uint32_t lo = 0, hi = 0;
         for (int w = 0; w < HT_WARPS; w++) {
-            uint32_t* col = reinterpret_cast<uint32_t*>(cnt + ((size_t)w * 256 + sl) * 32);
-            for (uint32_t j = 0; j < 16; j++) {
-                const uint32_t jj = (j + sl) & 15;     // rotate: neighbouring slots start in different banks
-                const uint32_t v = col[jj];
-                sum += (v & 0xffffu) + (v >> 16);
-                col[jj] = 0;
+            uint32_t* row = reinterpret_cast<uint32_t*>(cnt + (size_t)w * 256 * 32) + r * 32;
+            for (uint32_t j = 0; j < 32; j++) {
+                const uint32_t jj = (j + r) & 31;     // rotate: neighbouring rows start in different banks
+                const uint32_t v = row[jj];
+                lo += v & 0xffffu; hi += v >> 16;
+                row[jj] = 0;
             }
         }
-        tot[sl] += sum;
+        tot[2 * r] += lo;
+        if (2 * r + 1 < nslots) tot[2 * r + 1] += hi;
     }
     __syncthreads();
 }
@@ -427,7 +436,7 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
     __shared__ uint32_t s_ns;
     uint16_t* cnt = reinterpret_cast<uint16_t*>(hsm);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint16_t* mycol = cnt + (size_t)warp * 256 * 32 + lane;          // + slot * 32
+    uint16_t* myarea = cnt + (size_t)warp * 256 * 32;                // this warp's 16 KB of counters
 
     for (uint32_t k = tid; k < HIST_SMEM / 16; k += HT) reinterpret_cast<uint4*>(hsm)[k] = make_uint4(0, 0, 0, 0);
     for (uint32_t si = blockIdx.x; si < W->nstreams; si += gridDim.x) {
@@ -448,15 +457,18 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
             for (uint32_t i = tid; i < head; i += HT) atomicAdd(&h[in[i]], 1u);
             for (uint32_t i = head + nv * 16 + tid; i < n; i += HT) atomicAdd(&h[in[i]], 1u);
             uint32_t since = 0;
+            uint4 nq = make_uint4(0, 0, 0, 0);
+            if (tid < nv) nq = __ldg(v + tid);                       // one chunk ahead
             for (uint32_t i0 = 0; i0 < nv; i0 += HT) {
                 const uint32_t i = i0 + tid;
+                const uint4 q = nq;
+                if (i + HT < nv) nq = __ldg(v + i + HT);
                 if (i < nv) {
-                    const uint4 q = __ldg(v + i);
                     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
 #pragma unroll
-                        for (int bb = 0; bb < 4; bb++) mycol[((w[k] >> (8 * bb)) & 0xffu) * 32]++;
+                        for (int bb = 0; bb < 4; bb++) (*hist_ctr(myarea, (w[k] >> (8 * bb)) & 0xffu, lane))++;
                     }
                 }
                 since += 16;
@@ -491,19 +503,23 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
             // the segment starts are coded in context 0 (:720-723, with 4 -> nway)
             for (uint32_t k = 1 + tid; k < nway; k += HT) atomicAdd(&ptot[rank[0] * ns + rank[in[k * seg]]], 1u);
             uint32_t since = 0;
+            uint4 nq = make_uint4(0, 0, 0, 0);
+            uint32_t nc = 0;                                         // byte preceding the prefetched chunk
+            if (tid < nv) { nq = __ldg(v + tid); const uint32_t at = head + tid * 16; nc = at ? in[at - 1] : 0u; }
             for (uint32_t i0 = 0; i0 < nv; i0 += HT) {
                 const uint32_t i = i0 + tid;
+                const uint4 q = nq;
+                const uint32_t c0 = nc;
+                if (i + HT < nv) { nq = __ldg(v + i + HT); nc = in[head + (i + HT) * 16 - 1]; }
                 if (i < nv) {
-                    const uint4 q = __ldg(v + i);
                     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                    const uint32_t at = head + i * 16;
-                    uint32_t rc = rank[at ? in[at - 1] : 0u] * ns;   // context of the chunk's first byte
+                    uint32_t rc = rank[c0] * ns;                     // context of the chunk's first byte
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
 #pragma unroll
                         for (int bb = 0; bb < 4; bb++) {
                             const uint32_t r = rank[(w[k] >> (8 * bb)) & 0xffu];
-                            mycol[(rc + r) * 32]++;
+                            (*hist_ctr(myarea, rc + r, lane))++;
                             rc = r * ns;
                         }
                     }

@@ -71,3 +71,33 @@ GENERATORS = {
     "qual": qual_block, "acgt": acgt_block, "tag": tag_block,
     "u32": u32_block, "wide": wide_block, "random": random_block,
 }
+
+
+def mixed_corpus(nblk, seed=5, size=1 << 20, ragged=True):
+    """Config 5: a mixed-flag CRAM block corpus.  Returns a list of
+    (generator, block_seed, n_bytes, flags, method) with method 0 = rANS 4x16 (flags = the
+    reference's `order` argument) and 1 = legacy rANS 4x8 (flags = order 0/1).  Shares follow the
+    survey's example mix: 40 % o0, 30 % o1, 10 % X_32 o0, 10 % X_32 o1, 5 % PACK/RLE/STRIPE
+    variants, 5 % rANS 4x8."""
+    rng = np.random.default_rng(seed)
+    out = []
+    variants = [("acgt", 0x80), ("acgt", 0x81), ("tag", 0x40), ("tag", 0xc1), ("tag", 0xc5), ("u32", 0x408),
+                ("u32", 0x409), ("tag", 0x3c9), ("acgt", 0x84), ("u32", 0x40c)]
+    for i in range(nblk):
+        u = rng.random()
+        n = int(size if (not ragged or rng.random() < 0.7) else rng.integers(1, size + 1))
+        if u < 0.40:
+            gen, flags, method = ("qual", "wide")[int(rng.random() < 0.2)], 0, 0
+        elif u < 0.70:
+            gen, flags, method = ("qual", "wide")[int(rng.random() < 0.2)], 1, 0
+        elif u < 0.80:
+            gen, flags, method = "qual", 4, 0
+        elif u < 0.90:
+            gen, flags, method = "qual", 5, 0
+        elif u < 0.95:
+            gen, flags = variants[int(rng.integers(0, len(variants)))]
+            method = 0
+        else:
+            gen, flags, method = "qual", int(rng.integers(0, 2)), 1
+        out.append((gen, i, n, flags, method))
+    return out

@@ -1,0 +1,64 @@
+"""Config 5 (BASELINE.json configs[4], scaled down): a mixed-flag corpus -- rANS 4x16 o0/o1, X_32,
+PACK/RLE/STRIPE variants and legacy rANS 4x8 -- in ONE batched call per direction.  Encoded
+streams must equal the CPU oracle's byte for byte; decoded blocks must equal the source."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import htscodecs_b200 as hb
+from htscodecs_b200 import shard, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = hb.Context(0)
+    yield c
+    c.close()
+
+
+def _corpus(nblk, size):
+    spec = synth.mixed_corpus(nblk, seed=5, size=size)
+    blocks = [synth.GENERATORS[g](b, n).tobytes() for g, b, n, _, _ in spec]
+    return spec, blocks
+
+
+def test_mixed_corpus_parity(ctx, oracle, reflib):
+    spec, blocks = _corpus(160, 200_000)
+    i16 = [i for i, s in enumerate(spec) if s[4] == 0]
+    i8 = [i for i, s in enumerate(spec) if s[4] == 1]
+    assert i16 and i8
+    # ---- encode every 4x16 block in one call; compare with the oracle
+    comp, status = ctx.compress_many([blocks[i] for i in i16], [spec[i][3] for i in i16])
+    assert (status == 0).all()
+    for k, i in enumerate(i16):
+        assert comp[k] == oracle.compress(blocks[i], spec[i][3]), (i, spec[i])
+    # ---- one mixed decode batch: our 4x16 streams + reference-made 4x8 streams
+    streams = [None] * len(spec)
+    for k, i in enumerate(i16):
+        streams[i] = comp[k]
+    for i in i8:
+        streams[i] = reflib.compress_4x8(blocks[i], spec[i][3])
+    out, st = ctx.uncompress_many(streams, [len(b) for b in blocks], [s[4] for s in spec])
+    assert (st == 0).all(), st
+    assert out == blocks
+
+
+def test_mixed_corpus_full_size_roundtrip(ctx):
+    """1 MiB blocks (ragged tail sizes included): GPU encode -> GPU decode, checked through a
+    checksum of checksums so the test stays cheap at full block size."""
+    spec, blocks = _corpus(96, 1 << 20)
+    i16 = [i for i, s in enumerate(spec) if s[4] == 0]
+    comp, status = ctx.compress_many([blocks[i] for i in i16], [spec[i][3] for i in i16])
+    assert (status == 0).all()
+    out, st = ctx.uncompress_many(comp, [len(blocks[i]) for i in i16])
+    assert (st == 0).all()
+    want = hashlib.sha256(b"".join(hashlib.sha256(blocks[i]).digest() for i in i16)).hexdigest()
+    got = hashlib.sha256(b"".join(hashlib.sha256(o).digest() for o in out)).hexdigest()
+    assert got == want
+    # and the partition the multi-GPU path would use keeps every rank within one block of the mean
+    w = [len(blocks[i]) for i in i16]
+    for lo, hi in shard.partition_blocks(w, 8):
+        assert abs(sum(w[lo:hi]) - sum(w) / 8) <= max(w)
