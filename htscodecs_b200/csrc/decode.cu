@@ -385,6 +385,13 @@ template <int NWAY> struct WordRing {
     uint32_t head;          // byte offset (from abase) of the next unread byte
     uint32_t filled;
     uint4 pre[C::U];
+    bool mirror;            // the first MIRROR bytes of the ring are repeated behind its end, so a read that
+                            // starts inside the ring may run up to MIRROR bytes past it without wrapping
+    static constexpr uint32_t MIRROR = 64;
+    __device__ __forceinline__ void put(uint32_t off, uint4 v) const {       // off < RING
+        sts_v4(ring + off, v);
+        if (mirror && off < MIRROR) sts_v4(ring + C::RING + off, v);
+    }
 
     __device__ __forceinline__ uint4 fetch(uint32_t byte_off) const {
         const uint8_t* gp = abase + byte_off;
@@ -394,7 +401,8 @@ template <int NWAY> struct WordRing {
     }
     // called by the lanes of one group (group-uniform `active`)
     __device__ __forceinline__ void init(const uint8_t* first, const uint8_t* end, uint32_t ring_addr,
-                                         const Grp<NWAY>& G, bool active) {
+                                         const Grp<NWAY>& G, bool active, bool with_mirror = false) {
+        mirror = with_mirror;
         abase = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(first) & ~uintptr_t(15));
         in_end = end;
         ring = ring_addr;
@@ -408,7 +416,7 @@ template <int NWAY> struct WordRing {
 #pragma unroll
                 for (int u = 0; u < C::U; u++) {
                     uint32_t off = h * C::HALF + (u * NWAY + G.glane) * 16;
-                    sts_v4(ring + off, fetch(off));
+                    put(off, fetch(off));
                 }
 #pragma unroll
             for (int u = 0; u < C::U; u++) pre[u] = fetch(filled + (u * NWAY + G.glane) * 16);
@@ -423,7 +431,7 @@ template <int NWAY> struct WordRing {
             if (need) {
 #pragma unroll
                 for (int u = 0; u < C::U; u++)
-                    sts_v4(ring + ((filled + (u * NWAY + glane) * 16) & (C::RING - 1)), pre[u]);
+                    put((filled + (u * NWAY + glane) * 16) & (C::RING - 1), pre[u]);
                 filled += C::HALF;
 #pragma unroll
                 for (int u = 0; u < C::U; u++) pre[u] = fetch(filled + (u * NWAY + glane) * 16);
@@ -442,10 +450,11 @@ template <int NWAY> struct WordRing {
 // BYTE: rANS_byte.h:435-551, up to two single bytes, L = 2^23.  Else rANS_word.h:356-410, at
 // most one little-endian u16, L = 2^15.
 template <int NWAY, bool BYTE, bool ALIGNED>
-__device__ __forceinline__ uint32_t renorm_step(uint32_t R, bool act, WordRing<NWAY>& ring, uint32_t lt, uint32_t gshift) {
+__device__ __forceinline__ uint32_t renorm_step(uint32_t R, bool p, WordRing<NWAY>& ring, uint32_t lt, uint32_t gshift) {
     constexpr uint32_t GM = GroupCfg<NWAY>::GM;
+    // p: this lane's state is below the lower bound (and the lane is active)
     if (BYTE) {
-        bool p1 = act && R < (1u << 23), p2 = act && R < (1u << 15);
+        const bool p1 = p, p2 = p && R < (1u << 15);
         uint32_t m1 = (__ballot_sync(0xffffffffu, p1) >> gshift) & GM;
         uint32_t m2 = (__ballot_sync(0xffffffffu, p2) >> gshift) & GM;
         uint32_t off = ring.head + __popc(m1 & lt) + __popc(m2 & lt);
@@ -455,7 +464,6 @@ __device__ __forceinline__ uint32_t renorm_step(uint32_t R, bool act, WordRing<N
         }
         ring.head += __popc(m1) + __popc(m2);
     } else {
-        bool p = act && R < (1u << 15);
         uint32_t m = (__ballot_sync(0xffffffffu, p) >> gshift) & GM;
         if (p) R = (R << 16) | ring.template word_at<ALIGNED>(ring.head + 2 * __popc(m & lt));
         ring.head += 2 * __popc(m);
@@ -564,22 +572,24 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 // ------------------------------------------------------------------------------------------
 // Shared memory of dec_o0_kernel: G symbol LUTs (4096 B each; during set-up a LUT doubles as
 // header staging [0,1040), presence bytes [1280,1536) and frequency scratch [2048,3072)),
-// then G fc tables (256 x u32, F << 16 | C), then G word rings.  7 KB per X_32 warp with the
-// per-CTA reserve: 32 resident warps per SM.
+// then G fc tables (256 x {F, L + C}, L = the renormalisation bound), then G word rings.  8 KB per
+// X_32 warp with the per-CTA reserve: 28 resident warps per SM.
 template <int NWAY> struct O0Smem {
     static constexpr int G = GroupCfg<NWAY>::G;
-    static constexpr int LUT = 0, FC = G * 4096, RINGO = G * 5120;
-    static constexpr int TOTAL = G * (5120 + GroupCfg<NWAY>::RING);
+    static constexpr int LUT = 0, FC = G * 4096, RINGO = G * 6144;
+    static constexpr int RINGSZ = GroupCfg<NWAY>::RING + 64;            // ring + mirror of its first 64 bytes
+    static constexpr int TOTAL = G * (6144 + RINGSZ);
 };
 constexpr int HDR_STAGE = 1040;     // bytes of stream head staged for the table parser
 
 // Turn 256 frequencies (shared u32 array F) into the decode tables of one group:
-//   fc[s]  = F[s] << 16 | C[s]     so that   x' = F*(x>>12) + m - C
+//   fc[s]  = { F[s], L + C[s] }    so that   X = F*(x>>12) + m,  x' = X + L - fc.y  and the
+//                                  renormalisation test x' < L is X < fc.y, one level earlier
 //   lut[m] = s                     for C[s] <= m < C[s]+F[s]
 // Group-synchronous.  Returns false unless the frequencies sum to `want` (or `want_alt`).
 template <int NWAY>
 __device__ bool build_o0_tables(const Grp<NWAY>& G, uint32_t F, uint32_t fc, uint32_t lut, uint32_t want,
-                                uint32_t want_alt) {
+                                uint32_t want_alt, uint32_t L) {
     constexpr int K = 256 / NWAY;
     uint32_t mine = 0;
     bool bad = false;
@@ -594,13 +604,13 @@ __device__ bool build_o0_tables(const Grp<NWAY>& G, uint32_t F, uint32_t fc, uin
     for (int k = 0; k < K; k++) {
         uint32_t s = G.glane * K + k;
         uint32_t f = lds_u32(F + 4 * s);
-        sts_u32(fc + 4 * s, (f << 16) | c);
+        sts_v2(fc + 8 * s, make_uint2(f, L + c));
         c += f;
     }
     G.sync();
     for (uint32_t s = 0; s < 256; s++) {                             // :538-549, the group fills one symbol at a time
-        uint32_t e = lds_u32(fc + 4 * s);
-        uint32_t f = e >> 16, cs = e & 0xffffu;
+        uint2 e = lds_v2(fc + 8 * s);
+        uint32_t f = e.x, cs = e.y - L;
         for (uint32_t k = G.glane; k < f; k += NWAY) sts_u8(lut + cs + k, s);
     }
     G.sync();
@@ -646,19 +656,67 @@ __device__ bool o0_setup(const Grp<NWAY>& G, const DecJob& job, uint32_t lut, ui
     if (!G.all(r0 >= (BYTE ? (1u << 23) : (1u << 15)))) return false;            // :557-561
     *R = r0;
     *first_word = first + 4 * NWAY;
-    return build_o0_tables<NWAY>(G, Ftmp, fc, lut, 4096u, BYTE ? 4095u : 4096u); // 4x8 tables may sum to 4095 (:305)
+    return build_o0_tables<NWAY>(G, Ftmp, fc, lut, 4096u, BYTE ? 4095u : 4096u,   // 4x8 tables may sum to 4095 (:305)
+                                 BYTE ? (1u << 23) : (1u << 15));
 }
 
 // One decode step (rANS_static4x16pr.c:576-597 / rANS_static.c:318-344) for every lane.
 template <int NWAY, bool BYTE, bool ALIGNED, bool ALLACT>
 __device__ __forceinline__ uint32_t o0_step(uint32_t R, bool act, WordRing<NWAY>& ring, uint32_t lut, uint32_t fc,
                                             uint8_t* op, uint32_t lt, uint32_t gshift) {
+    constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
     const uint32_t m = R & 0xfffu;
     const uint32_t s = lds_u8(lut + m);
-    const uint32_t e = lds_u32(fc + s * 4);
-    const uint32_t Rn = (e >> 16) * (R >> 12) + m - (e & 0xffffu);
-    if (ALLACT || act) { R = Rn; *op = (uint8_t)s; }
-    return renorm_step<NWAY, BYTE, ALIGNED>(R, ALLACT || act, ring, lt, gshift);
+    const uint2 e = lds_v2(fc + s * 8);
+    const uint32_t X = e.x * (R >> 12) + m;
+    const bool p = (ALLACT || act) && X < e.y;               // x' < L
+    if (ALLACT || act) { R = X + L - e.y; *op = (uint8_t)s; }
+    return renorm_step<NWAY, BYTE, ALIGNED>(R, p, ring, lt, gshift);
+}
+
+// The X_32 hot step in PTX, so that the dependent chain is exactly
+//   LUT -> (F, L+C) -> mad -> setp -> vote -> and/popc -> mad -> word -> and -> LUT ...
+// Everything else (state merge, head bookkeeping, the output store) hangs off it.  `m` = R & 0xfff
+// is carried between steps (after a renormalisation it comes straight from the fetched word);
+// `hp` = shared address of the next unread word, wrapped inside the ring (1 KB, 1 KB-aligned, with a
+// 64-byte mirror so that hp + 2k needs no wrap); `head` = the same position, unwrapped, for refills.
+template <int OFF>
+__device__ __forceinline__ void o0_step_x32(uint32_t& R, uint32_t& m, uint32_t& hp, uint32_t& head, uint32_t lut,
+                                            uint32_t fc, uint32_t ringbase, uint32_t lt, uint8_t* op) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 s, sa, F, Y, q, X, b, k, a, w, Rs, kk;\n\t"
+        "add.u32 sa, %1, %4;\n\t"
+        "ld.shared.u8 s, [sa];\n\t"
+        "shr.u32 q, %0, 12;\n\t"
+        "shl.b32 sa, s, 3;\n\t"
+        "add.u32 sa, sa, %5;\n\t"
+        "ld.shared.v2.u32 {F, Y}, [sa];\n\t"
+        "st.global.u8 [%8+%9], s;\n\t"
+        "mad.lo.u32 X, F, q, %1;\n\t"
+        "setp.lt.u32 p, X, Y;\n\t"
+        "sub.u32 %0, X, Y;\n\t"
+        "add.u32 %0, %0, 32768;\n\t"
+        "vote.sync.ballot.b32 b, p, 0xffffffff;\n\t"
+        "and.b32 %1, %0, 4095;\n\t"
+        "shl.b32 Rs, %0, 16;\n\t"
+        "and.b32 k, b, %7;\n\t"
+        "popc.b32 k, k;\n\t"
+        "mad.lo.u32 a, k, 2, %2;\n\t"
+        "@p ld.shared.u16 w, [a];\n\t"
+        "@p and.b32 %1, w, 4095;\n\t"
+        "@p or.b32 %0, Rs, w;\n\t"
+        "popc.b32 kk, b;\n\t"
+        "shl.b32 kk, kk, 1;\n\t"
+        "add.u32 %3, %3, kk;\n\t"
+        "add.u32 %2, %2, kk;\n\t"
+        "and.b32 %2, %2, 1023;\n\t"
+        "or.b32 %2, %2, %6;\n\t"
+        "}"
+        : "+r"(R), "+r"(m), "+r"(hp), "+r"(head)
+        : "r"(lut), "r"(fc), "r"(ringbase), "r"(lt), "l"(op), "n"(OFF)
+        : "memory");
 }
 
 // `minit` (warp-uniform) = steps for which every lane of the warp is active: they run four to a
@@ -669,12 +727,24 @@ __device__ __forceinline__ void o0_loop(uint32_t R, WordRing<NWAY>& ring, uint32
     const uint32_t lt = (NWAY == 32) ? lanemask_lt() : ((1u << G.glane) - 1u);
     uint8_t* op = out + G.glane;
     uint32_t i = 0;
-    for (; i + 4 <= minit; i += 4) {
+    if (NWAY == 32 && !BYTE && ALIGNED && (ring.ring & 1023u) == 0) {
+        uint32_t m = R & 0xfffu, hp = ring.ring + (ring.head & 1023u);
+        for (; i + 4 <= minit; i += 4) {
+            o0_step_x32<0>(R, m, hp, ring.head, lut, fc, ring.ring, lt, op);
+            o0_step_x32<32>(R, m, hp, ring.head, lut, fc, ring.ring, lt, op);
+            o0_step_x32<64>(R, m, hp, ring.head, lut, fc, ring.ring, lt, op);
+            o0_step_x32<96>(R, m, hp, ring.head, lut, fc, ring.ring, lt, op);
+            op += 128;
+            ring.advance(G.glane, true);
+        }
+    } else {
+        for (; i + 4 <= minit; i += 4) {
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            R = o0_step<NWAY, BYTE, ALIGNED, true>(R, true, ring, lut, fc, op + u * NWAY, lt, G.gshift);
-        op += 4 * NWAY;
-        ring.advance(G.glane, true);
+            for (int u = 0; u < 4; u++)
+                R = o0_step<NWAY, BYTE, ALIGNED, true>(R, true, ring, lut, fc, op + u * NWAY, lt, G.gshift);
+            op += 4 * NWAY;
+            ring.advance(G.glane, true);
+        }
     }
     for (; i < maxit; i++) {
         const bool act = i < iters;
@@ -694,15 +764,19 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
     const Grp<NWAY> G;
     uint32_t base = smem_addr(smem_raw);
     asm volatile("" : "+r"(base));                      // keep the window base in a register (no re-derivation per step)
-    const uint32_t lut = base + S::LUT + G.g * 4096, fc = base + S::FC + G.g * 1024;
-    const uint32_t ringa = base + S::RINGO + G.g * C::RING;
+    const uint32_t lut = base + S::LUT + G.g * 4096, fc = base + S::FC + G.g * 2048;
+    const uint32_t ringa = base + S::RINGO + G.g * S::RINGSZ;
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
 
-    for (;;) {
-        uint32_t j0 = 0;
-        if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], (uint32_t)C::G);
-        j0 = __shfl_sync(0xffffffffu, j0, 0);
+    // The first round is assigned statically (CTA i takes jobs i*G ..), which spreads a batch that
+    // fits in one wave evenly over the SMs; later rounds are claimed from an atomic cursor.
+    for (uint32_t round = 0;; round++) {
+        uint32_t j0 = blockIdx.x * C::G;
+        if (round) {
+            if (lane_id() == 0) j0 = gridDim.x * C::G + atomicAdd(&W->next[kind], (uint32_t)C::G);
+            j0 = __shfl_sync(0xffffffffu, j0, 0);
+        }
         if (j0 >= njobs) break;
         const uint32_t ji = j0 + G.g;
         const bool active = ji < njobs;
@@ -715,7 +789,7 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
             ok = o0_setup<NWAY, BYTE>(G, job, lut, fc, &R, &first_word);
             if (!ok && G.glane == 0) set_status(status, job.blk, ST_FORMAT);
         }
-        ring.init(job.in + first_word, job.in + job.in_len, ringa, G, ok);
+        ring.init(job.in + first_word, job.in + job.in_len, ringa, G, ok, true);
         __syncwarp();
         const uint32_t iters = ok ? job.out_len / NWAY : 0, rem = ok ? job.out_len % NWAY : 0;
         const uint32_t maxit = __reduce_max_sync(0xffffffffu, iters), minit = __reduce_min_sync(0xffffffffu, iters);
@@ -1079,6 +1153,7 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
     const uint32_t mask = (1u << T.shift) - 1u;
     const uint32_t mine = seg + ((G.glane == NWAY - 1) ? tail : 0u);   // symbols this lane decodes
     const uint32_t group_steps = seg + tail;
+    constexpr uint32_t LB = BYTE ? (1u << 23) : (1u << 15);            // renormalisation bound
     ByteSink sink;
     uint8_t* const op0 = out + (size_t)G.glane * seg;
     sink.init(op0);
@@ -1092,7 +1167,7 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
             for (int u = 0; u < 4; u++) {
                 const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
                 pack |= lds_u8(unrank + r) << (8 * u);
-                R = renorm_step<NWAY, BYTE, ALIGNED>(R, true, ring, lt, G.gshift);
+                R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
             }
             sink.put4(pack);
             ring.advance(G.glane, true);
@@ -1103,7 +1178,7 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
             for (int u = 0; u < 4; u++) {
                 const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
                 sink.put(lds_u8(unrank + r));
-                R = renorm_step<NWAY, BYTE, ALIGNED>(R, true, ring, lt, G.gshift);
+                R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
             }
             ring.advance(G.glane, true);
         }
@@ -1114,7 +1189,7 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
             const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
             sink.put(lds_u8(unrank + r));
         }
-        R = renorm_step<NWAY, BYTE, ALIGNED>(R, act, ring, lt, G.gshift);
+        R = renorm_step<NWAY, BYTE, ALIGNED>(R, act && R < LB, ring, lt, G.gshift);
         ring.advance(G.glane, i < group_steps);
     }
     sink.finish();
@@ -1132,10 +1207,14 @@ __global__ void __launch_bounds__(32, SMALL ? 28 : 1) dec_o1_kernel(DecWork* W, 
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
 
-    for (;;) {
-        uint32_t j0 = 0;
-        if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], (uint32_t)C::G);
-        j0 = __shfl_sync(0xffffffffu, j0, 0);
+    // The first round is assigned statically (CTA i takes jobs i*G ..), which spreads a batch that
+    // fits in one wave evenly over the SMs; later rounds are claimed from an atomic cursor.
+    for (uint32_t round = 0;; round++) {
+        uint32_t j0 = blockIdx.x * C::G;
+        if (round) {
+            if (lane_id() == 0) j0 = gridDim.x * C::G + atomicAdd(&W->next[kind], (uint32_t)C::G);
+            j0 = __shfl_sync(0xffffffffu, j0, 0);
+        }
         if (j0 >= njobs) break;
         const uint32_t ji = j0 + G.g;
         const bool active = ji < njobs;

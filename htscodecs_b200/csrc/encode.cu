@@ -901,11 +901,14 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
     uint32_t* cursor = &W->next_misc[cursor_id];
     const uint32_t nstreams = W->nstreams;
 
-    for (;;) {
-        // streams are claimed EG::G at a time; those of another nway/order/size class are skipped by predicate
-        uint32_t s0 = 0;
-        if (lane_id() == 0) s0 = atomicAdd(cursor, (uint32_t)EG::G);
-        s0 = __shfl_sync(0xffffffffu, s0, 0);
+    // streams are claimed EG::G at a time (first round statically by CTA index, which spreads a batch
+    // that fits in one wave evenly over the SMs); those of another nway/order/size class are skipped
+    for (uint32_t round = 0;; round++) {
+        uint32_t s0 = blockIdx.x * EG::G;
+        if (round) {
+            if (lane_id() == 0) s0 = gridDim.x * EG::G + atomicAdd(cursor, (uint32_t)EG::G);
+            s0 = __shfl_sync(0xffffffffu, s0, 0);
+        }
         if (s0 >= nstreams) break;
         const uint32_t si = s0 + G.g;
         bool act_s = si < nstreams;
