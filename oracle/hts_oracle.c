@@ -1084,3 +1084,178 @@ int ho_uncompress_4x8(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     if (in_size < 9) return -1;
     return in[0] ? dec4x8_o1(in, in_size, out, out_size) : dec4x8_o0(in, in_size, out, out_size);
 }
+
+/* ------------------------------------------------------------------ rANS 4x8 encode (legacy) */
+/* the CRAM 3.0 encoder, restated.  PINNED: reproduces the 8
+ * tests/dat/r4x8 golden streams and libref.so's rans_compress byte for byte (tests/test_oracle.py). */
+
+/* RansEncPutSymbol, rANS_byte.h:281-315: up to two renormalisation bytes (low byte first, each
+ * written below the previous one), then x = C(s,x) with M = 4096. */
+static inline uint32_t enc_step8(uint32_t x, backw *b, uint32_t start, uint32_t freq) {
+    uint32_t x_max = ((L8 >> TF12) << 8) * freq;
+    if (x >= x_max) { *--b->p = (uint8_t)x; x >>= 8; }
+    if (x >= x_max) { *--b->p = (uint8_t)x; x >>= 8; }
+    return ((x / freq) << TF12) + (x % freq) + start;
+}
+
+/* the "sym [run]" list shared by both table levels, rANS_static.c:139-153 / :491-503 */
+static inline uint8_t *put_sym_rle(uint8_t *cp, int j, int *rle, const int present[256]) {
+    if (*rle) { (*rle)--; return cp; }
+    *cp++ = (uint8_t)j;
+    if (j && present[j - 1]) {
+        int e = j + 1;
+        while (e < 256 && present[e]) e++;
+        *rle = e - (j + 1);
+        *cp++ = (uint8_t)*rle;
+    }
+    return cp;
+}
+
+static inline uint8_t *put_freq8(uint8_t *cp, int f) {         /* :155-161 */
+    if (f < 128) *cp++ = (uint8_t)f;
+    else { *cp++ = (uint8_t)(128 | (f >> 8)); *cp++ = (uint8_t)(f & 0xff); }
+    return cp;
+}
+
+static void put_hdr8(uint8_t *out, int order, uint32_t total, uint32_t n) {   /* :201-213 */
+    out[0] = (uint8_t)order;
+    for (int k = 0; k < 4; k++) { out[1 + k] = (uint8_t)((total - 9) >> (8 * k)); out[5 + k] = (uint8_t)(n >> (8 * k)); }
+}
+
+unsigned int ho_compress_bound_4x8(unsigned int n) {            /* malloc size, :87 / :449 */
+    return (unsigned int)(1.05 * n + 257 * 257 * 3 + 9);
+}
+
+/* rans_compress_O0, rANS_static.c:85-218 */
+static int enc4x8_o0(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t *out_size) {
+    if (n == 0) return -1;                                  /* the reference divides by in_size (:105) */
+    int F[256] = {0}, present[256];
+    for (uint32_t i = 0; i < n; i++) F[in[i]]++;
+    uint64_t tr = ((uint64_t)4096 << 31) / n + (1 << 30) / n;
+    for (;;) {                                              /* :107-131 */
+        int fsum = 0, m = 0, M = 0;
+        for (int j = 0; j < 256; j++) {
+            if (!F[j]) continue;
+            if (m < F[j]) { m = F[j]; M = j; }
+            if ((F[j] = (int)(((uint64_t)F[j] * tr) >> 31)) == 0) F[j] = 1;
+            fsum += F[j];
+        }
+        fsum++;
+        if (fsum < 4096) { F[M] += 4096 - fsum; break; }
+        if (fsum - 4096 > F[M] / 2) { tr = 2104533975; continue; }
+        F[M] -= fsum - 4096;
+        break;
+    }
+    for (int j = 0; j < 256; j++) present[j] = F[j] != 0;
+    uint32_t C[256];
+    uint8_t *cp = out + 9;
+    int rle = 0;
+    for (uint32_t j = 0, x = 0; j < 256; j++) {             /* :136-166 */
+        if (!F[j]) continue;
+        cp = put_sym_rle(cp, (int)j, &rle, present);
+        cp = put_freq8(cp, F[j]);
+        C[j] = x; x += (uint32_t)F[j];
+    }
+    *cp++ = 0;
+    uint32_t tab = (uint32_t)(cp - out);
+
+    uint32_t cap = ho_compress_bound_4x8(n);
+    uint8_t *scratch = malloc(cap);
+    if (!scratch) return -1;
+    backw b = { scratch + cap };
+    uint32_t R[4] = { L8, L8, L8, L8 };
+    for (uint32_t i = n; i-- > 0;)                          /* :176-194: symbol i <-> state i & 3, last first */
+        R[i & 3] = enc_step8(R[i & 3], &b, C[in[i]], (uint32_t)F[in[i]]);
+    for (int z = 3; z >= 0; z--) bw_u32(&b, R[z]);
+    uint32_t body = (uint32_t)(scratch + cap - b.p);
+    memcpy(out + tab, b.p, body);
+    *out_size = tab + body;
+    put_hdr8(out, 0, *out_size, n);
+    free(scratch);
+    return 0;
+}
+
+/* rans_compress_O1, rANS_static.c:409-631 */
+static int enc4x8_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t *out_size) {
+    if (n < 4) return enc4x8_o0(in, n, out, out_size);      /* :438-439 */
+    int (*F)[256] = calloc(256, sizeof(*F));
+    uint32_t (*Cm)[256] = calloc(256, sizeof(*Cm));
+    uint8_t *scratch = NULL;
+    int T[256] = {0}, tp[256], present[256];
+    int rc = -1;
+    if (!F || !Cm) goto done;
+    {
+        uint8_t prev = 0;
+        for (uint32_t i = 0; i < n; i++) { F[prev][in[i]]++; T[prev]++; prev = in[i]; }   /* hist1_4 */
+    }
+    uint32_t q4 = n >> 2;
+    for (int k = 1; k < 4; k++) F[0][in[(uint32_t)k * q4]]++;  /* :455-458 */
+    T[0] += 3;
+    for (int i = 0; i < 256; i++) tp[i] = T[i] != 0;
+
+    uint8_t *cp = out + 9;
+    int rle_i = 0;
+    for (int i = 0; i < 256; i++) {
+        if (!T[i]) continue;
+        double p = ((double)4096) / T[i];                    /* :469 */
+        for (;;) {                                           /* :470-492 */
+            int t2 = 0, m = 0, M = 0;
+            for (int j = 0; j < 256; j++) {
+                if (!F[i][j]) continue;
+                if (m < F[i][j]) { m = F[i][j]; M = j; }
+                if ((F[i][j] = (int)(F[i][j] * p)) == 0) F[i][j] = 1;
+                t2 += F[i][j];
+            }
+            t2++;
+            if (t2 < 4096) { F[i][M] += 4096 - t2; break; }
+            if (t2 - 4096 >= F[i][M] / 2) { p = .98; continue; }
+            F[i][M] -= t2 - 4096;
+            break;
+        }
+        cp = put_sym_rle(cp, i, &rle_i, tp);                 /* :495-508 */
+        for (int j = 0; j < 256; j++) present[j] = F[i][j] != 0;
+        int rle_j = 0;
+        for (uint32_t j = 0, x = 0; j < 256; j++) {          /* :510-540 */
+            if (!F[i][j]) continue;
+            cp = put_sym_rle(cp, (int)j, &rle_j, present);
+            cp = put_freq8(cp, F[i][j]);
+            Cm[i][j] = x; x += (uint32_t)F[i][j];
+        }
+        *cp++ = 0;
+    }
+    *cp++ = 0;
+    uint32_t tab = (uint32_t)(cp - out);
+
+    uint32_t cap = ho_compress_bound_4x8(n);
+    scratch = malloc(cap);
+    if (!scratch) goto done;
+    backw b = { scratch + cap };
+    uint32_t R[4] = { L8, L8, L8, L8 };
+    /* state k owns quarter k; state 3 also the remainder; coded last to first with the
+     * preceding byte as context and context 0 at the start of each quarter (:557-600) */
+    for (uint32_t i = n - 1; i >= 4 * q4; i--)
+        R[3] = enc_step8(R[3], &b, Cm[in[i - 1]][in[i]], (uint32_t)F[in[i - 1]][in[i]]);
+    for (uint32_t t = q4; t-- > 1;)
+        for (int k = 3; k >= 0; k--) {
+            uint32_t pos = (uint32_t)k * q4 + t;
+            R[k] = enc_step8(R[k], &b, Cm[in[pos - 1]][in[pos]], (uint32_t)F[in[pos - 1]][in[pos]]);
+        }
+    for (int k = 3; k >= 0; k--) {
+        uint8_t s = in[(uint32_t)k * q4];
+        R[k] = enc_step8(R[k], &b, Cm[0][s], (uint32_t)F[0][s]);
+    }
+    for (int k = 3; k >= 0; k--) bw_u32(&b, R[k]);
+    uint32_t body = (uint32_t)(scratch + cap - b.p);
+    memcpy(out + tab, b.p, body);
+    *out_size = tab + body;
+    put_hdr8(out, 1, *out_size, n);
+    rc = 0;
+done:
+    free(scratch); free(F); free(Cm);
+    return rc;
+}
+
+/* rans_compress, rANS_static.c:927-932.  out must hold ho_compress_bound_4x8(n) bytes. */
+int ho_compress_4x8(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t *out_size, int order) {
+    return order ? enc4x8_o1(in, n, out, out_size) : enc4x8_o0(in, n, out, out_size);
+}

@@ -45,6 +45,11 @@ int ho_peek_size(const uint8_t *in, uint32_t in_size, uint32_t *ulen);
 /* rans_uncompress (legacy 4x8), reference rANS_static.c:934-943.  *out_size: in = capacity. */
 int ho_uncompress_4x8(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_t *out_size);
 
+/* rans_compress (legacy 4x8 encoder), reference rANS_static.c:927-932 (O0 :85-218, O1 :409-631).
+ * out must hold ho_compress_bound_4x8(n) bytes.  0 ok, -1 error (n == 0 is undefined in the reference). */
+unsigned int ho_compress_bound_4x8(unsigned int n);
+int ho_compress_4x8(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t *out_size, int order);
+
 /* Bare entropy coders (no container), exposed so tests can pin them separately.
  * nway is 4 or 32.  out capacity must be >= ho_compress_bound(n, order)-20. */
 int ho_enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, uint32_t *out_size, int nway);

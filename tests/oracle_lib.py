@@ -60,6 +60,9 @@ class Oracle:
         L.ho_uncompress.argtypes = [u8p, C.c_uint32, u8p, u32p]
         L.ho_uncompress_4x8.argtypes = [u8p, C.c_uint32, u8p, u32p]
         L.ho_peek_size.argtypes = [u8p, C.c_uint32, u32p]
+        L.ho_compress_bound_4x8.restype = C.c_uint
+        L.ho_compress_bound_4x8.argtypes = [C.c_uint]
+        L.ho_compress_4x8.argtypes = [u8p, C.c_uint32, u8p, u32p, C.c_int]
         L.ho_var_put_u32.argtypes = [u8p, C.c_uint32]
         L.ho_var_get_u32.argtypes = [u8p, u8p, u32p]
 
@@ -102,6 +105,16 @@ class Oracle:
         out = (C.c_uint8 * max(1, ulen))()
         osz = C.c_uint32(ulen)
         rc = self.lib.ho_uncompress_4x8(_buf(comp), len(comp), out, C.byref(osz))
+        if rc != 0:
+            return None
+        return C.string_at(out, osz.value)
+
+    def compress_4x8(self, data, order):
+        data = bytes(data)
+        cap = self.lib.ho_compress_bound_4x8(len(data)) + 64
+        out = (C.c_uint8 * cap)()
+        osz = C.c_uint32(cap)
+        rc = self.lib.ho_compress_4x8(_buf(data), len(data), out, C.byref(osz), order)
         if rc != 0:
             return None
         return C.string_at(out, osz.value)
