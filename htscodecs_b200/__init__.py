@@ -18,10 +18,12 @@ LIB_PATH = os.path.join(_HERE, "libhtscodecs_b200.so")
 RANS_ORDER_1, RANS_ORDER_X32, RANS_ORDER_STRIPE, RANS_ORDER_NOSZ = 0x01, 0x04, 0x08, 0x10
 RANS_ORDER_CAT, RANS_ORDER_RLE, RANS_ORDER_PACK = 0x20, 0x40, 0x80
 RANS4x16, RANS4x8 = 0, 1
+ORDER_RANS4x8 = 0x40000000          # OR into a batched encoder's order[i]: legacy rANS 4x8 codec
 
 EXPORTS = [
     "rans_compress_bound_4x16", "rans_compress_to_4x16", "rans_compress_4x16",
-    "rans_uncompress_to_4x16", "rans_uncompress_4x16", "rans_uncompress",
+    "rans_uncompress_to_4x16", "rans_uncompress_4x16", "rans_uncompress", "rans_compress",
+    "hts_b200_compress_bound_4x8",
     "hts_b200_create", "hts_b200_destroy", "hts_b200_last_error", "hts_b200_launch_count",
     "hts_b200_stream", "hts_b200_uncompress_batch_dev", "hts_b200_uncompress_batch_host",
     "hts_b200_compress_batch_dev", "hts_b200_compress_batch_host", "rans4x16_uncompress_batch",
@@ -56,6 +58,10 @@ def load_library():
     lib.rans_uncompress_4x16.argtypes = [vp, C.c_uint, _u32p]
     lib.rans_uncompress.restype = vp
     lib.rans_uncompress.argtypes = [vp, C.c_uint, _u32p]
+    lib.rans_compress.restype = vp
+    lib.rans_compress.argtypes = [vp, C.c_uint, _u32p, C.c_int]
+    lib.hts_b200_compress_bound_4x8.restype = C.c_uint
+    lib.hts_b200_compress_bound_4x8.argtypes = [C.c_uint]
     lib.hts_b200_create.restype = vp
     lib.hts_b200_create.argtypes = [C.c_int]
     lib.hts_b200_destroy.argtypes = [vp]
@@ -146,6 +152,19 @@ def rans_uncompress(data):
     buf, n = _inbuf(data)
     osz = C.c_uint32(0)
     p = lib.rans_uncompress(buf, n, C.byref(osz))
+    if not p:
+        return None
+    out = C.string_at(p, osz.value)
+    lib._free(p)
+    return out
+
+
+def rans_compress(data, order):
+    """Legacy rANS 4x8 (CRAM 3.0) encode; None on failure (empty input included)."""
+    lib = load_library()
+    buf, n = _inbuf(data)
+    osz = C.c_uint32(0)
+    p = lib.rans_compress(buf, n, C.byref(osz), order)
     if not p:
         return None
     out = C.string_at(p, osz.value)
@@ -286,7 +305,8 @@ class Context:
         lib = self.lib
         in_len = np.array([len(b) for b in blocks], np.uint32)
         order = np.array(orders, np.int32)
-        caps = np.array([lib.rans_compress_bound_4x16(int(in_len[i]), int(order[i])) for i in range(n)], np.uint32)
+        caps = np.array([lib.hts_b200_compress_bound_4x8(int(in_len[i])) if int(order[i]) & ORDER_RANS4x8
+                         else lib.rans_compress_bound_4x16(int(in_len[i]), int(order[i])) for i in range(n)], np.uint32)
         in_off = np.zeros(n, np.uint64)
         out_off = np.zeros(n, np.uint64)
         if n > 1:

@@ -637,3 +637,25 @@ extern "C" unsigned char* rans_compress_to_4x16(unsigned char* in, unsigned int 
 extern "C" unsigned char* rans_compress_4x16(unsigned char* in, unsigned int in_size, unsigned int* out_size, int order) {
     return rans_compress_to_4x16(in, in_size, nullptr, out_size, order);
 }
+
+// the reference's own malloc size, rANS_static.c:87 (double arithmetic on purpose)
+extern "C" unsigned int hts_b200_compress_bound_4x8(unsigned int size) {
+    return (unsigned int)(1.05 * size + 257 * 257 * 3 + 9);
+}
+
+extern "C" unsigned char* rans_compress(unsigned char* in, unsigned int in_size, unsigned int* out_size, int order) {
+    if (!out_size || !in || in_size == 0) return nullptr;
+    hts_b200_ctx* ctx = tls_ctx();
+    if (!ctx) { fprintf(stderr, "htscodecs_b200: no usable sm_100 device (there is no CPU fallback)\n"); return nullptr; }
+    const unsigned int bound = hts_b200_compress_bound_4x8(in_size);
+    unsigned char* dst = (unsigned char*)malloc(bound);
+    if (!dst) return nullptr;
+    const unsigned char* ins[1] = {in};
+    unsigned char* outs[1] = {dst};
+    unsigned int isz[1] = {in_size}, osz[1] = {bound};
+    int st[1] = {0}, ord[1] = {(order ? 1 : 0) | HTS_B200_ORDER_RANS4x8};
+    int rc = run_ptr_batch(ctx, true, 1, ins, isz, outs, osz, ord, st, nullptr);
+    if (rc != 0 || st[0] != 0) { free(dst); return nullptr; }
+    *out_size = osz[0];
+    return dst;
+}

@@ -55,7 +55,8 @@ struct EncStream {
     uint32_t* F1;          // order-1: ns x ns pair counts, then normalised freqs (compact by rank)
     EncSym* syms;          // order-0: 256 entries; order-1: ns x ns entries (compact)
     uint8_t* ctab;         // scratch for the order-0 compressed order-1 table
-    uint32_t pad0, pad1;
+    uint32_t codec;        // 0: rANS Nx16 (CRAM 3.1), 1: legacy rANS 4x8 (CRAM 3.0; byte-wise renormalisation)
+    uint32_t pad1;
 };
 
 struct EncLeaf {
@@ -88,7 +89,7 @@ struct EncBlock {
     uint32_t n;
     uint32_t order;        // as passed by the caller
     uint32_t cap;
-    uint32_t mode;         // 0 plain leaf, 1 stripe, 2 X_CAT requested, 3 error
+    uint32_t mode;         // 0 plain leaf, 1 stripe, 2 X_CAT requested, 3 error, 4 legacy rANS 4x8 leaf
     uint32_t leaf0;        // first leaf
     uint32_t N, ncand;     // stripe: leaves are [j * ncand + c]
     uint32_t pad;
@@ -154,9 +155,12 @@ __device__ int scale_freqs(uint32_t* F, uint32_t cnt, uint32_t total, uint32_t t
 }
 
 // RansEncSymbolInit, rANS_word.h:190-266
-__device__ __forceinline__ EncSym make_sym(uint32_t start, uint32_t freq, uint32_t bits) {
+// lbits: log2 of the coder's lower bound (15 for Nx16 with 16-bit words; 23 for 4x8 with bytes,
+// rANS_byte.h:195-266), wbits: renormalisation unit in bits
+__device__ __forceinline__ EncSym make_sym(uint32_t start, uint32_t freq, uint32_t bits, uint32_t lbits = 15,
+                                           uint32_t wbits = 16) {
     EncSym s;
-    s.x_max = (((1u << 15) >> bits) << 16) * freq;
+    s.x_max = (((1u << lbits) >> bits) << wbits) * freq;
     uint32_t cmpl = ((1u << bits) - freq) & 0xffffu;
     if (freq < 2) {
         s.rcp_freq = ~0u;
@@ -445,7 +449,8 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
         const uint8_t* in = S.src;
         const uint32_t n = S.n, nway = S.nway;
         uint32_t order = S.order;
-        if (order && (n < 8 || n < nway)) order = 0;                 // :1322-1325 (+ N-way analogue)
+        if (S.codec == 0) { if (order && (n < 8 || n < nway)) order = 0; }   // :1322-1325 (+ N-way analogue)
+        else if (order && n < 4) order = 0;                          // rANS_static.c:438-439
         for (uint32_t k = tid; k < 256; k += HT) h[k] = 0;
         __syncthreads();
         // ---- hist8, utils.h:81-102: aligned 16-byte chunks, one per thread per step
@@ -579,6 +584,34 @@ __device__ __forceinline__ uint32_t enc_put(uint32_t x, bool act, const EncSym s
     return x;
 }
 
+// The 4x8 form (rANS_byte.h:281-315): up to two renormalisation BYTES per state per step, low byte
+// first, each written below the previous one; states emit in descending lane order.
+template <int NWAY>
+__device__ __forceinline__ uint32_t enc_put8(uint32_t x, bool act, const EncSym s, uint8_t*& wp, const EGrp<NWAY>& G) {
+    const bool e1 = act && x >= s.x_max;
+    const uint32_t x1 = e1 ? (x >> 8) : x;
+    const bool e2 = e1 && x1 >= s.x_max;
+    const uint32_t m1 = (__ballot_sync(0xffffffffu, e1) >> G.gshift) & EGrp<NWAY>::GM;
+    const uint32_t m2 = (__ballot_sync(0xffffffffu, e2) >> G.gshift) & EGrp<NWAY>::GM;
+    if (e1) {
+        const uint32_t above = __popc((m1 >> G.glane) >> 1) + __popc((m2 >> G.glane) >> 1);
+        uint8_t* p = wp - 1 - above;
+        p[0] = (uint8_t)x;
+        if (e2) p[-1] = (uint8_t)(x >> 8);
+    }
+    x = e2 ? (x1 >> 8) : x1;
+    wp -= __popc(m1) + __popc(m2);
+    if (act) {
+        const uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift >> 16);
+        x = x + s.bias + q * (s.cmpl_shift & 0xffffu);
+    }
+    return x;
+}
+template <int NWAY, bool BYTE>
+__device__ __forceinline__ uint32_t enc_step(uint32_t x, bool act, const EncSym s, uint8_t*& wp, const EGrp<NWAY>& G) {
+    return BYTE ? enc_put8<NWAY>(x, act, s, wp, G) : enc_put<NWAY>(x, act, s, wp, G);
+}
+
 // ------------------------------------------------------------------------------------------
 // enc_table_kernel: one CTA (128 threads) per stream
 // ------------------------------------------------------------------------------------------
@@ -600,6 +633,58 @@ __device__ int build_o0_tables_enc(uint32_t* F, uint32_t n, uint8_t* tab, EncSym
         if (F[j]) { syms[j] = make_sym(x, F[j], 12); x += F[j]; }
     }
     return 0;
+}
+
+// ---- legacy rANS 4x8 tables ------------------------------------------------------------------
+// One "sym [run]" list step of the 4x8 table format (rANS_static.c:139-153 / :495-508 / :518-529):
+// `present(r)` tells whether rank r is listed, `sym(r)` its byte value.  Writes 0, 1 or 2 bytes.
+template <typename P, typename Y>
+__device__ __forceinline__ uint32_t put_sym_run(uint8_t* cp, uint32_t r, uint32_t nr, uint32_t& run, P present, Y sym) {
+    if (run) { run--; return 0; }
+    cp[0] = (uint8_t)sym(r);
+    if (sym(r) && r && present(r - 1) && sym(r - 1) + 1 == sym(r)) {
+        uint32_t e = r + 1;
+        while (e < nr && present(e) && sym(e) == sym(e - 1) + 1) e++;
+        run = e - (r + 1);
+        cp[1] = (uint8_t)run;
+        return 2;
+    }
+    return 1;
+}
+__device__ __forceinline__ uint32_t put_freq8(uint8_t* cp, uint32_t f) {          // :155-161
+    if (f < 128) { cp[0] = (uint8_t)f; return 1; }
+    cp[0] = (uint8_t)(128 | (f >> 8)); cp[1] = (uint8_t)(f & 0xff);
+    return 2;
+}
+
+// rans_compress_O0's table half, rANS_static.c:100-166: one thread.  F: 256 counts (modified).
+__device__ void table_4x8_o0(int* F, uint32_t n, uint8_t* tab, EncSym* syms, uint32_t* tab_len) {
+    unsigned long long tr = (((unsigned long long)4096 << 31) / n) + (unsigned long long)((1 << 30) / (int)n);
+    for (;;) {
+        int fsum = 0, m = 0, M = 0;
+        for (int j = 0; j < 256; j++) {
+            if (!F[j]) continue;
+            if (m < F[j]) { m = F[j]; M = j; }
+            if ((F[j] = (int)(((unsigned long long)F[j] * tr) >> 31)) == 0) F[j] = 1;
+            fsum += F[j];
+        }
+        fsum++;
+        if (fsum < 4096) { F[M] += 4096 - fsum; break; }
+        if (fsum - 4096 > F[M] / 2) { tr = 2104533975ull; continue; }
+        F[M] -= fsum - 4096;
+        break;
+    }
+    uint8_t* cp = tab;
+    uint32_t run = 0, x = 0;
+    for (uint32_t j = 0; j < 256; j++) {
+        if (!F[j]) continue;
+        cp += put_sym_run(cp, j, 256, run, [&](uint32_t r) { return F[r] != 0; }, [&](uint32_t r) { return r; });
+        cp += put_freq8(cp, (uint32_t)F[j]);
+        syms[j] = make_sym(x, (uint32_t)F[j], 12, 23, 8);
+        x += (uint32_t)F[j];
+    }
+    *cp++ = 0;
+    *tab_len = (uint32_t)(cp - tab);
 }
 
 // rANS 4x16 order-0 encode of the serialised order-1 table (:767-780) by one CTA: histogram by all
@@ -678,12 +763,14 @@ __global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
         EncStream& S = W->streams[si];
         __syncthreads();
         const uint32_t n = S.n;
-        if (n == 0) { if (tid == 0) { S.size = 0; S.tab_len = 0; } continue; }     // :405-406
+        const bool legacy = S.codec != 0;
+        if (n == 0) { if (tid == 0) { S.size = legacy ? 0xffffffffu : 0u; S.tab_len = 0; } continue; }   // :405-406
         if (S.order_eff == 0) {
             if (tid == 0) {
                 uint32_t tab = 0;
                 for (int j = 0; j < 256; j++) Fs[j] = S.F0[j];
-                if (build_o0_tables_enc(Fs, n, S.out, S.syms, &tab) < 0) S.size = 0xffffffffu;
+                if (legacy) table_4x8_o0(reinterpret_cast<int*>(Fs), n, S.out, S.syms, &tab);
+                else if (build_o0_tables_enc(Fs, n, S.out, S.syms, &tab) < 0) S.size = 0xffffffffu;
                 S.tab_len = tab;
             }
             continue;
@@ -704,6 +791,72 @@ __global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
             Tv[i] = t;
         }
         __syncthreads();
+        if (legacy) {
+            // ---- rans_compress_O1's table half, rANS_static.c:460-545, over ranks (ascending symbols)
+            auto symof = [&](uint32_t r) { return (uint32_t)unrank[r]; };
+            for (uint32_t i = tid; i < ns; i += KT) {        // normalise each context to 4096, size its table
+                int* row = reinterpret_cast<int*>(F1 + i * ns);
+                const int T = (int)Tv[i];
+                uint32_t len = 0;
+                if (T) {
+                    double p = __ddiv_rn(4096.0, (double)T);                         // :469
+                    for (;;) {
+                        int t2 = 0, m = 0, M = 0;
+                        for (uint32_t j = 0; j < ns; j++) {
+                            if (!row[j]) continue;
+                            if (m < row[j]) { m = row[j]; M = (int)j; }
+                            if ((row[j] = __double2int_rz(__dmul_rn((double)row[j], p))) == 0) row[j] = 1;
+                            t2 += row[j];
+                        }
+                        t2++;
+                        if (t2 < 4096) { row[M] += 4096 - t2; break; }
+                        if (t2 - 4096 >= row[M] / 2) { p = .98; continue; }
+                        row[M] -= t2 - 4096;
+                        break;
+                    }
+                    uint32_t run = 0;
+                    uint8_t tmp[2];
+                    for (uint32_t j = 0; j < ns; j++) {
+                        if (!row[j]) continue;
+                        len += put_sym_run(tmp, j, ns, run, [&](uint32_t r) { return row[r] != 0; }, symof);
+                        len += row[j] < 128 ? 1u : 2u;
+                    }
+                    len++;                                                           // the row's terminating 0
+                }
+                rowlen[i] = len;
+            }
+            __syncthreads();
+            uint8_t* tab = S.out;
+            if (tid == 0) {                                  // context list (:495-508) and row offsets
+                uint32_t o = 0, run = 0;
+                for (uint32_t i = 0; i < ns; i++) {
+                    if (!Tv[i]) continue;
+                    o += put_sym_run(tab + o, i, ns, run, [&](uint32_t r) { return Tv[r] != 0; }, symof);
+                    rowoff[i] = o;
+                    o += rowlen[i];
+                }
+                tab[o++] = 0;
+                S.tab_len = o;
+                S.shift = 12;
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < ns; i += KT) {        // write the rows, build the encoder symbols
+                if (!Tv[i]) continue;
+                const int* row = reinterpret_cast<const int*>(F1 + i * ns);
+                uint8_t* cp = tab + rowoff[i];
+                EncSym* srow = S.syms + (size_t)i * ns;
+                uint32_t run = 0, x = 0;
+                for (uint32_t j = 0; j < ns; j++) {
+                    if (!row[j]) continue;
+                    cp += put_sym_run(cp, j, ns, run, [&](uint32_t r) { return row[r] != 0; }, symof);
+                    cp += put_freq8(cp, (uint32_t)row[j]);
+                    srow[j] = make_sym(x, (uint32_t)row[j], 12, 23, 8);
+                    x += (uint32_t)row[j];
+                }
+                *cp = 0;
+            }
+            continue;
+        }
         // compute_shift, :629-691.  The per-pair terms are computed in parallel; the two running sums
         // are then accumulated by ONE thread in the reference's index order (double addition does
         // not commute with reordering), with no fused multiply-add anywhere.
@@ -889,7 +1042,7 @@ struct ByteSrc {
 // Order-1 symbol tables live in shared memory when the alphabet has at most NSCAP symbols; two
 // kernel variants (NSCAP 16: 4 KB per group, many resident warps; NSCAP 48: 36 KB) split the
 // streams between them by alphabet size, larger alphabets read the table from global memory.
-template <int NWAY, int ORDER, int NSCAP>
+template <int NWAY, int ORDER, int NSCAP, bool BYTE = false>
 __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t cursor_id, uint32_t ns_lo, uint32_t ns_hi) {
     using EG = EGrp<NWAY>;
     extern __shared__ __align__(16) uint8_t esm[];
@@ -913,7 +1066,8 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
         const uint32_t si = s0 + G.g;
         bool act_s = si < nstreams;
         EncStream* S = act_s ? &W->streams[si] : nullptr;
-        if (act_s && (S->nway != NWAY || S->order_eff != ORDER || S->n == 0 || S->size == 0xffffffffu)) act_s = false;
+        if (act_s && (S->nway != NWAY || S->order_eff != ORDER || S->n == 0 || S->size == 0xffffffffu ||
+                      (S->codec != 0) != BYTE)) act_s = false;
         if (ORDER && act_s && (S->ns <= ns_lo || S->ns > ns_hi)) act_s = false;    // another variant's alphabet class
         if (!__any_sync(0xffffffffu, act_s)) continue;
 
@@ -934,7 +1088,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
         __syncwarp();
 
         uint8_t* wp = act_s ? S->out + S->cap : nullptr;             // payload grows down from the end
-        uint32_t x = 1u << 15;                                       // RansEncInit, rANS_word.h:69-72
+        uint32_t x = BYTE ? (1u << 23) : (1u << 15);                 // RansEncInit, rANS_word.h:69-72 / rANS_byte.h:68-71
         if (ORDER == 0) {
             // symbol i belongs to state i % NWAY; rows are coded from the last to the first (:442-480).
             // The symbol bytes do not depend on the coder state, so they are fetched a batch of rows
@@ -951,7 +1105,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                 const uint32_t pos = in_rows ? (rows - 1 - kk) * NWAY + G.glane : 0;
                 const bool act = in_rows && pos < n;
                 EncSym s = ssym[act ? __ldg(in + pos) : 0];
-                x = enc_put<NWAY>(x, act, s, wp, G);
+                x = enc_step<NWAY, BYTE>(x, act, s, wp, G);
             }
             // from here on every lane of the warp codes rows full-1 .. 0 of its stream
             constexpr int B = 8;
@@ -971,13 +1125,13 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
 #pragma unroll
                 for (int u = 0; u < B; u++) sy[u] = ssym[b[u]];
 #pragma unroll
-                for (int u = 0; u < B; u++) x = enc_put<NWAY>(x, true, sy[u], wp, G);
+                for (int u = 0; u < B; u++) x = enc_step<NWAY, BYTE>(x, true, sy[u], wp, G);
             }
             for (uint32_t u = 0; u < r; u++) {                       // fewer than B rows left (already fetched)
                 uint32_t bsel = nb[0];
 #pragma unroll
                 for (int q = 1; q < B; q++) if (u == (uint32_t)q) bsel = nb[q];
-                x = enc_put<NWAY>(x, true, ssym[bsel], wp, G);
+                x = enc_step<NWAY, BYTE>(x, true, ssym[bsel], wp, G);
             }
         } else {
             // state z owns in[z*seg, (z+1)*seg), the last state also the tail; coded last-to-first
@@ -1005,7 +1159,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                     s = syms[rc * ns + rs];
                     rs = rc; left--;
                 }
-                x = enc_put<NWAY>(x, act, s, wp, G);
+                x = enc_step<NWAY, BYTE>(x, act, s, wp, G);
             }
             // every lane active, a context byte exists.  Table look-ups do not depend on the coder
             // state: four steps' symbols are gathered first, then the four serial state updates run.
@@ -1023,17 +1177,17 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                     rs = rc;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) x = enc_put<NWAY>(x, true, sy[u], wp, G);
+                for (int u = 0; u < 4; u++) x = enc_step<NWAY, BYTE>(x, true, sy[u], wp, G);
             }
             for (; k + 1 < maxsteps; k++) {
                 const uint32_t rc = srank[src.get()];
                 const EncSym s = syms[rc * ns + rs];
                 rs = rc;
-                x = enc_put<NWAY>(x, true, s, wp, G);
+                x = enc_step<NWAY, BYTE>(x, true, s, wp, G);
             }
             if (k < maxsteps && minsteps) {                          // segment starts: context 0
                 const EncSym s = syms[(uint32_t)srank[0] * ns + rs];
-                x = enc_put<NWAY>(x, true, s, wp, G);
+                x = enc_step<NWAY, BYTE>(x, true, s, wp, G);
             }
         }
         // RansEncFlush (rANS_word.h:104-116): states NWAY-1 .. 0, so state 0 ends lowest
@@ -1083,6 +1237,21 @@ __global__ void __launch_bounds__(256) enc_finish_kernel(EncWork* W) {
         __syncthreads();
         const EncStream& B = W->streams[L.body];
         uint8_t* out = L.out;
+        if (B.codec != 0) {
+            // legacy rANS 4x8 block (rANS_static.c:197-215): [order][u32 size - 9][u32 n][table][payload]
+            const bool bad = B.size == 0xffffffffu;
+            const uint32_t pay = B.cap - B.pay_off, total = 9 + B.tab_len + pay;
+            if (threadIdx.x == 0 && !bad) {
+                out[0] = (uint8_t)B.order_eff;
+                for (int k = 0; k < 4; k++) { out[1 + k] = (uint8_t)((total - 9) >> (8 * k)); out[5 + k] = (uint8_t)(L.n >> (8 * k)); }
+            }
+            if (!bad) {
+                cta_copy(out + 9, B.out, B.tab_len);
+                cta_copy(out + 9 + B.tab_len, B.out + B.pay_off, pay);
+            }
+            if (threadIdx.x == 0) { L.out_size = bad ? 0u : total; L.status = bad ? ST_FORMAT : ST_OK; }
+            continue;
+        }
         if (threadIdx.x == 0) {
             uint32_t flags = L.out_flags;
             uint32_t hdr = 1;
@@ -1157,7 +1326,7 @@ __global__ void __launch_bounds__(256) enc_block_kernel(EncWork* W, uint32_t* ou
             if (threadIdx.x == 0) { out_len[b] = s_hdr + B.n; status[b] = ST_OK; }
             continue;
         }
-        if (B.mode == 0) {
+        if (B.mode == 0 || B.mode == 4) {
             if (threadIdx.x == 0) { const EncLeaf& L = W->leaves[B.leaf0]; out_len[b] = L.out_size; status[b] = L.status; }
             continue;
         }
@@ -1201,7 +1370,7 @@ __global__ void enc_fix_kernel(EncWork* W, const uint8_t* in_base, const uint64_
     EncBlock& B = W->blocks[b];
     B.in = in_base + in_off[b];
     B.out = out_base + out_off[b];
-    if (B.mode == 0) {
+    if (B.mode == 0 || B.mode == 4) {
         EncLeaf& L = W->leaves[B.leaf0];
         L.src = B.in; L.out = B.out;
         W->streams[L.body].src = B.in;
@@ -1239,6 +1408,11 @@ unsigned int host_bound(unsigned int size, int order) {        // rans_compress_
     int sz = (int)d;
     return (unsigned int)(sz + (sz & 1) + 2);
 }
+
+unsigned int host_bound_4x8(unsigned int size) {               // the reference's malloc size, rANS_static.c:87
+    return (unsigned int)(1.05 * size + 257 * 257 * 3 + 9);
+}
+constexpr int ORDER_LEGACY_4x8 = 0x40000000;                    // HTS_B200_ORDER_RANS4x8
 
 size_t up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
@@ -1279,6 +1453,8 @@ int encode_init(int device) {
     g_grid_enc[0][0] = occ_grid(enc_rans_kernel<4, 0, 16>, SM_O0_4, g_sms_enc);
     g_grid_enc[1][0] = occ_grid(enc_rans_kernel<32, 0, 16>, SM_O0_32, g_sms_enc);
     g_grid_o1_4_s = occ_grid(enc_rans_kernel<4, 1, 16>, SM_O1_4_S, g_sms_enc);
+    occ_grid(enc_rans_kernel<4, 0, 16, true>, SM_O0_4, g_sms_enc);
+    occ_grid(enc_rans_kernel<4, 1, 16, true>, SM_O1_4_S, g_sms_enc);
     g_grid_o1_32_s = occ_grid(enc_rans_kernel<32, 1, 16>, SM_O1_32_S, g_sms_enc);
     g_grid_o1_32_l = occ_grid(enc_rans_kernel<32, 1, 48>, SM_O1_32_L, g_sms_enc);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -1311,11 +1487,11 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     struct Fix { uint32_t kind; uint32_t idx; uint32_t field; uint32_t blk; };
     (void)in_off_needed;
 
-    auto add_stream = [&](uint32_t leaf, uint32_t n_max, uint32_t order, uint32_t nway, bool is_meta) {
+    auto add_stream = [&](uint32_t leaf, uint32_t n_max, uint32_t order, uint32_t nway, bool is_meta, uint32_t codec = 0) {
         EncStream S;
         memset(&S, 0, sizeof(S));
-        S.n = n_max; S.order = order; S.nway = nway; S.leaf = leaf;
-        uint32_t cap = (host_bound(n_max, order) + 4 * nway + 64) & ~1u;
+        S.n = n_max; S.order = order; S.nway = nway; S.leaf = leaf; S.codec = codec;
+        uint32_t cap = ((codec ? host_bound_4x8(n_max) : host_bound(n_max, order)) + 4 * nway + 64) & ~1u;
         S.cap = cap;
         S.out = reinterpret_cast<uint8_t*>(take(cap));
         S.F0 = reinterpret_cast<uint32_t*>(take(1024));
@@ -1336,7 +1512,7 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     std::vector<uint64_t> leaf_src_off, leaf_out_off;
 
     auto add_leaf = [&](uint32_t blk, uint32_t n, uint32_t flags, bool src_scratch, uint64_t src_off, bool out_scratch,
-                        uint64_t out_off) {
+                        uint64_t out_off, uint32_t codec = 0) {
         EncLeaf L;
         memset(&L, 0, sizeof(L));
         L.n = n; L.flags = flags; L.blk = blk; L.out_flags = flags; L.cur_n = n;
@@ -1347,7 +1523,7 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
         }
         const uint32_t li = (uint32_t)leaves.size();
         const uint32_t nway = (flags & F_X32) ? 32 : 4;
-        L.body = add_stream(li, n, flags & 1, nway, false);
+        L.body = add_stream(li, n, flags & 1, nway, false, codec);
         L.meta = (flags & F_RLE) ? add_stream(li, n + 272, 0, nway, true) : 0xffffffffu;
         leaves.push_back(L);
         leaf_src_is_scratch.push_back(src_scratch); leaf_src_off.push_back(src_off);
@@ -1362,6 +1538,12 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
         uint32_t n = h_in_len[i];
         int order = h_order[i];
         B.n = n; B.order = (uint32_t)order;
+        if (order & ORDER_LEGACY_4x8) {                            // legacy CRAM 3.0 codec: order 0 / 1 only
+            B.cap = host_bound_4x8(n);
+            B.mode = 4;
+            B.leaf0 = add_leaf(i, n, (uint32_t)(order & 0xff) ? 1u : 0u, false, 0, false, 0, 1);
+            continue;
+        }
         B.cap = host_bound(n, order);
         if (n <= 20) order &= ~(int)F_STRIPE;                      // :1151
         if (order & F_STRIPE) {
@@ -1456,10 +1638,14 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     int launches = 0;
     const int g = g_sms_enc * 4;
     enc_fix_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(dW, b.in_base, b.in_off, b.out_base, b.out_off); launches++;
-    bool any_stripe = false, any_tr = false, any32[2] = {false, false}, any4[2] = {false, false};
+    bool any_stripe = false, any_tr = false, any32[2] = {false, false}, any4[2] = {false, false}, any8[2] = {false, false};
     for (auto& B : blocks) any_stripe |= B.mode == 1;
     for (auto& L : leaves) any_tr |= (L.flags & (F_PACK | F_RLE)) != 0;
-    for (auto& S : streams) { if (S.nway == 32) { any32[0] = true; any32[1] |= S.order != 0; } else { any4[0] = true; any4[1] |= S.order != 0; } }
+    for (auto& S : streams) {
+        if (S.codec) { any8[0] = true; any8[1] |= S.order != 0; }
+        else if (S.nway == 32) { any32[0] = true; any32[1] |= S.order != 0; }
+        else { any4[0] = true; any4[1] |= S.order != 0; }
+    }
     if (any_stripe) { enc_stripe_kernel<<<g, 256, 0, st>>>(dW); launches++; }
     if (any_tr) { enc_transform_kernel<<<g, TT, 0, st>>>(dW); launches++; }
     if (!streams.empty()) {
@@ -1473,6 +1659,8 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
         if (any32[0]) { enc_rans_kernel<32, 0, 16><<<g_grid_enc[1][0], 32, SM_O0_32, st>>>(dW, 2, 0, 256); launches++; }
         if (any32[1]) { enc_rans_kernel<32, 1, 16><<<g_grid_o1_32_s, 32, SM_O1_32_S, st>>>(dW, 3, 0, 16); launches++;
                         enc_rans_kernel<32, 1, 48><<<g_grid_o1_32_l, 32, SM_O1_32_L, st>>>(dW, 4, 16, 256); launches++; }
+        if (any8[0])  { enc_rans_kernel<4, 0, 16, true><<<g_grid_enc[0][0], 32, SM_O0_4, st>>>(dW, 5, 0, 256); launches++; }
+        if (any8[1])  { enc_rans_kernel<4, 1, 16, true><<<g_grid_o1_4_s, 32, SM_O1_4_S, st>>>(dW, 6, 0, 256); launches++; }
         enc_finish_kernel<<<g, 256, 0, st>>>(dW); launches++;
     }
     enc_block_kernel<<<g, 256, 0, st>>>(dW, b.out_len, b.status); launches++;

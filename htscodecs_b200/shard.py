@@ -7,7 +7,7 @@ data path, hence no NCCL collective in it; the gather below moves 8 bytes per bl
 whatever process group the caller initialised (gloo on CPU, nccl on GPUs).
 
 The codec call is injected (``worker``) so the same host logic is exercised by the CPU-only
-world_size-2 gloo test (tests/test_shard.py, worker = CPU oracle) and by bench.py / the GPU tests
+world_size-2 gloo test (tests/test_shard.py, where the worker is a CPU checker) and by bench.py / the GPU tests
 (worker = Context.uncompress_batch_host / compress_batch_host).
 """
 import numpy as np

@@ -58,8 +58,13 @@ unsigned char *rans_uncompress_4x16(unsigned char *in, unsigned int in_size,
                                     unsigned int *out_size);
 
 /* replaces rans_uncompress (legacy CRAM 3.0 rANS 4x8), reference rANS_static.h:42-43
- * (rANS_static.c:934-943).  The 4x8 encoder is out of scope. */
+ * (rANS_static.c:934-943). */
 unsigned char *rans_uncompress(unsigned char *in, unsigned int in_size, unsigned int *out_size);
+
+/* replaces rans_compress (legacy rANS 4x8 encoder), reference rANS_static.h:40-41
+ * (rANS_static.c:927-932; order 0 :85-218, order 1 :409-631).  The result is malloc'ed;
+ * in_size == 0 returns NULL (the reference divides by in_size there). */
+unsigned char *rans_compress(unsigned char *in, unsigned int in_size, unsigned int *out_size, int order);
 
 /* ------------------------------------------------------------------------------------------
  * 2. Batched API (new; no reference equivalent -- the reference's callers loop over blocks,
@@ -67,6 +72,12 @@ unsigned char *rans_uncompress(unsigned char *in, unsigned int in_size, unsigned
  * ---------------------------------------------------------------------------------------- */
 
 typedef struct hts_b200_ctx hts_b200_ctx;
+
+/* OR this into order[i] of the batched encoders to code block i with the legacy rANS 4x8 codec
+ * (order 0 / 1 in the low bits); its capacity bound is hts_b200_compress_bound_4x8(). */
+#define HTS_B200_ORDER_RANS4x8 0x40000000
+/* the reference encoder's own buffer size for n input bytes, rANS_static.c:87 */
+unsigned int hts_b200_compress_bound_4x8(unsigned int size);
 
 /* per-block status codes */
 #define HTS_B200_OK            0

@@ -153,3 +153,24 @@ def test_differential_vs_reference(oracle, reflib):
         for order in (0, 1):
             c8 = reflib.compress_4x8(data, order)
             assert oracle.uncompress_4x8(c8) == data
+
+
+# ------------------------------------------------------------------ rANS 4x8 encoder
+@pytest.mark.parametrize("name", list(GOLD16))
+@pytest.mark.parametrize("order", [0, 1])
+def test_golden_4x8_encode(oracle, golden_dir, name, order):
+    """The oracle's 4x8 encoder reproduces the reference's pre-compressed r4x8 files."""
+    data = open(os.path.join(golden_dir, "src", name + ".bin"), "rb").read()
+    gold = open(os.path.join(golden_dir, "r4x8", f"{name}.{order}"), "rb").read()
+    assert oracle.compress_4x8(data, order) == gold
+
+
+def test_4x8_encode_differential_vs_reference(oracle, reflib):
+    from vectors import small_inputs
+    from htscodecs_b200 import synth
+    cases = [(n, d) for n, d in small_inputs() if len(d) >= 1]
+    cases += [(g, synth.GENERATORS[g](2, 70001).tobytes()) for g in ("qual", "wide", "tag", "random", "acgt", "u32")]
+    for name, data in cases:
+        for order in (0, 1):
+            assert oracle.compress_4x8(data, order) == reflib.compress_4x8(data, order), (name, order)
+    assert oracle.compress_4x8(b"", 0) is None
