@@ -167,8 +167,12 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3):
     d_out = torch.empty(nblk * n, dtype=torch.uint8, device="cuda")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res = {}
-    for name, f in (("o0_x32", 4), ("o1_x32", 5), ("o0_4way", 0), ("o1_4way", 1)):
-        cap = (hb.rans_compress_bound_4x16(n, f) + 15) // 16 * 16
+    for name, f in (("o0_x32", 4), ("o1_x32", 5), ("o0_4way", 0), ("o1_4way", 1),
+                    ("r4x8_o0", hb.ORDER_RANS4x8), ("r4x8_o1", hb.ORDER_RANS4x8 | 1)):
+        legacy = bool(f & hb.ORDER_RANS4x8)
+        bound = hb.load_library().hts_b200_compress_bound_4x8(n) if legacy else hb.rans_compress_bound_4x16(n, f)
+        cap = (bound + 15) // 16 * 16
+        method = torch.full((nblk,), 1, dtype=torch.uint8, device="cuda") if legacy else None
         d_comp = torch.empty(nblk * cap, dtype=torch.uint8, device="cuda")
         comp_off = torch.arange(nblk, dtype=torch.int64, device="cuda") * cap
         comp_len = torch.full((nblk,), cap, dtype=torch.int32, device="cuda")
@@ -194,7 +198,7 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3):
             out_len.fill_(n)
             torch.cuda.synchronize()
             e0.record(stream)
-            ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, sync=False)
+            ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, method, sync=False)
             e1.record(stream)
             torch.cuda.synchronize()
             return e0.elapsed_time(e1)

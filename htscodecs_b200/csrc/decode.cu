@@ -544,15 +544,15 @@ __device__ uint32_t parse_o0_table_4x16(uint32_t src, uint32_t lim, uint32_t F, 
 
 // One 4x8 "sym [run] freq ... 0" table (rANS_static.c:271-303; zero_is_4096 for the order-1
 // inner tables, :775-776).  Returns false when malformed; *sum = frequency total.
-template <typename RD>
-__device__ bool parse_table_4x8(RD& r, uint32_t F, uint32_t* sum, bool zero_is_4096) {
+template <typename RD, typename ST>
+__device__ bool parse_table_4x8(RD& r, ST store, uint32_t* sum, bool zero_is_4096) {
     uint32_t run = 0, x = 0, j = r.get();
     do {
         uint32_t f = r.get();
         if (f >= 128) f = ((f & 127) << 8) | r.get();
         if (!f && zero_is_4096) f = 4096;
         if (x + f > 4096) return false;
-        sts_u32(F + 4 * j, f);
+        store(j, f);
         x += f;
         if (!run && j + 1 == r.peek()) { r.get(); j++; run = r.get(); }
         else if (run) { run--; if (++j > 255) return false; }
@@ -561,6 +561,10 @@ __device__ bool parse_table_4x8(RD& r, uint32_t F, uint32_t* sum, bool zero_is_4
     } while (j);
     *sum = x;
     return true;
+}
+template <typename RD>
+__device__ bool parse_table_4x8(RD& r, uint32_t F, uint32_t* sum, bool zero_is_4096) {
+    return parse_table_4x8(r, [&](uint32_t j, uint32_t f) { sts_u32(F + 4 * j, f); }, sum, zero_is_4096);
 }
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
@@ -847,7 +851,8 @@ struct O1Tables {
 // entries used) -> compact row + coarse index.  Returns false if they do not sum to 1 << shift
 // after the power-of-two shift (…4x16pr.c:982-997).
 template <int NWAY>
-__device__ bool build_o1_row_compact(const Grp<NWAY>& G, uint32_t F, const O1Tables& T, uint32_t ctx, uint32_t Tsum) {
+__device__ bool build_o1_row_compact(const Grp<NWAY>& G, uint32_t F, const O1Tables& T, uint32_t ctx, uint32_t Tsum,
+                                     bool allow_4095 = false) {
     const uint32_t M = 1u << T.shift, ns = T.ns, bs = T.shift - 6;
     uint32_t sh = 0;
     if (Tsum < M) while ((Tsum << sh) < M) sh++;
@@ -864,7 +869,9 @@ __device__ bool build_o1_row_compact(const Grp<NWAY>& G, uint32_t F, const O1Tab
     uint32_t total, nzt;
     uint32_t c = G.exscan(bad ? 2 * M : mine, &total);
     uint32_t idx = G.exscan(nz, &nzt);
-    if (total != M) return false;
+    // 4x8 tables written by the reference sum to M - 1 (rANS_static.c:122-130); slot M - 1 then
+    // belongs to no symbol and resolves to the row's sentinel (never reached by a valid stream)
+    if (total != M && !(allow_4095 && total == M - 1)) return false;
     const uint32_t crs = T.tabs + ctx * T.bstride, row = crs + 64;
     for (uint32_t k = 0; k < K; k++) {
         const uint32_t r = r0 + k;
@@ -928,15 +935,31 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     const uint8_t* in_end = job.in + job.in_len;
 
     // ---- phase 1 (one lane): locate the table bytes, read the alphabet
-    for (uint32_t k = G.glane; k < 256; k += NWAY) { sts_u8(rank + k, BYTE ? k : 0xffu); sts_u8(unrank + k, BYTE ? k : 0u); }
+    for (uint32_t k = G.glane; k < 256; k += NWAY) { sts_u8(rank + k, 0xffu); sts_u8(unrank + k, 0u); }
     G.sync();
-    uint32_t err = 0, shift = 12, ns = BYTE ? 256u : 0u;
+    uint32_t err = 0, shift = 12, ns = 0u;
     GRd rd{nullptr, nullptr};
     const uint8_t* body = nullptr;
     if (G.glane == 0) {
         if (BYTE) {                                          // rANS_static.c:676-: tables follow the 9-byte header
             if (job.in_len < 27) err = 1;
             rd.p = job.in + 9; rd.end = in_end;
+            // The 4x8 format names no alphabet up front: a first pass over the tables marks every
+            // byte value that occurs as a context or as a symbol (plus 0, the segment-start context).
+            if (!err) {
+                GRd sc = rd;
+                uint32_t run_i = 0, c = sc.get(), dummy;
+                sts_u8(rank + 0, 0u);
+                for (;;) {
+                    sts_u8(rank + c, 0u);
+                    if (sc.p + 16 > sc.end ||
+                        !parse_table_4x8(sc, [&](uint32_t j, uint32_t) { sts_u8(rank + j, 0u); }, &dummy, true)) { err = 1; break; }
+                    if (!run_i && c + 1 == sc.peek()) { sc.get(); c++; run_i = sc.get(); }
+                    else if (run_i) { run_i--; if (++c > 255) { err = 1; break; } }
+                    else c = sc.get();
+                    if (!c) break;
+                }
+            }
         } else if (job.in_len < 4 * NWAY) {                  // :872
             err = 1;
         } else {
@@ -954,8 +977,10 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
             } else {
                 rd.p = job.in + 1; rd.end = in_end;
             }
+            if (!err && (!read_alphabet(rd, rank, 0u) || !rd.more())) err = 1;   // :959-965
+        }
+        {
             if (!err) {
-                if (!read_alphabet(rd, rank, 0u) || !rd.more()) err = 1;         // :959-965
                 for (uint32_t s = 0; s < 256 && !err; s++)
                     if (lds_u8(rank + s) == 0) { sts_u8(unrank + ns, s); sts_u8(rank + s, 0xfeu); ns++; }
                 // second pass: 0xfe marks -> ranks (a rank can legitimately be 0xfe/0xff when ns > 254)
@@ -977,7 +1002,7 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     T.g_rows = nullptr; T.g_fc = nullptr;
     T.bstride = 64 + 4 * (ns + 3);
     T.tabs = tabs;
-    T.compact = (!BYTE && o1_compact_bytes(ns) <= (uint32_t)S::TAB) ? 1u : 0u;
+    T.compact = (o1_compact_bytes(ns) <= (uint32_t)S::TAB) ? 1u : 0u;
     if (T.compact) {
         for (uint32_t k = G.glane; k < ns * (T.bstride / 4); k += NWAY)     // coarse: 0, entries: sentinels
             sts_u32(tabs + 4 * k, (k % (T.bstride / 4)) < 16 ? 0u : O1_SENTINEL);
@@ -1020,21 +1045,25 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
                           : !build_o1_row_lut<NWAY>(G, Ftmp, T, ci, Tsum, false)) return ST_FORMAT;
         }
     } else {
-        // rANS_static.c:748-813: outer "sym [run]" list of contexts, one 4x8 table each
+        // rANS_static.c:748-813: outer "sym [run]" list of contexts, one 4x8 table each (second pass:
+        // frequencies land at their symbol's rank)
         uint32_t run_i = 0, ctx = 0;
         if (G.glane == 0) ctx = rd.get();
         for (;;) {
-            for (uint32_t k = G.glane; k < 256; k += NWAY) sts_u32(Ftmp + 4 * k, 0u);
+            for (uint32_t k = G.glane; k < (T.compact ? ns : 256u); k += NWAY) sts_u32(Ftmp + 4 * k, 0u);
             G.sync();
             uint32_t x = 0;
             if (G.glane == 0) {
-                if (rd.p + 16 > rd.end || !parse_table_4x8(rd, Ftmp, &x, true)) err = 1;
+                if (rd.p + 16 > rd.end ||
+                    !parse_table_4x8(rd, [&](uint32_t j, uint32_t f) { sts_u32(Ftmp + 4 * lds_u8(rank + j), f); }, &x, true)) err = 1;
                 else if (x < 4095 || x > 4096) err = 1;      // :797
             }
             G.sync();
             err = G.bcast(err); ctx = G.bcast(ctx); x = G.bcast(x);
             if (err) return ST_FORMAT;
-            if (!build_o1_row_lut<NWAY>(G, Ftmp, T, ctx, 4096u, true)) return ST_FORMAT;
+            const uint32_t rctx = lds_u8(rank + ctx);
+            if (T.compact ? !build_o1_row_compact<NWAY>(G, Ftmp, T, rctx, 4096u, true)
+                          : !build_o1_row_lut<NWAY>(G, Ftmp, T, rctx, 4096u, true)) return ST_FORMAT;
             uint32_t more = 0;
             if (G.glane == 0) {
                 if (!run_i && ctx + 1 == rd.peek()) { rd.get(); ctx++; run_i = rd.get(); }
@@ -1239,12 +1268,11 @@ __global__ void __launch_bounds__(32, SMALL ? 28 : 1) dec_o1_kernel(DecWork* W, 
         const uint32_t seg = ok ? job.out_len / NWAY : 0, tail = ok ? job.out_len - seg * NWAY : 0;
         const uint32_t maxit = __reduce_max_sync(0xffffffffu, seg + tail), minit = __reduce_min_sync(0xffffffffu, seg);
         const bool aligned = !BYTE && __all_sync(0xffffffffu, (ring.head & 1u) == 0);
-        const bool compact = !BYTE && __all_sync(0xffffffffu, T.compact != 0);
+        const bool compact = __all_sync(0xffffffffu, T.compact != 0);
         const uint32_t unrank = base + S::UNRANK;
-        if (BYTE)                    o1_loop<NWAY, BYTE, false, false>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
-        else if (compact && aligned) o1_loop<NWAY, false, true, true>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
-        else if (compact)            o1_loop<NWAY, false, false, true>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
-        else                         o1_loop<NWAY, false, false, false>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
+        if (compact && aligned)      o1_loop<NWAY, BYTE, true, true>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
+        else if (compact)            o1_loop<NWAY, BYTE, false, true>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
+        else                         o1_loop<NWAY, BYTE, false, false>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
         __syncwarp();
     }
 }

@@ -36,7 +36,8 @@ def main():
     raw_len = torch.full((nblk,), n, dtype=torch.int32, device="cuda")
     for fs in args.flags.split(","):
         f = int(fs, 0)
-        cap = hb.rans_compress_bound_4x16(n, f)
+        legacy = bool(f & hb.ORDER_RANS4x8)          # e.g. --flags 0x40000000,0x40000001
+        cap = hb.load_library().hts_b200_compress_bound_4x8(n) if legacy else hb.rans_compress_bound_4x16(n, f)
         cap = (cap + 15) // 16 * 16
         d_comp = torch.empty(nblk * cap, dtype=torch.uint8, device="cuda")
         comp_off = torch.arange(nblk, dtype=torch.int64, device="cuda") * cap
@@ -65,18 +66,19 @@ def main():
         d_out = torch.empty(nblk * n, dtype=torch.uint8, device="cuda")
         out_len = torch.full((nblk,), n, dtype=torch.int32, device="cuda")
         in_len = comp_len.clone()
-        ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status)
+        method = torch.full((nblk,), 1, dtype=torch.uint8, device="cuda") if legacy else None
+        ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, method)
         assert int((status != 0).sum()) == 0, "decode failed"
         assert torch.equal(d_out, d_raw), "round trip mismatch"
         tt = 0.0
         for _ in range(args.reps):
             out_len.fill_(n); torch.cuda.synchronize()
             e0.record(stream)
-            ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, sync=False)
+            ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, method, sync=False)
             e1.record(stream); torch.cuda.synchronize()
             tt += e0.elapsed_time(e1)
         dec_gbs = nblk * n / (tt / args.reps * 1e-3) / 1e9
-        print(f"gen={args.gen} flags={f:#06x} ratio={csz / (nblk * n):.3f}  encode {enc_gbs:8.1f} GB/s   decode {dec_gbs:8.1f} GB/s", flush=True)
+        print(f"gen={args.gen} flags={f:#010x} ratio={csz / (nblk * n):.3f}  encode {enc_gbs:8.1f} GB/s   decode {dec_gbs:8.1f} GB/s", flush=True)
         del d_comp, d_out
 
 
