@@ -819,9 +819,9 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
 //    bucket is reached by a short scan; rows end in sentinels whose last slot is 0xfff).  This
 //    takes ns * (64 + 4 * (ns + 3)) bytes whatever the table precision: 1 KB for binned
 //    qualities, 12 KB for 46 symbols -- where byte-per-slot rows need 9-184 KB.
-//  * LUT (global memory, from the arena; 4x8 streams and alphabets that do not fit):
-//    rows[ctx][m] -> rank, fc[ctx * ns + rank] = F << 16 | C, as in the reference
-//    (rANS_static4x16pr.c:922-930).
+//  * the same compact layout in global memory (from the arena, L1/L2 cached) for alphabets that
+//    do not fit the shared-memory budget: 12 KB for 46 symbols, 282 KB for all 256 -- against
+//    0.2-1.3 MB for the reference's byte-per-slot rows (rANS_static4x16pr.c:922-930).
 //
 // Shared memory of one group: [0,256) rank -> symbol, [256,512) symbol -> rank, frequency
 // scratch, the word ring, then TAB bytes of compact tables.
@@ -842,8 +842,7 @@ struct O1Tables {
     uint32_t compact;       // 1: compact form in shared memory
     uint32_t tabs;          // compact: shared address of context 0's block [64 B coarse | 4 * (ns + 3) B entries]
     uint32_t bstride;       // compact: bytes per context block
-    uint8_t* g_rows;        // LUT form
-    uint32_t* g_fc;
+    uint8_t* g_tabs;        // the same layout in global memory when it does not fit (compact == 0)
     uint32_t ns, shift;
 };
 
@@ -872,56 +871,26 @@ __device__ bool build_o1_row_compact(const Grp<NWAY>& G, uint32_t F, const O1Tab
     // 4x8 tables written by the reference sum to M - 1 (rANS_static.c:122-130); slot M - 1 then
     // belongs to no symbol and resolves to the row's sentinel (never reached by a valid stream)
     if (total != M && !(allow_4095 && total == M - 1)) return false;
-    const uint32_t crs = T.tabs + ctx * T.bstride, row = crs + 64;
+    const uint32_t crs = T.tabs + ctx * T.bstride, row = crs + 64;   // shared form
+    uint8_t* gcrs = T.g_tabs + (size_t)ctx * T.bstride;             // global form
+    uint32_t* grow = reinterpret_cast<uint32_t*>(gcrs + 64);
     for (uint32_t k = 0; k < K; k++) {
         const uint32_t r = r0 + k;
         if (r >= ns) break;
         const uint32_t f = lds_u32(F + 4 * r) << sh;
         if (!f) continue;
         const uint32_t last = c + f - 1;
-        sts_u32(row + 4 * idx, (last << 20) | (r << 12) | (f - 1));
-        for (uint32_t q = (c + (1u << bs) - 1) >> bs; q <= (last >> bs); q++) sts_u8(crs + q, idx);
+        const uint32_t e = (last << 20) | (r << 12) | (f - 1);
+        if (T.compact) {
+            sts_u32(row + 4 * idx, e);
+            for (uint32_t q = (c + (1u << bs) - 1) >> bs; q <= (last >> bs); q++) sts_u8(crs + q, idx);
+        } else {
+            grow[idx] = e;
+            for (uint32_t q = (c + (1u << bs) - 1) >> bs; q <= (last >> bs); q++) gcrs[q] = (uint8_t)idx;
+        }
         idx++;
         c += f;
     }
-    G.sync();
-    return true;
-}
-
-// LUT form of one context row (global memory).  Sums of M - 1 are accepted for 4x8.
-template <int NWAY>
-__device__ bool build_o1_row_lut(const Grp<NWAY>& G, uint32_t F, const O1Tables& T, uint32_t ctx, uint32_t Tsum,
-                                 bool allow_4095) {
-    constexpr int K = 256 / NWAY;
-    const uint32_t M = 1u << T.shift;
-    uint32_t sh = 0;
-    if (Tsum < M) while ((Tsum << sh) < M) sh++;
-    uint32_t mine = 0;
-    bool bad = false;
-    for (int k = 0; k < K; k++) {
-        uint32_t f = lds_u32(F + 4 * (G.glane * K + k)) << sh;
-        if (f > M) bad = true;
-        mine += f;
-    }
-    uint32_t total;
-    uint32_t c = G.exscan(bad ? 2 * M : mine, &total);
-    if (total != M && !(allow_4095 && total == M - 1)) return false;
-    for (int k = 0; k < K; k++) {
-        uint32_t sj = G.glane * K + k;
-        uint32_t f = lds_u32(F + 4 * sj) << sh;
-        if (sj < T.ns) T.g_fc[ctx * T.ns + sj] = (f << 16) | c;
-        sts_u32(F + 4 * sj, (f << 16) | c);
-        c += f;
-    }
-    G.sync();
-    uint8_t* rowp = T.g_rows + (size_t)ctx * M;
-    for (uint32_t sj = 0; sj < T.ns; sj++) {
-        uint32_t e = lds_u32(F + 4 * sj);
-        uint32_t f = e >> 16, cs = e & 0xffffu;
-        for (uint32_t k = G.glane; k < f; k += NWAY) rowp[cs + k] = (uint8_t)sj;
-    }
-    G.sync();
-    if (total == M - 1 && G.glane == 0) rowp[M - 1] = rowp[M - 2];   // rANS_static.c:799
     G.sync();
     return true;
 }
@@ -999,28 +968,28 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     // ---- table storage
     O1Tables T;
     T.ns = ns; T.shift = shift;
-    T.g_rows = nullptr; T.g_fc = nullptr;
+    T.g_tabs = nullptr;
     T.bstride = 64 + 4 * (ns + 3);
     T.tabs = tabs;
     T.compact = (o1_compact_bytes(ns) <= (uint32_t)S::TAB) ? 1u : 0u;
+    const uint32_t nwords = ns * (T.bstride / 4);
     if (T.compact) {
-        for (uint32_t k = G.glane; k < ns * (T.bstride / 4); k += NWAY)     // coarse: 0, entries: sentinels
+        for (uint32_t k = G.glane; k < nwords; k += NWAY)                    // coarse: 0, entries: sentinels
             sts_u32(tabs + 4 * k, (k % (T.bstride / 4)) < 16 ? 0u : O1_SENTINEL);
     } else {
-        const uint64_t rows_bytes = ((uint64_t)ns * M + 15) & ~15ull;
         uint8_t* a = nullptr;
-        if (G.glane == 0) a = arena_alloc(W, rows_bytes + (uint64_t)ns * ns * 4);
-        T.g_rows = const_cast<uint8_t*>(G.bcast_ptr(a));
-        if (!T.g_rows) return ST_ARENA;
-        T.g_fc = reinterpret_cast<uint32_t*>(T.g_rows + rows_bytes);
-        for (uint32_t k = G.glane; k < ns * ns; k += NWAY) T.g_fc[k] = 0u;       // absent (ctx,sym) pairs: F = 0
+        if (G.glane == 0) a = arena_alloc(W, (uint64_t)nwords * 4);
+        T.g_tabs = const_cast<uint8_t*>(G.bcast_ptr(a));
+        if (!T.g_tabs) return ST_ARENA;
+        uint32_t* gw = reinterpret_cast<uint32_t*>(T.g_tabs);
+        for (uint32_t k = G.glane; k < nwords; k += NWAY) gw[k] = (k % (T.bstride / 4)) < 16 ? 0u : O1_SENTINEL;
     }
     G.sync();
 
     // ---- phase 2: one row per context; lane 0 parses, the group fills
     if (!BYTE) {
         for (uint32_t ci = 0; ci < ns; ci++) {               // :967-998 (ascending symbol == ascending rank)
-            for (uint32_t k = G.glane; k < (T.compact ? ns : 256u); k += NWAY) sts_u32(Ftmp + 4 * k, 0u);
+            for (uint32_t k = G.glane; k < ns; k += NWAY) sts_u32(Ftmp + 4 * k, 0u);
             G.sync();
             uint32_t Tsum = 0;
             if (G.glane == 0) {                              // decode_freq_d :327-358
@@ -1041,8 +1010,7 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
             err = G.bcast(err); Tsum = G.bcast(Tsum);
             if (err) return ST_FORMAT;
             if (!Tsum) continue;                             // :977-980
-            if (T.compact ? !build_o1_row_compact<NWAY>(G, Ftmp, T, ci, Tsum)
-                          : !build_o1_row_lut<NWAY>(G, Ftmp, T, ci, Tsum, false)) return ST_FORMAT;
+            if (!build_o1_row_compact<NWAY>(G, Ftmp, T, ci, Tsum)) return ST_FORMAT;
         }
     } else {
         // rANS_static.c:748-813: outer "sym [run]" list of contexts, one 4x8 table each (second pass:
@@ -1050,7 +1018,7 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
         uint32_t run_i = 0, ctx = 0;
         if (G.glane == 0) ctx = rd.get();
         for (;;) {
-            for (uint32_t k = G.glane; k < (T.compact ? ns : 256u); k += NWAY) sts_u32(Ftmp + 4 * k, 0u);
+            for (uint32_t k = G.glane; k < ns; k += NWAY) sts_u32(Ftmp + 4 * k, 0u);
             G.sync();
             uint32_t x = 0;
             if (G.glane == 0) {
@@ -1062,8 +1030,7 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
             err = G.bcast(err); ctx = G.bcast(ctx); x = G.bcast(x);
             if (err) return ST_FORMAT;
             const uint32_t rctx = lds_u8(rank + ctx);
-            if (T.compact ? !build_o1_row_compact<NWAY>(G, Ftmp, T, rctx, 4096u, true)
-                          : !build_o1_row_lut<NWAY>(G, Ftmp, T, rctx, 4096u, true)) return ST_FORMAT;
+            if (!build_o1_row_compact<NWAY>(G, Ftmp, T, rctx, 4096u, true)) return ST_FORMAT;
             uint32_t more = 0;
             if (G.glane == 0) {
                 if (!run_i && ctx + 1 == rd.peek()) { rd.get(); ctx++; run_i = rd.get(); }
@@ -1163,12 +1130,21 @@ __device__ __forceinline__ uint32_t o1_symbol(uint32_t& R, uint32_t& cs, const O
         cs = COMPACT ? T.tabs + r * T.bstride : r;
         return r;
     }
-    uint32_t sr = T.g_rows[(size_t)cs * (mask + 1u) + m];
-    sr = min(sr, T.ns - 1u);                                 // rows of never-seen contexts are uninitialised
-    const uint32_t e = T.g_fc[cs * T.ns + sr];
-    R = (e >> 16) * (R >> T.shift) + m - (e & 0xffffu);
-    cs = sr;
-    return sr;
+    // the same look-up in global memory (cs = rank of the context)
+    const uint8_t* blk = T.g_tabs + (size_t)cs * T.bstride;
+    const uint32_t ci = blk[m >> (T.shift - 6)];
+    const uint32_t* ep = reinterpret_cast<const uint32_t*>(blk + 64) + ci;
+    const uint32_t e0 = ep[0], e1 = ep[1], e2 = ep[2];
+    const uint32_t mk = m << 20;
+    uint32_t e = (mk > e1) ? e2 : ((mk > e0) ? e1 : e0);
+    if (mk > e) {
+        ep += 3;
+        do { e = *ep++; } while (mk > e);
+    }
+    const uint32_t q = R >> T.shift;
+    R = (e & 0xfffu) * (q + 1u) + (q + m - (e >> 20));
+    cs = (e >> 12) & 0xffu;
+    return cs;
 }
 
 // `minit` (warp-uniform) = steps for which every lane of the warp is active; they run four to a
@@ -1250,7 +1226,7 @@ __global__ void __launch_bounds__(32, SMALL ? 28 : 1) dec_o1_kernel(DecWork* W, 
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         O1Tables T;
         T.compact = 1; T.tabs = base + S::TABO; T.bstride = 0;
-        T.g_rows = nullptr; T.g_fc = nullptr; T.ns = 1; T.shift = 12;
+        T.g_tabs = nullptr; T.ns = 1; T.shift = 12;
         uint32_t R = 0, ctx0 = 0;
         const uint8_t* first_word = nullptr;
         bool ok = false;
