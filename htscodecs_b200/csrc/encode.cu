@@ -34,7 +34,7 @@ namespace hb {
 // descriptors
 // ------------------------------------------------------------------------------------------
 struct EncSym {            // RansEncSymbol, rANS_word.h:170-181 (16 bytes)
-    uint32_t x_max, rcp_freq, bias, cmpl_shift;   // cmpl_freq | (rcp_shift - 32) << 16
+    uint32_t x_max, rcp_freq, bias, cmpl_shift;   // cmpl_freq << 16 | (rcp_shift - 32)
 };
 
 struct EncStream {
@@ -165,13 +165,13 @@ __device__ __forceinline__ EncSym make_sym(uint32_t start, uint32_t freq, uint32
     if (freq < 2) {
         s.rcp_freq = ~0u;
         s.bias = start + (1u << bits) - 1;
-        s.cmpl_shift = cmpl;                            // shift 0
+        s.cmpl_shift = cmpl << 16;                      // shift 0
     } else {
         uint32_t sh = 0;
         while (freq > (1u << sh)) sh++;
         s.rcp_freq = (uint32_t)(((1ull << (sh + 31)) + freq - 1) / freq);
         s.bias = start;
-        s.cmpl_shift = cmpl | ((sh - 1) << 16);
+        s.cmpl_shift = (cmpl << 16) | (sh - 1);
     }
     return s;
 }
@@ -578,9 +578,41 @@ __device__ __forceinline__ uint32_t enc_put(uint32_t x, bool act, const EncSym s
     }
     wp -= 2 * __popc(m);
     if (act) {
-        const uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift >> 16);
-        x = x + s.bias + q * (s.cmpl_shift & 0xffffu);
+        const uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift & 31u);
+        x = x + s.bias + q * (s.cmpl_shift >> 16);
     }
+    return x;
+}
+
+// The X_32 Nx16 step in PTX (every lane active): 15 instructions, one predicate feeding the vote,
+// the compacted 16-bit store and the state shift.  `wpo` = write offset from `base` (moves down).
+__device__ __forceinline__ uint32_t enc_put_x32(uint32_t x, const EncSym s, uint32_t& wpo, const uint8_t* base, uint32_t gt) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 b, k, t, q;\n\t"
+        ".reg .b16 h;\n\t"
+        ".reg .b64 a;\n\t"
+        "setp.ge.u32 p, %0, %2;\n\t"
+        "vote.sync.ballot.b32 b, p, 0xffffffff;\n\t"
+        "and.b32 k, b, %7;\n\t"
+        "popc.b32 k, k;\n\t"
+        "mad.lo.u32 t, k, 0xfffffffe, %1;\n\t"
+        "mad.wide.u32 a, t, 1, %6;\n\t"
+        "cvt.u16.u32 h, %0;\n\t"
+        "@p st.global.u16 [a+-2], h;\n\t"
+        "@p shr.u32 %0, %0, 16;\n\t"
+        "popc.b32 k, b;\n\t"
+        "mad.lo.u32 %1, k, 0xfffffffe, %1;\n\t"
+        "add.u32 t, %0, %4;\n\t"
+        "mul.hi.u32 q, %0, %3;\n\t"
+        "shf.r.wrap.b32 q, q, 0, %5;\n\t"
+        "shr.u32 k, %5, 16;\n\t"
+        "mad.lo.u32 %0, q, k, t;\n\t"
+        "}"
+        : "+r"(x), "+r"(wpo)
+        : "r"(s.x_max), "r"(s.rcp_freq), "r"(s.bias), "r"(s.cmpl_shift), "l"(base), "r"(gt)
+        : "memory");
     return x;
 }
 
@@ -602,8 +634,8 @@ __device__ __forceinline__ uint32_t enc_put8(uint32_t x, bool act, const EncSym 
     x = e2 ? (x1 >> 8) : x1;
     wp -= __popc(m1) + __popc(m2);
     if (act) {
-        const uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift >> 16);
-        x = x + s.bias + q * (s.cmpl_shift & 0xffffu);
+        const uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift & 31u);
+        x = x + s.bias + q * (s.cmpl_shift >> 16);
     }
     return x;
 }
@@ -1053,6 +1085,8 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
     uint8_t* srank = gsm + NSCAP * NSCAP * 16;                      // order-1 only
     uint32_t* cursor = &W->next_misc[cursor_id];
     const uint32_t nstreams = W->nstreams;
+    uint32_t gt_mask;
+    asm("mov.u32 %0, %%lanemask_gt;" : "=r"(gt_mask));
 
     // streams are claimed EG::G at a time (first round statically by CTA index, which spreads a batch
     // that fits in one wave evenly over the SMs); those of another nway/order/size class are skipped
@@ -1124,8 +1158,15 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                 EncSym sy[B];
 #pragma unroll
                 for (int u = 0; u < B; u++) sy[u] = ssym[b[u]];
+                if (NWAY == 32 && !BYTE) {
+                    uint32_t wpo = (uint32_t)(wp - S->out);
 #pragma unroll
-                for (int u = 0; u < B; u++) x = enc_step<NWAY, BYTE>(x, true, sy[u], wp, G);
+                    for (int u = 0; u < B; u++) x = enc_put_x32(x, sy[u], wpo, S->out, gt_mask);
+                    wp = S->out + wpo;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < B; u++) x = enc_step<NWAY, BYTE>(x, true, sy[u], wp, G);
+                }
             }
             for (uint32_t u = 0; u < r; u++) {                       // fewer than B rows left (already fetched)
                 uint32_t bsel = nb[0];
@@ -1176,8 +1217,15 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                     }
                     rs = rc;
                 }
+                if (NWAY == 32 && !BYTE) {
+                    uint32_t wpo = (uint32_t)(wp - S->out);
 #pragma unroll
-                for (int u = 0; u < 4; u++) x = enc_step<NWAY, BYTE>(x, true, sy[u], wp, G);
+                    for (int u = 0; u < 4; u++) x = enc_put_x32(x, sy[u], wpo, S->out, gt_mask);
+                    wp = S->out + wpo;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) x = enc_step<NWAY, BYTE>(x, true, sy[u], wp, G);
+                }
             }
             for (; k + 1 < maxsteps; k++) {
                 const uint32_t rc = srank[src.get()];
@@ -1452,10 +1500,12 @@ int encode_init(int device) {
     cudaFuncSetAttribute(enc_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM);
     g_grid_enc[0][0] = occ_grid(enc_rans_kernel<4, 0, 16>, SM_O0_4, g_sms_enc);
     g_grid_enc[1][0] = occ_grid(enc_rans_kernel<32, 0, 16>, SM_O0_32, g_sms_enc);
+    cudaFuncSetAttribute(enc_rans_kernel<32, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7168);
     g_grid_o1_4_s = occ_grid(enc_rans_kernel<4, 1, 16>, SM_O1_4_S, g_sms_enc);
     occ_grid(enc_rans_kernel<4, 0, 16, true>, SM_O0_4, g_sms_enc);
     occ_grid(enc_rans_kernel<4, 1, 16, true>, SM_O1_4_S, g_sms_enc);
     g_grid_o1_32_s = occ_grid(enc_rans_kernel<32, 1, 16>, SM_O1_32_S, g_sms_enc);
+    cudaFuncSetAttribute(enc_rans_kernel<32, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7168);
     g_grid_o1_32_l = occ_grid(enc_rans_kernel<32, 1, 48>, SM_O1_32_L, g_sms_enc);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1656,8 +1706,11 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
         // shared memory at high occupancy) or the large one (ns > 16: shared up to 48 symbols, else global)
         if (any4[0])  { enc_rans_kernel<4, 0, 16><<<g_grid_enc[0][0], 32, SM_O0_4, st>>>(dW, 0, 0, 256); launches++; }
         if (any4[1])  { enc_rans_kernel<4, 1, 16><<<g_grid_o1_4_s, 32, SM_O1_4_S, st>>>(dW, 1, 0, 256); launches++; }
-        if (any32[0]) { enc_rans_kernel<32, 0, 16><<<g_grid_enc[1][0], 32, SM_O0_32, st>>>(dW, 2, 0, 256); launches++; }
-        if (any32[1]) { enc_rans_kernel<32, 1, 16><<<g_grid_o1_32_s, 32, SM_O1_32_S, st>>>(dW, 3, 0, 16); launches++;
+        // A batch that fits in one wave of 28 warps per SM runs ~12 % faster when the kernel is held to
+        // 28 resident warps (the CTA scheduler does not spread a 32-per-SM grid evenly): pad the request.
+        const int pad32 = (streams.size() <= (size_t)28 * g_sms_enc) ? 7168 : 0;
+        if (any32[0]) { enc_rans_kernel<32, 0, 16><<<g_grid_enc[1][0], 32, std::max(SM_O0_32, pad32), st>>>(dW, 2, 0, 256); launches++; }
+        if (any32[1]) { enc_rans_kernel<32, 1, 16><<<g_grid_o1_32_s, 32, std::max(SM_O1_32_S, pad32), st>>>(dW, 3, 0, 16); launches++;
                         enc_rans_kernel<32, 1, 48><<<g_grid_o1_32_l, 32, SM_O1_32_L, st>>>(dW, 4, 16, 256); launches++; }
         if (any8[0])  { enc_rans_kernel<4, 0, 16, true><<<g_grid_enc[0][0], 32, SM_O0_4, st>>>(dW, 5, 0, 256); launches++; }
         if (any8[1])  { enc_rans_kernel<4, 1, 16, true><<<g_grid_o1_4_s, 32, SM_O1_4_S, st>>>(dW, 6, 0, 256); launches++; }
