@@ -518,15 +518,19 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
                 if (i + HT < nv) { nq = __ldg(v + i + HT); nc = in[head + (i + HT) * 16 - 1]; }
                 if (i < nv) {
                     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                    uint32_t rc = rank[c0] * ns;                     // context of the chunk's first byte
+                    // all 17 rank look-ups first (the counter stores below could alias the rank table as far
+                    // as the compiler knows, which would serialise look-up and update per byte)
+                    uint32_t rk[16];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
 #pragma unroll
-                        for (int bb = 0; bb < 4; bb++) {
-                            const uint32_t r = rank[(w[k] >> (8 * bb)) & 0xffu];
-                            (*hist_ctr(myarea, rc + r, lane))++;
-                            rc = r * ns;
-                        }
+                        for (int bb = 0; bb < 4; bb++) rk[4 * k + bb] = rank[(w[k] >> (8 * bb)) & 0xffu];
+                    }
+                    uint32_t rc = rank[c0] * ns;                     // context of the chunk's first byte
+#pragma unroll
+                    for (int t = 0; t < 16; t++) {
+                        (*hist_ctr(myarea, rc + rk[t], lane))++;
+                        rc = rk[t] * ns;
                     }
                 }
                 since += 16;
