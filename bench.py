@@ -216,8 +216,6 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3):
 def run_ours(args, rank, world, local_rank):
     import torch
     import htscodecs_b200 as hb
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_lib import Oracle
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -230,11 +228,10 @@ def run_ours(args, rank, world, local_rank):
     ctx = hb.Context(local_rank)
     nblk, distinct = args.blocks, min(args.distinct, args.blocks)
     blocks = make_blocks(distinct, rank)
-    # compressed inputs: X_32 order-0 streams (the bench measures DECODE; the streams come from the
-    # encoder under test when available, else from the CPU oracle as data preparation only)
-    oracle = Oracle()
-    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
-        comps = list(ex.map(lambda b: oracle.compress(b.tobytes(), 4), blocks))
+    # compressed inputs: X_32 order-0 streams made by the encoder under test (the GPU encoder; its
+    # byte-exactness against the CPU checkers is what tests/test_gpu_encode.py establishes)
+    comps, cst = ctx.compress_many([b.tobytes() for b in blocks], [hb.RANS_ORDER_X32] * distinct)
+    assert (cst == 0).all(), "GPU encode of the bench inputs failed"
     in_len = np.array([len(comps[i % distinct]) for i in range(nblk)], np.uint32)
     in_off = np.zeros(nblk, np.uint64)
     in_off[1:] = np.cumsum(in_len[:-1].astype(np.uint64))

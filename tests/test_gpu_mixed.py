@@ -80,3 +80,25 @@ def test_big_blocks(ctx, oracle):
         assert c == want, hex(f)
     out, st = ctx.uncompress_many(comp, [len(b) for b in blocks], [1 if f & hb.ORDER_RANS4x8 else 0 for f in orders])
     assert (st == 0).all() and out == blocks
+
+
+def test_dropin_calls_from_many_host_threads(oracle):
+    """The reference is re-entrant (one block per thread, rANS_static4x16pr.c:853-858); the drop-in
+    symbols keep a context per host thread, so concurrent callers must not disturb each other."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def work(t):
+        bad = 0
+        for i in range(12):
+            d = synth.qual_block(1000 * t + i, 30000 + 977 * i).tobytes()
+            f = (0, 1, 4, 5, 0x40, 0x81)[i % 6]
+            c = hb.rans_compress_4x16(d, f)
+            bad += c != oracle.compress(d, f)
+            bad += hb.rans_uncompress_4x16(c) != d
+            c8 = hb.rans_compress(d, i & 1)
+            bad += c8 != oracle.compress_4x8(d, i & 1)
+            bad += hb.rans_uncompress(c8) != d
+        return bad
+
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        assert sum(ex.map(work, range(6))) == 0
