@@ -1305,6 +1305,8 @@ __global__ void __launch_bounds__(RLE_T) rle_kernel(DecWork* W, int32_t* status,
     __shared__ unsigned long long wtot64[RLE_T / 32];
     __shared__ uint32_t* runval_s;
     __shared__ int skip_s;
+    __shared__ uint32_t s_off[RLE_T + 1];
+    __shared__ uint8_t s_lit[RLE_T];
     const uint32_t tid = threadIdx.x;
     for (uint32_t li = blockIdx.x; li < W->nrle; li += gridDim.x) {
         const uint32_t ci = W->rle_list[li];
@@ -1353,7 +1355,9 @@ __global__ void __launch_bounds__(RLE_T) rle_kernel(DecWork* W, int32_t* status,
         }
         __syncthreads();
 
-        // pass B
+        // pass B: per tile of RLE_T literals, output offsets by a CTA scan, then the tile's output
+        // is produced 16 aligned bytes per thread (binary search for the chunk's first literal,
+        // then a walk), so the stores are full 128-bit lines instead of one byte loop per run.
         const uint8_t* lit = c.t1;
         const uint32_t nlit = c.t1_size;
         uint8_t* out = c.t2;
@@ -1371,11 +1375,46 @@ __global__ void __launch_bounds__(RLE_T) rle_kernel(DecWork* W, int32_t* status,
                 if (isr) { uint32_t kk = kbase + k; len += (kk < nvar) ? runval[kk] : 0u; }
             }
             unsigned long long ltot, off = block_exscan<unsigned long long>(len, wtot64, &ltot);
-            off += opos;
-            if (i < nlit) {
-                if (off + len > c.osz) overflow = 1;         // rle.c:161,172
-                else for (unsigned long long q = 0; q < len; q++) out[off + q] = (uint8_t)b;
+            if (opos + ltot > c.osz) { overflow = 1; break; }            // rle.c:161,172 (CTA-uniform)
+            s_off[tid] = (uint32_t)off;                                  // tile-relative; ltot <= osz < 2^31
+            s_lit[tid] = (uint8_t)b;
+            if (tid == 0) s_off[RLE_T] = (uint32_t)ltot;
+            __syncthreads();
+            const uint32_t nt = min((uint32_t)RLE_T, nlit - t0);         // literals in this tile
+            uint8_t* tout = out + opos;
+            const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(tout) & 15);
+            // chunk m covers tile-relative bytes [16 m - skew, 16 m - skew + 16)
+            const uint32_t nchunk = (uint32_t)((ltot + skew + 15) / 16);
+            for (uint32_t m = tid; m < nchunk; m += RLE_T) {
+                const int64_t c0 = (int64_t)16 * m - skew;
+                const uint32_t lo = c0 < 0 ? 0u : (uint32_t)c0;
+                const uint32_t hi = (uint32_t)min((unsigned long long)(c0 + 16), ltot);
+                // last literal whose offset is <= lo
+                uint32_t a = 0, z = nt;
+                while (z - a > 1) { const uint32_t mid = (a + z) >> 1; if (s_off[mid] <= lo) a = mid; else z = mid; }
+                uint32_t j = a, nxt = (j + 1 < nt) ? s_off[j + 1] : (uint32_t)ltot;
+                unsigned long long wl = 0, wh = 0;                       // the chunk's 16 bytes
+                uint32_t cur = s_lit[j];
+                auto ones = [](uint32_t k) { return k >= 8 ? ~0ull : ((1ull << (8 * k)) - 1ull); };   // k low bytes set
+                for (uint32_t p = lo; p < hi;) {
+                    while (p >= nxt) { j++; cur = s_lit[j]; nxt = (j + 1 < nt) ? s_off[j + 1] : (uint32_t)ltot; }
+                    const uint32_t e = min(nxt, hi);
+                    const uint32_t q0 = (uint32_t)(p - c0), q1 = (uint32_t)(e - c0);     // 0 <= q0 < q1 <= 16
+                    const unsigned long long v = cur * 0x0101010101010101ull;
+                    wl |= v & (ones(min(q1, 8u)) & ~ones(min(q0, 8u)));
+                    wh |= v & (ones(max(q1, 8u) - 8) & ~ones(max(q0, 8u) - 8));
+                    p = e;
+                }
+                if (hi - lo == 16) {
+                    *reinterpret_cast<uint4*>(tout + c0) = make_uint4((uint32_t)wl, (uint32_t)(wl >> 32), (uint32_t)wh, (uint32_t)(wh >> 32));
+                } else {
+                    for (uint32_t p = lo; p < hi; p++) {
+                        const uint32_t q = (uint32_t)(p - c0);
+                        tout[p] = (uint8_t)(q < 8 ? (wl >> (8 * q)) : (wh >> (8 * (q - 8))));
+                    }
+                }
             }
+            __syncthreads();
             opos += ltot;
             kbase += tot;
         }

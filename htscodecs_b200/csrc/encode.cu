@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(TT) enc_transform_kernel(EncWork* W) {
     __shared__ int score[256];
     __shared__ uint32_t wtot[TT / 32];
     __shared__ int wmax[TT / 32];
+    __shared__ int s_sp[TT];
     __shared__ uint32_t s_n, s_cnt;
     const uint32_t tid = threadIdx.x;
     for (uint32_t li = blockIdx.x; li < W->nleaves; li += gridDim.x) {
@@ -312,9 +313,20 @@ __global__ void __launch_bounds__(TT) enc_transform_kernel(EncWork* W) {
                 score[tid] = 0;
                 __syncthreads();
                 // rle_find_syms: +1 when a byte repeats its predecessor, -1 otherwise
-                for (uint32_t i = tid; i < cur_n; i += TT) {
-                    uint32_t b = cur[i];
-                    atomicAdd(&score[b], (i > 0 && cur[i - 1] == b) ? 1 : -1);
+                // (each thread scores 16 consecutive bytes and adds one total per stretch of equal
+                // bytes: run-heavy data would otherwise serialise on same-address atomics)
+                for (uint32_t t0 = 0; t0 < cur_n; t0 += TT * 16) {
+                    const uint32_t base = t0 + tid * 16;
+                    if (base >= cur_n) continue;
+                    const uint32_t cnt = min(16u, cur_n - base);
+                    int prev = base ? (int)cur[base - 1] : -1, sym = -1, acc = 0;
+                    for (uint32_t k = 0; k < cnt; k++) {
+                        const int b = cur[base + k];
+                        if (b != sym) { if (sym >= 0) atomicAdd(&score[sym], acc); sym = b; acc = 0; }
+                        acc += (prev == b) ? 1 : -1;
+                        prev = b;
+                    }
+                    atomicAdd(&score[sym], acc);
                 }
                 __syncthreads();
                 if (tid == 0) {
@@ -332,34 +344,74 @@ __global__ void __launch_bounds__(TT) enc_transform_kernel(EncWork* W) {
                 uint8_t* runs = L.rmeta + 272;
                 // A byte starts a literal unless it continues a run of an RLE symbol.  A run's varint
                 // is emitted at the run's LAST byte (varints appear in literal order either way).
+                // Each thread owns RE consecutive bytes of a TT*RE-byte tile: three register-resident
+                // walks over them, separated by one CTA scan each (literal count; position of the most
+                // recent literal start, a max-scan; varint bytes).
+                constexpr int RE = 16;
                 uint32_t lit_base = 0, run_base = 0;
-                int start_carry = -1;
-                for (uint32_t t0 = 0; t0 < cur_n; t0 += TT) {
-                    const uint32_t i = t0 + tid;
-                    uint32_t b = 0, isr = 0, is_start = 0, is_end = 0;
-                    if (i < cur_n) {
-                        b = cur[i];
-                        isr = score[b] > 0;
-                        is_start = !(isr && i > 0 && cur[i - 1] == b);
-                        is_end = isr && (i + 1 == cur_n || cur[i + 1] != b);
+                int start_carry = -1;                                // last literal start before this tile
+                for (uint32_t t0 = 0; t0 < cur_n; t0 += TT * RE) {
+                    const uint32_t base = t0 + tid * RE;
+                    const uint32_t cnt = base < cur_n ? min((uint32_t)RE, cur_n - base) : 0u;
+                    uint8_t bv[RE];
+                    uint32_t isr_mask = 0;
+#pragma unroll
+                    for (int k = 0; k < RE; k++) {
+                        bv[k] = (uint32_t)k < cnt ? cur[base + k] : 0;
+                        if ((uint32_t)k < cnt && score[bv[k]] > 0) isr_mask |= 1u << k;
+                    }
+                    const int prevb = (cnt && base > 0) ? (int)cur[base - 1] : -1;
+                    const int nextb = (cnt && base + cnt < cur_n) ? (int)cur[base + cnt] : -1;
+                    // walk 1: which bytes start a literal
+                    uint32_t start_mask = 0;
+                    int last = -1;
+                    {
+                        int pb = prevb;
+#pragma unroll
+                        for (int k = 0; k < RE; k++) {
+                            if ((uint32_t)k < cnt) {
+                                const bool st = !(((isr_mask >> k) & 1u) && pb == (int)bv[k]);
+                                if (st) { start_mask |= 1u << k; last = (int)(base + k); }
+                                pb = bv[k];
+                            }
+                        }
                     }
                     uint32_t tot;
-                    uint32_t lidx = cta_exscan<uint32_t>(is_start, wtot, &tot);
-                    int sp = cta_incl_maxscan(is_start ? (int)i : -1, wmax);
-                    sp = max(sp, start_carry);
-                    if (is_start) L.lits[lit_base + lidx] = (uint8_t)b;
-                    uint32_t vlen = 0, rl = 0;
-                    if (is_end) { rl = i - (uint32_t)sp; vlen = (uint32_t)var_len_u32(rl); }
+                    const uint32_t lidx = cta_exscan<uint32_t>(__popc(start_mask), wtot, &tot);
+                    int sp = cta_incl_maxscan(last, wmax);           // inclusive over threads ...
+                    s_sp[tid] = sp;
+                    __syncthreads();
+                    sp = tid ? max(s_sp[tid - 1], start_carry) : start_carry;   // ... made exclusive + tile carry
+                    const int tile_last = max(s_sp[TT - 1], start_carry);
+                    __syncthreads();
+                    // walk 2: literals out, run lengths and their varint sizes
+                    uint32_t rl[RE], vlen_tot = 0, end_mask = 0;
+                    {
+                        uint32_t li = lit_base + lidx;
+                        int cs = sp;
+#pragma unroll
+                        for (int k = 0; k < RE; k++) {
+                            rl[k] = 0;
+                            if ((uint32_t)k < cnt) {
+                                if ((start_mask >> k) & 1u) { L.lits[li++] = bv[k]; cs = (int)(base + k); }
+                                const int nb = (k + 1 < (int)cnt) ? (int)bv[k + 1 < RE ? k + 1 : RE - 1] : nextb;
+                                if (((isr_mask >> k) & 1u) && nb != (int)bv[k]) {
+                                    end_mask |= 1u << k;
+                                    rl[k] = base + k - (uint32_t)cs;
+                                    vlen_tot += (uint32_t)var_len_u32(rl[k]);
+                                }
+                            }
+                        }
+                    }
                     uint32_t vtot;
-                    uint32_t voff = cta_exscan<uint32_t>(vlen, wtot, &vtot);
-                    if (is_end) var_put_u32(runs + run_base + voff, rl);
+                    uint32_t voff = cta_exscan<uint32_t>(vlen_tot, wtot, &vtot);
+                    // walk 3: the varints
+#pragma unroll
+                    for (int k = 0; k < RE; k++)
+                        if ((end_mask >> k) & 1u) voff += (uint32_t)var_put_u32(runs + run_base + voff, rl[k]);
                     lit_base += tot;
                     run_base += vtot;
-                    // carry the most recent literal start into the next tile
-                    if (tid == TT - 1) wmax[0] = sp;
-                    __syncthreads();
-                    start_carry = wmax[0];
-                    __syncthreads();
+                    start_carry = tile_last;
                 }
                 rmeta_len = 1 + nrs + run_base;
                 const uint32_t lit_len = lit_base;
