@@ -1499,7 +1499,25 @@ __global__ void __launch_bounds__(256) unstripe_kernel(DecWork* W, int32_t* stat
         __syncthreads();
         if (bad) { if (threadIdx.x == 0 && bad == 1) set_status(status, op.blk, ST_FORMAT); continue; }
         const uint32_t N = op.N, ulen = op.ulen;
-        for (uint32_t i = threadIdx.x; i < ulen; i += blockDim.x) op.out[i] = op.parts[at[i % N] + i / N];
+        const bool fast4 = N == 4 && (ulen & 15) == 0 && (reinterpret_cast<uintptr_t>(op.out) & 15) == 0 &&
+                           (reinterpret_cast<uintptr_t>(op.parts) & 3) == 0;
+        if (fast4) {
+            // one 32-bit word from each of the four sub-streams -> 16 interleaved output bytes
+            const uint32_t q = ulen / 4;
+            for (uint32_t t = threadIdx.x; t < ulen / 16; t += blockDim.x) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) w[j] = *reinterpret_cast<const uint32_t*>(op.parts + (size_t)j * q + 4 * (size_t)t);
+                uint4 v;                                     // output word e = bytes e of w[0..3]
+                v.x = __byte_perm(__byte_perm(w[0], w[1], 0x0040), __byte_perm(w[2], w[3], 0x0040), 0x5410);
+                v.y = __byte_perm(__byte_perm(w[0], w[1], 0x0051), __byte_perm(w[2], w[3], 0x0051), 0x5410);
+                v.z = __byte_perm(__byte_perm(w[0], w[1], 0x0062), __byte_perm(w[2], w[3], 0x0062), 0x5410);
+                v.w = __byte_perm(__byte_perm(w[0], w[1], 0x0073), __byte_perm(w[2], w[3], 0x0073), 0x5410);
+                reinterpret_cast<uint4*>(op.out)[t] = v;
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < ulen; i += blockDim.x) op.out[i] = op.parts[at[i % N] + i / N];
+        }
     }
 }
 

@@ -210,7 +210,24 @@ __global__ void __launch_bounds__(256) enc_stripe_kernel(EncWork* W) {
             for (uint32_t j = 0; j < B.N; j++) { at[j] = a; a += B.n / B.N + ((B.n % B.N) > j); }
         }
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < B.n; i += blockDim.x) B.tr[at[i % B.N] + i / B.N] = B.in[i];
+        const bool fast4 = B.N == 4 && (B.n & 15) == 0 && (reinterpret_cast<uintptr_t>(B.in) & 15) == 0 &&
+                           (reinterpret_cast<uintptr_t>(B.tr) & 3) == 0;
+        if (fast4) {
+            // 16 input bytes = 4 elements x 4 streams: one 32-bit word per stream, 128-byte lines per warp
+            const uint4* src = reinterpret_cast<const uint4*>(B.in);
+            const uint32_t q = B.n / 4;                      // bytes per stream (multiple of 4)
+            for (uint32_t t = threadIdx.x; t < B.n / 16; t += blockDim.x) {
+                const uint4 v = __ldg(src + t);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t sel = (uint32_t)j | ((4u + j) << 4);          // byte j of each of two words
+                    const uint32_t lo = __byte_perm(v.x, v.y, sel), hi = __byte_perm(v.z, v.w, sel);
+                    *reinterpret_cast<uint32_t*>(B.tr + (size_t)j * q + 4 * (size_t)t) = __byte_perm(lo, hi, 0x5410);
+                }
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < B.n; i += blockDim.x) B.tr[at[i % B.N] + i / B.N] = B.in[i];
+        }
     }
 }
 
