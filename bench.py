@@ -56,6 +56,8 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        if self.index is None:
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -223,9 +225,16 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    sampler = ClockSampler(local_rank)
+    # one nvidia-smi poller per job, not per rank: eight of them at 50 Hz contend on the driver and
+    # slow every rank's copies (the GPUs of one box share clocks policy; rank 0's is reported)
+    sampler = ClockSampler(local_rank if rank == 0 else None)
     sampler.start()                                          # nvidia-smi needs ~1 s before its first sample
     ctx = hb.Context(local_rank)
+    # host link policy of the e2e leg: overlapping H2D with D2H wins on one or two GPUs; with more GPUs
+    # active this host's aggregate device->host rate collapses under mixed traffic (tools/numa_probe.py:
+    # 304 GB/s D2H alone vs 134 GB/s with concurrent H2D at 8 GPUs), so inputs go first, results after
+    duplex = args.duplex if args.duplex != "auto" else ("full" if world <= 2 else "half")
+    ctx.set_copy_duplex(duplex == "full")
     nblk, distinct = args.blocks, min(args.distinct, args.blocks)
     blocks = make_blocks(distinct, rank)
     # compressed inputs: X_32 order-0 streams made by the encoder under test (the GPU encoder; its
@@ -371,7 +380,8 @@ def run_ours(args, rank, world, local_rank):
                    "blocks_per_gpu": nblk, "block_bytes": BLOCK, "distinct_blocks": distinct,
                    "compressed_bytes_per_gpu": c_bytes, "ratio": c_bytes / u_bytes,
                    "l2": "inputs+outputs (%.1f GiB) exceed the 126 MB L2; no flush needed" % ((c_bytes + u_bytes) / 2**30),
-                   "parallelism": f"blocks sharded over {world} GPU(s), no collective"},
+                   "parallelism": f"blocks sharded over {world} GPU(s), no collective",
+                   "e2e_copy_duplex": duplex},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": c_bytes, "d2h_bytes_per_step": u_bytes,
                 "steps": e2e_steps, "timer": "host perf_counter around hts_b200_uncompress_batch_host (synchronous)"},
         "gpu_launches": int(launches),
@@ -404,6 +414,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the CPU baseline leg")
     ap.add_argument("--skip-paths", action="store_true", help="skip the extra encode / order-1 / 4-way legs")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget for the reference leg")
+    ap.add_argument("--duplex", default="auto", choices=["auto", "full", "half"], help="host copy policy of the e2e leg")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

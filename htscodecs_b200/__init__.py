@@ -28,6 +28,7 @@ EXPORTS = [
     "hts_b200_stream", "hts_b200_uncompress_batch_dev", "hts_b200_uncompress_batch_host",
     "hts_b200_compress_batch_dev", "hts_b200_compress_batch_host", "rans4x16_uncompress_batch",
     "rans4x16_compress_batch", "hts_b200_peek_size", "hts_b200_host_alloc", "hts_b200_host_free",
+    "hts_b200_set_copy_duplex",
 ]
 
 _lib = None
@@ -82,6 +83,7 @@ def load_library():
     lib.hts_b200_host_alloc.restype = vp
     lib.hts_b200_host_alloc.argtypes = [C.c_size_t]
     lib.hts_b200_host_free.argtypes = [vp]
+    lib.hts_b200_set_copy_duplex.argtypes = [vp, C.c_int]
     _libc = C.CDLL(None)
     _libc.free.argtypes = [vp]
     lib._free = _libc.free
@@ -237,6 +239,10 @@ class Context:
     @property
     def stream(self):
         return self.lib.hts_b200_stream(self.h)
+
+    def set_copy_duplex(self, full):
+        """False: send every input of a host-buffer call before fetching any result (half duplex)."""
+        self.lib.hts_b200_set_copy_duplex(self.h, 1 if full else 0)
 
     def last_error(self):
         return self.lib.hts_b200_last_error(self.h).decode()

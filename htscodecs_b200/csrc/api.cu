@@ -83,6 +83,16 @@ struct Stage {
     cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
     cudaStream_t s_compute = nullptr;   // one per stage: a block is decoded by ONE warp, so a chunk's kernels
                                         // last as long as its slowest block; chunks must overlap on the SMs
+    // what the device->host half of a chunk needs (it may be enqueued later than the first half)
+    int c_a = 0, c_n = 0; bool c_dense = false; uint64_t c_lo = 0, c_bytes = 0;
+    int init() {
+        if (s_compute) return 0;
+        if (cudaEventCreateWithFlags(&h2d_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&compute_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d2h_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&s_compute, cudaStreamNonBlocking) != cudaSuccess) return -1;
+        return 0;
+    }
     void release() {
         if (s_compute) cudaStreamDestroy(s_compute);
         d_in.release(); d_out.release(); d_off.release(); d_u32.release(); d_method.release();
@@ -103,7 +113,9 @@ struct hts_b200_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     DecSlot dec;                        // device-resident API
     EncSlot enc;
-    Stage stage[NSTAGE];
+    std::vector<Stage> stage;           // NSTAGE slots reused round-robin (full duplex) or one per chunk (half duplex)
+    cudaEvent_t all_h2d = nullptr;
+    bool full_duplex = true;            // overlap host->device with device->host copies (see hts_b200_set_copy_duplex)
     PinBuf<uint8_t> pin_in, pin_out;    // pointer-array wrappers
     size_t arena_hint = 0;
     unsigned long long launches = 0;
@@ -135,15 +147,11 @@ extern "C" hts_b200_ctx* hts_b200_create(int device) {
         delete ctx;
         return nullptr;
     }
-    for (int s = 0; s < NSTAGE; s++) {
-        cudaEventCreateWithFlags(&ctx->stage[s].h2d_done, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ctx->stage[s].compute_done, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ctx->stage[s].d2h_done, cudaEventDisableTiming);
-        if (cudaStreamCreateWithFlags(&ctx->stage[s].s_compute, cudaStreamNonBlocking) != cudaSuccess) {
-            hts_b200_destroy(ctx);
-            return nullptr;
-        }
-    }
+    ctx->stage.resize(NSTAGE);
+    for (int s = 0; s < NSTAGE; s++)
+        if (ctx->stage[s].init()) { hts_b200_destroy(ctx); return nullptr; }
+    cudaEventCreateWithFlags(&ctx->all_h2d, cudaEventDisableTiming);
+    if (const char* e = getenv("HTSCODECS_B200_COPY_DUPLEX")) ctx->full_duplex = strcmp(e, "half") != 0;
     return ctx;
 }
 
@@ -153,7 +161,8 @@ extern "C" void hts_b200_destroy(hts_b200_ctx* ctx) {
     cudaDeviceSynchronize();
     ctx->dec.release();
     ctx->enc.release();
-    for (int s = 0; s < NSTAGE; s++) ctx->stage[s].release();
+    for (auto& st : ctx->stage) st.release();
+    if (ctx->all_h2d) cudaEventDestroy(ctx->all_h2d);
     ctx->pin_in.release(); ctx->pin_out.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -164,6 +173,7 @@ extern "C" void hts_b200_destroy(hts_b200_ctx* ctx) {
 extern "C" const char* hts_b200_last_error(const hts_b200_ctx* ctx) { return ctx ? ctx->err : "no context"; }
 extern "C" unsigned long long hts_b200_launch_count(const hts_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* hts_b200_stream(const hts_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" void hts_b200_set_copy_duplex(hts_b200_ctx* ctx, int full) { if (ctx) ctx->full_duplex = full != 0; }
 extern "C" void* hts_b200_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -317,7 +327,18 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
     std::vector<int> redo;
     std::vector<uint32_t> caps(out_len, out_len + nblk);           // capacities, for retries
 
-    auto launch_chunk = [&](int k, Stage& S, bool sync_mode) -> int {
+    auto launch_out = [&](Stage& S) -> int {                         // device->host half of a chunk
+        const int a = S.c_a, n = S.c_n;
+        const uint64_t* h_out_off = S.h_off.p + n;
+        CK(cudaStreamWaitEvent(ctx->s_out, S.compute_done, 0));
+        CK(cudaMemcpyAsync(S.h_u32.p + n, S.d_u32.p + n, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->s_out));   // out_len + status
+        if (S.c_dense) CK(cudaMemcpyAsync(out_base + S.c_lo, S.d_out.p, S.c_bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+        else for (int i = 0; i < n; i++)
+            CK(cudaMemcpyAsync(out_base + out_off[a + i], S.d_out.p + h_out_off[i], caps[a + i], cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaEventRecord(S.d2h_done, ctx->s_out));
+        return 0;
+    };
+    auto launch_chunk = [&](int k, Stage& S, bool defer_out) -> int {
         const int a = cuts[k], b = cuts[k + 1], n = b - a;
         Range ri = span_of(in_off, in_len, a, b);
         Range ro = span_of(out_off, caps.data(), a, b);
@@ -389,15 +410,8 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
             ctx->launches += l;
         }
         CK(cudaEventRecord(S.compute_done, cs));
-        // ---- D2H
-        CK(cudaStreamWaitEvent(ctx->s_out, S.compute_done, 0));
-        CK(cudaMemcpyAsync(S.h_u32.p + n, S.d_u32.p + n, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->s_out));   // out_len + status
-        if (ro.dense) CK(cudaMemcpyAsync(out_base + ro.lo, S.d_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->s_out));
-        else for (int i = 0; i < n; i++)
-            CK(cudaMemcpyAsync(out_base + out_off[a + i], S.d_out.p + h_out_off[i], caps[a + i], cudaMemcpyDeviceToHost, ctx->s_out));
-        CK(cudaEventRecord(S.d2h_done, ctx->s_out));
-        (void)sync_mode;
-        return 0;
+        S.c_a = a; S.c_n = n; S.c_dense = ro.dense; S.c_lo = ro.dense ? ro.lo : 0; S.c_bytes = out_bytes;
+        return defer_out ? 0 : launch_out(S);
     };
     auto collect_chunk = [&](int k, Stage& S) -> int {               // after S.d2h_done
         const int a = cuts[k], n = cuts[k + 1] - a;
@@ -413,19 +427,37 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
         return 0;
     };
 
-    // ---- software pipeline: chunk k uses stage k % NSTAGE; collect k - NSTAGE before reusing it
-    for (int k = 0; k < nchunk; k++) {
-        Stage& S = ctx->stage[k % NSTAGE];
-        if (k >= NSTAGE) {
-            CK(cudaEventSynchronize(S.d2h_done));
-            if (collect_chunk(k - NSTAGE, S)) return -1;
+    if (ctx->full_duplex || nchunk == 1) {
+        // ---- software pipeline: chunk k uses stage k % NSTAGE; collect k - NSTAGE before reusing it
+        for (int k = 0; k < nchunk; k++) {
+            Stage& S = ctx->stage[k % NSTAGE];
+            if (k >= NSTAGE) {
+                CK(cudaEventSynchronize(S.d2h_done));
+                if (collect_chunk(k - NSTAGE, S)) return -1;
+            }
+            if (launch_chunk(k, S, false)) return -1;
         }
-        if (launch_chunk(k, S, false)) return -1;
-    }
-    for (int k = std::max(0, nchunk - NSTAGE); k < nchunk; k++) {
-        Stage& S = ctx->stage[k % NSTAGE];
-        CK(cudaEventSynchronize(S.d2h_done));
-        if (collect_chunk(k, S)) return -1;
+        for (int k = std::max(0, nchunk - NSTAGE); k < nchunk; k++) {
+            Stage& S = ctx->stage[k % NSTAGE];
+            CK(cudaEventSynchronize(S.d2h_done));
+            if (collect_chunk(k, S)) return -1;
+        }
+    } else {
+        // ---- half duplex: every chunk has its own stage; all host->device copies (and the kernels behind
+        // them) are enqueued first, the device->host copies start once the last input has landed.  Some
+        // hosts lose most of their device->host rate while any host->device traffic is in flight.
+        if ((int)ctx->stage.size() < nchunk) ctx->stage.resize(nchunk);
+        for (int k = 0; k < nchunk; k++) {
+            if (ctx->stage[k].init()) { snprintf(ctx->err, sizeof(ctx->err), "cannot create a staging slot"); return -1; }
+            if (launch_chunk(k, ctx->stage[k], true)) return -1;
+        }
+        CK(cudaEventRecord(ctx->all_h2d, ctx->s_in));
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->all_h2d, 0));
+        for (int k = 0; k < nchunk; k++) if (launch_out(ctx->stage[k])) return -1;
+        for (int k = 0; k < nchunk; k++) {
+            CK(cudaEventSynchronize(ctx->stage[k].d2h_done));
+            if (collect_chunk(k, ctx->stage[k])) return -1;
+        }
     }
     // ---- rare: chunks whose scratch overflowed are redone one at a time with the grown arena
     for (int attempt = 0; !redo.empty() && attempt < 8; attempt++) {
@@ -433,7 +465,7 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
         again.swap(redo);
         for (int k : again) {
             Stage& S = ctx->stage[0];
-            if (launch_chunk(k, S, true)) return -1;
+            if (launch_chunk(k, S, false)) return -1;
             CK(cudaEventSynchronize(S.d2h_done));
             if (collect_chunk(k, S)) return -1;
         }
