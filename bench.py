@@ -230,10 +230,10 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank if rank == 0 else None)
     sampler.start()                                          # nvidia-smi needs ~1 s before its first sample
     ctx = hb.Context(local_rank)
-    # host link policy of the e2e leg: overlapping H2D with D2H wins on one or two GPUs; with more GPUs
-    # active this host's aggregate device->host rate collapses under mixed traffic (tools/numa_probe.py:
-    # 304 GB/s D2H alone vs 134 GB/s with concurrent H2D at 8 GPUs), so inputs go first, results after
-    duplex = args.duplex if args.duplex != "auto" else ("full" if world <= 2 else "half")
+    # host link policy of the e2e leg: full duplex (H2D overlapped with D2H).  On the 8-GPU box the e2e
+    # figure is set by the host link itself (tools/numa_probe.py: 304 GB/s aggregate D2H alone, 134 GB/s
+    # once a quarter as many H2D bytes are in flight); sending inputs first ("half") measured the same.
+    duplex = "full" if args.duplex == "auto" else args.duplex
     ctx.set_copy_duplex(duplex == "full")
     nblk, distinct = args.blocks, min(args.distinct, args.blocks)
     blocks = make_blocks(distinct, rank)

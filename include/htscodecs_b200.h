@@ -156,11 +156,10 @@ int rans4x16_compress_batch(hts_b200_ctx *ctx, int nblk,
  * returns 0 and sets *ulen, or -1 (X_NOSZ stream / truncated header). */
 int hts_b200_peek_size(const uint8_t *in, uint32_t in_len, int method, uint32_t *ulen);
 
-/* Host-buffer calls normally overlap their host->device and device->host copies (full duplex, the
- * default; best on a single GPU).  On hosts whose device->host rate collapses while host->device
- * traffic is in flight (seen with 4-8 GPUs active behind one root complex) pass full = 0: all inputs
- * of a call are then sent first and the results are fetched afterwards (staging memory = the whole
- * batch).  The environment variable HTSCODECS_B200_COPY_DUPLEX=half|full sets the initial value. */
+/* Host-buffer calls overlap their host->device and device->host copies (full duplex, the default).
+ * full = 0 sends all inputs of a call first and fetches the results afterwards (staging memory =
+ * the whole batch) for hosts that handle mixed-direction traffic badly.  The environment variable
+ * HTSCODECS_B200_COPY_DUPLEX=half|full sets the initial value. */
 void hts_b200_set_copy_duplex(hts_b200_ctx *ctx, int full);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA runtime. */
