@@ -24,6 +24,8 @@ enum : int32_t {
 enum JobKind : uint32_t {
     JK_O0_4 = 0, JK_O0_32, JK_O1_4, JK_O1_32, JK_R8_O0, JK_R8_O1, JK_COPY,
     JK_O1_32S,             // X_32 order-1 streams with a small alphabet: the high-occupancy kernel variant
+    JK_O0_4C, JK_R8_O0C,   // 4-way / 4x8 order-0 streams on compact tables: 256 resident streams per SM, used
+                           // for batches too large for one wave of the 4 KB-LUT kernels
     JK_NKINDS
 };
 
@@ -74,7 +76,8 @@ struct DecWork {
     uint32_t overflow;                 // a list capacity was exceeded
     unsigned long long arena_used;     // bytes requested from the arena (may exceed capacity)
     // capacities and pointers (host-written)
-    uint32_t job_cap, chain_cap, stripe_cap, pad0;
+    uint32_t job_cap, chain_cap, stripe_cap;
+    uint32_t big_batch;                // host hint: more 4-way streams than the LUT kernels hold in one wave
     unsigned long long arena_cap;
     DecJob* jobs[JK_NKINDS];
     Chain* chains;

@@ -97,13 +97,40 @@ struct GRd {
     }
 };
 
+// One 4x8 "sym [run] freq ... 0" table (rANS_static.c:271-303; zero_is_4096 for the order-1
+// inner tables, :775-776).  Returns false when malformed; *sum = frequency total.
+template <typename RD, typename ST>
+__device__ bool parse_table_4x8(RD& r, ST store, uint32_t* sum, bool zero_is_4096) {
+    uint32_t run = 0, x = 0, j = r.get();
+    do {
+        uint32_t f = r.get();
+        if (f >= 128) f = ((f & 127) << 8) | r.get();
+        if (!f && zero_is_4096) f = 4096;
+        if (x + f > 4096) return false;
+        store(j, f);
+        x += f;
+        if (!run && j + 1 == r.peek()) { r.get(); j++; run = r.get(); }
+        else if (run) { run--; if (++j > 255) return false; }
+        else j = r.get();
+        if (!r.more()) return false;
+    } while (j);
+    *sum = x;
+    return true;
+}
+template <typename RD>
+__device__ bool parse_table_4x8(RD& r, uint32_t F, uint32_t* sum, bool zero_is_4096) {
+    return parse_table_4x8(r, [&](uint32_t j, uint32_t f) { sts_u32(F + 4 * j, f); }, sum, zero_is_4096);
+}
+
 // decode_alphabet (rANS_static4x16pr.c:208-255) as a counter: number of symbols listed (an upper
 // bound on distinct symbols; exact for streams whose list is strictly increasing, as written by
 // the encoder).  Returns false when the bytes run out.
-__device__ bool count_alphabet(GRd& r, uint32_t* ns) {
+template <typename E>
+__device__ bool list_alphabet(GRd& r, uint32_t* ns, E emit) {
     if (!r.more()) return false;
     uint32_t run = 0, j = r.get(), n = 0;
     do {
+        emit(j);
         n++;
         if (!r.more()) return false;
         if (!run && j + 1 == r.peek()) {
@@ -121,6 +148,9 @@ __device__ bool count_alphabet(GRd& r, uint32_t* ns) {
     *ns = n;
     return true;
 }
+__device__ bool count_alphabet(GRd& r, uint32_t* ns) { return list_alphabet(r, ns, [](uint32_t) {}); }
+constexpr uint32_t O0C_MAX_NS = 64;     // alphabet limit of the compact order-0 kernels
+constexpr uint32_t O1_SENTINEL = 0xfff00fffu;   // compact-table row terminator: last slot 0xfff, rank 0, F 4096
 
 // One non-striped container, rANS_static4x16pr.c:1435-1629, turned into a plan.  `cap` is the
 // caller's capacity (the exact size for X_NOSZ); expect != 0xffffffff marks a stripe sub-stream
@@ -228,7 +258,13 @@ __device__ int32_t plan_chain(DecWork* W, const uint8_t* in, uint32_t in_len, ui
             }
             if (!push_job(W, kind, j)) return ST_ARENA;
         } else {
-            if (!push_job(W, x32 ? JK_O0_32 : JK_O0_4, j)) return ST_ARENA;
+            uint32_t kind = x32 ? JK_O0_32 : JK_O0_4;
+            if (!x32 && W->big_batch) {                              // large batch: small alphabets decode from compact
+                GRd ar{in, end};                                     // tables at six times the occupancy
+                uint32_t ns = 0;
+                if (count_alphabet(ar, &ns) && ns <= O0C_MAX_NS) kind = JK_O0_4C;
+            }
+            if (!push_job(W, kind, j)) return ST_ARENA;
         }
     } else {
         t1_size = 0;
@@ -276,7 +312,13 @@ __global__ void plan_kernel(PlanArgs A) {
             if (clen != in_len - 9 || n >= 0x7fffffffu) st = ST_FORMAT;
             else if (n > cap) st = ST_SIZE;
             else {
-                if (!push_job(W, in[0] ? JK_R8_O1 : JK_R8_O0, make_job(in, in_len, out, n, blk))) st = ST_ARENA;
+                uint32_t kind = in[0] ? JK_R8_O1 : JK_R8_O0;
+                if (!in[0] && W->big_batch) {
+                    GRd ar{in + 9, in + in_len};
+                    uint32_t ns = 0, sum = 0;
+                    if (parse_table_4x8(ar, [&](uint32_t, uint32_t) { ns++; }, &sum, false) && ns <= O0C_MAX_NS) kind = JK_R8_O0C;
+                }
+                if (!push_job(W, kind, make_job(in, in_len, out, n, blk))) st = ST_ARENA;
                 A.out_len[blk] = n;
             }
         }
@@ -542,31 +584,6 @@ __device__ uint32_t parse_o0_table_4x16(uint32_t src, uint32_t lim, uint32_t F, 
     return r.a - src;
 }
 
-// One 4x8 "sym [run] freq ... 0" table (rANS_static.c:271-303; zero_is_4096 for the order-1
-// inner tables, :775-776).  Returns false when malformed; *sum = frequency total.
-template <typename RD, typename ST>
-__device__ bool parse_table_4x8(RD& r, ST store, uint32_t* sum, bool zero_is_4096) {
-    uint32_t run = 0, x = 0, j = r.get();
-    do {
-        uint32_t f = r.get();
-        if (f >= 128) f = ((f & 127) << 8) | r.get();
-        if (!f && zero_is_4096) f = 4096;
-        if (x + f > 4096) return false;
-        store(j, f);
-        x += f;
-        if (!run && j + 1 == r.peek()) { r.get(); j++; run = r.get(); }
-        else if (run) { run--; if (++j > 255) return false; }
-        else j = r.get();
-        if (!r.more()) return false;
-    } while (j);
-    *sum = x;
-    return true;
-}
-template <typename RD>
-__device__ bool parse_table_4x8(RD& r, uint32_t F, uint32_t* sum, bool zero_is_4096) {
-    return parse_table_4x8(r, [&](uint32_t j, uint32_t f) { sts_u32(F + 4 * j, f); }, sum, zero_is_4096);
-}
-
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
 }
@@ -664,17 +681,28 @@ __device__ bool o0_setup(const Grp<NWAY>& G, const DecJob& job, uint32_t lut, ui
                                  BYTE ? (1u << 23) : (1u << 15));
 }
 
+// Four steps of a 4-lane group produce 16 contiguous output bytes: lane z holds the bytes of
+// positions 4k + z (k = 0..3, byte k of `w`).  A 4 x 4 byte transpose inside the group (two
+// shuffle/permute rounds) gives lane z positions 4z .. 4z + 3, so the group writes one 32-bit word
+// per lane instead of four scattered bytes per lane: a quarter of the (partial) sector writes.
+__device__ __forceinline__ uint32_t transpose4x4(uint32_t w, uint32_t glane) {
+    uint32_t t = __shfl_xor_sync(0xffffffffu, w, 1);
+    w = __byte_perm(w, t, (glane & 1) ? 0x3715 : 0x6240);
+    t = __shfl_xor_sync(0xffffffffu, w, 2);
+    return __byte_perm(w, t, (glane & 2) ? 0x3276 : 0x5410);
+}
+
 // One decode step (rANS_static4x16pr.c:576-597 / rANS_static.c:318-344) for every lane.
 template <int NWAY, bool BYTE, bool ALIGNED, bool ALLACT>
 __device__ __forceinline__ uint32_t o0_step(uint32_t R, bool act, WordRing<NWAY>& ring, uint32_t lut, uint32_t fc,
-                                            uint8_t* op, uint32_t lt, uint32_t gshift) {
+                                            uint8_t* op, uint32_t lt, uint32_t gshift, uint32_t* sym_out = nullptr) {
     constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
     const uint32_t m = R & 0xfffu;
     const uint32_t s = lds_u8(lut + m);
     const uint2 e = lds_v2(fc + s * 8);
     const uint32_t X = e.x * (R >> 12) + m;
     const bool p = (ALLACT || act) && X < e.y;               // x' < L
-    if (ALLACT || act) { R = X + L - e.y; *op = (uint8_t)s; }
+    if (ALLACT || act) { R = X + L - e.y; if (sym_out) *sym_out = s; else *op = (uint8_t)s; }
     return renorm_step<NWAY, BYTE, ALIGNED>(R, p, ring, lt, gshift);
 }
 
@@ -741,6 +769,19 @@ __device__ __forceinline__ void o0_loop(uint32_t R, WordRing<NWAY>& ring, uint32
             op += 128;
             ring.advance(G.glane, true);
         }
+    } else if (NWAY == 4 && __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(out) & 3) == 0)) {
+        for (; i + 4 <= minit; i += 4) {                     // word stores after a 4 x 4 transpose
+            uint32_t w = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                uint32_t sy;
+                R = o0_step<NWAY, BYTE, ALIGNED, true>(R, true, ring, lut, fc, nullptr, lt, G.gshift, &sy);
+                w |= sy << (8 * u);
+            }
+            *reinterpret_cast<uint32_t*>(op - G.glane + 4 * G.glane) = transpose4x4(w, G.glane);
+            op += 4 * NWAY;
+            ring.advance(G.glane, true);
+        }
     } else {
         for (; i + 4 <= minit; i += 4) {
 #pragma unroll
@@ -773,14 +814,12 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
 
-    // The first round is assigned statically (CTA i takes jobs i*G ..), which spreads a batch that
-    // fits in one wave evenly over the SMs; later rounds are claimed from an atomic cursor.
-    for (uint32_t round = 0;; round++) {
-        uint32_t j0 = blockIdx.x * C::G;
-        if (round) {
-            if (lane_id() == 0) j0 = gridDim.x * C::G + atomicAdd(&W->next[kind], (uint32_t)C::G);
-            j0 = __shfl_sync(0xffffffffu, j0, 0);
-        }
+    // Jobs are claimed from an atomic cursor.  The host shapes the launch so that every SM holds the
+    // same number of CTAs (shaped_launch below): a batch that fits in one wave is then spread evenly.
+    for (;;) {
+        uint32_t j0 = 0;
+        if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], (uint32_t)C::G);
+        j0 = __shfl_sync(0xffffffffu, j0, 0);
         if (j0 >= njobs) break;
         const uint32_t ji = j0 + G.g;
         const bool active = ji < njobs;
@@ -800,6 +839,164 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
         const bool aligned = !BYTE && __all_sync(0xffffffffu, (ring.head & 1u) == 0);
         if (aligned) o0_loop<NWAY, BYTE, true >(R, ring, lut, fc, job.out, iters, rem, minit, maxit, G);
         else         o0_loop<NWAY, BYTE, false>(R, ring, lut, fc, job.out, iters, rem, minit, maxit, G);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// order-0 on compact tables (4-way and 4x8 streams of large batches)
+// ------------------------------------------------------------------------------------------
+// The 4 KB symbol LUT limits the LUT kernels to 40 resident 4-way streams per SM, and a 4-way
+// stream is four lanes of strictly serial work, so a batch beyond one wave (5920 streams) gains
+// nothing.  Here a stream's table is the compact form of section "order-1" with a single context --
+// a 64-bucket coarse index and one packed entry (C+F-1)<<20 | sym<<12 | (F-1) per symbol -- 592
+// bytes per stream with its word ring: 256 resident streams per SM.  Alphabets of up to 64 symbols.
+struct O0CSmem {
+    static constexpr int COARSE = 0, ENT = 64, RINGO = 64 + 4 * (O0C_MAX_NS + 4), STRIDE = RINGO + 256;
+    static constexpr int TOTAL = 8 * STRIDE;
+};
+
+template <bool BYTE>
+__device__ bool o0c_setup(const Grp<4>& G, const DecJob& job, uint32_t gsm, uint32_t* R, uint32_t* first_word) {
+    constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
+    const uint32_t coarse = gsm + O0CSmem::COARSE, ent = gsm + O0CSmem::ENT, syms = gsm + O0CSmem::RINGO;   // ring: free for now
+    const uint8_t* in_end = job.in + job.in_len;
+    const uint32_t hdr0 = BYTE ? 9u : 0u;
+    uint32_t tab = 0;
+    if (G.glane == 0 && job.in_len >= hdr0 + 16) {
+        GRd rd{job.in + hdr0, in_end};
+        uint32_t ns = 0, sum = 0;
+        bool ok;
+        if (BYTE) {
+            ok = parse_table_4x8(rd, [&](uint32_t j, uint32_t f) {
+                if (ns < O0C_MAX_NS) { sts_u8(syms + ns, j); sts_u32(ent + 4 * ns, f); }
+                ns++; }, &sum, false);
+        } else {
+            uint32_t cnt = 0;
+            ok = list_alphabet(rd, &ns, [&](uint32_t j) { if (cnt < O0C_MAX_NS) sts_u8(syms + cnt, j); cnt++; });
+            if (ok && ns <= O0C_MAX_NS)
+                for (uint32_t i = 0; i < ns; i++) { const uint32_t f = rd.varint(); sts_u32(ent + 4 * i, f); sum += f; }
+        }
+        ok = ok && ns >= 1 && ns <= O0C_MAX_NS;
+        uint32_t sh = 0;
+        if (ok && !BYTE && sum != 0 && sum < 4096) while ((sum << sh) < 4096) sh++;      // normalise_freq_shift
+        uint32_t c = 0, idx = 0;
+        for (uint32_t k = 0; k < 16; k++) sts_u32(coarse + 4 * k, 0u);
+        for (uint32_t i = 0; ok && i < ns; i++) {
+            const uint32_t f = lds_u32(ent + 4 * i) << sh;
+            if (!f) continue;
+            if (f > 4096 - c) { ok = false; break; }
+            const uint32_t last = c + f - 1;
+            sts_u32(ent + 4 * idx, (last << 20) | (lds_u8(syms + i) << 12) | (f - 1));
+            for (uint32_t q = (c + 63) >> 6; q <= (last >> 6); q++) sts_u8(coarse + q, idx);
+            idx++;
+            c += f;
+        }
+        if (ok && c != 4096 && !(BYTE && c == 4095)) ok = false;                         // :551 / rANS_static.c:305
+        for (uint32_t k = 0; k < 3; k++) sts_u32(ent + 4 * (idx + k), O1_SENTINEL);
+        if (ok) tab = (uint32_t)(rd.p - job.in);
+    }
+    tab = G.bcast(tab);
+    if (tab == 0 || tab + 16 > job.in_len) return false;
+    const uint32_t r0 = ld_u32_le(job.in + tab + 4 * G.glane);
+    if (!G.all(r0 >= L)) return false;
+    *R = r0;
+    *first_word = tab + 16;
+    G.sync();
+    return true;
+}
+
+template <bool BYTE, bool ALIGNED, bool ALLACT>
+__device__ __forceinline__ uint32_t o0c_step(uint32_t R, bool act, WordRing<4>& ring, uint32_t coarse, uint32_t ent,
+                                             uint8_t* op, uint32_t lt, uint32_t gshift, uint32_t* sym_out = nullptr) {
+    constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
+    const uint32_t m = R & 0xfffu, mk = m << 20, q = R >> 12, qm = q + m;
+    uint32_t ea = ent + 4 * lds_u8(coarse + (m >> 6));
+    const uint32_t e0 = lds_u32(ea), e1 = lds_u32(ea + 4), e2 = lds_u32(ea + 8);
+    uint32_t e = (mk > e1) ? e2 : ((mk > e0) ? e1 : e0);
+    if (mk > e) {                                            // >= 4 symbols share the bucket (sentinel-bounded scan)
+        ea += 12;
+        do { e = lds_u32(ea); ea += 4; } while (mk > e);
+    }
+    const uint32_t Rn = (e & 0xfffu) * (q + 1u) + (qm - (e >> 20));
+    const bool p = (ALLACT || act) && Rn < L;
+    if (ALLACT || act) { R = Rn; if (sym_out) *sym_out = (e >> 12) & 0xffu; else *op = (uint8_t)(e >> 12); }
+    return renorm_step<4, BYTE, ALIGNED>(R, p, ring, lt, gshift);
+}
+
+template <bool BYTE, bool ALIGNED>
+__device__ __forceinline__ void o0c_loop(uint32_t R, WordRing<4>& ring, uint32_t coarse, uint32_t ent, uint8_t* out,
+                                         uint32_t iters, uint32_t rem, uint32_t minit, uint32_t maxit, const Grp<4>& G) {
+    const uint32_t lt = (1u << G.glane) - 1u;
+    uint8_t* op = out + G.glane;
+    uint32_t i = 0;
+    if (__all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(out) & 3) == 0)) {
+        for (; i + 4 <= minit; i += 4) {                     // word stores after a 4 x 4 transpose
+            uint32_t w = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                uint32_t sy;
+                R = o0c_step<BYTE, ALIGNED, true>(R, true, ring, coarse, ent, nullptr, lt, G.gshift, &sy);
+                w |= sy << (8 * u);
+            }
+            *reinterpret_cast<uint32_t*>(op + 3 * G.glane) = transpose4x4(w, G.glane);
+            op += 16;
+            ring.advance(G.glane, true);
+        }
+    }
+    for (; i + 4 <= minit; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            R = o0c_step<BYTE, ALIGNED, true>(R, true, ring, coarse, ent, op + u * 4, lt, G.gshift);
+        op += 16;
+        ring.advance(G.glane, true);
+    }
+    for (; i < maxit; i++) {
+        const bool act = i < iters;
+        R = o0c_step<BYTE, ALIGNED, false>(R, act, ring, coarse, ent, op, lt, G.gshift);
+        if (act) op += 4;
+        ring.advance(G.glane, act);
+    }
+    if (G.glane < rem) {                                     // rANS_static.c:346-355: peek only
+        const uint32_t m = R & 0xfffu, mk = m << 20;
+        uint32_t ea = ent + 4 * lds_u8(coarse + (m >> 6)), e;
+        do { e = lds_u32(ea); ea += 4; } while (mk > e);
+        *op = (uint8_t)(e >> 12);
+    }
+}
+
+template <bool BYTE>
+__global__ void __launch_bounds__(32, 32) dec_o0c_kernel(DecWork* W, int32_t* status, uint32_t kind) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const Grp<4> G;
+    uint32_t base = smem_addr(smem_raw) + G.g * O0CSmem::STRIDE;
+    asm volatile("" : "+r"(base));
+    const uint32_t njobs = W->njobs[kind];
+    const DecJob* jobs = W->jobs[kind];
+    for (;;) {
+        uint32_t j0 = 0;
+        if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], 8u);
+        j0 = __shfl_sync(0xffffffffu, j0, 0);
+        if (j0 >= njobs) break;
+        const uint32_t ji = j0 + G.g;
+        const bool active = ji < njobs;
+        DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
+        uint32_t R = 0, first_word = 0;
+        bool ok = false;
+        if (active) {
+            job = jobs[ji];
+            ok = o0c_setup<BYTE>(G, job, base, &R, &first_word);
+            if (!ok && G.glane == 0) set_status(status, job.blk, ST_FORMAT);
+        }
+        WordRing<4> ring;
+        ring.init(job.in + first_word, job.in + job.in_len, base + O0CSmem::RINGO, G, ok);
+        __syncwarp();
+        const uint32_t iters = ok ? job.out_len / 4 : 0, rem = ok ? job.out_len % 4 : 0;
+        const uint32_t maxit = __reduce_max_sync(0xffffffffu, iters), minit = __reduce_min_sync(0xffffffffu, iters);
+        const bool aligned = !BYTE && __all_sync(0xffffffffu, (ring.head & 1u) == 0);
+        const uint32_t coarse = base + O0CSmem::COARSE, ent = base + O0CSmem::ENT;
+        if (aligned) o0c_loop<BYTE, true >(R, ring, coarse, ent, job.out, iters, rem, minit, maxit, G);
+        else         o0c_loop<BYTE, false>(R, ring, coarse, ent, job.out, iters, rem, minit, maxit, G);
         __syncwarp();
     }
 }
@@ -836,7 +1033,6 @@ template <int NWAY, bool SMALL = false> struct O1Smem {
     static constexpr int STRIDE = TABO + TAB;                        // multiple of 16
     static constexpr int TOTAL = STRIDE * GroupCfg<NWAY>::G;
 };
-constexpr uint32_t O1_SENTINEL = 0xfff00fffu;                        // last slot 0xfff, rank 0, F 4096
 
 struct O1Tables {
     uint32_t compact;       // 1: compact form in shared memory
@@ -1212,14 +1408,12 @@ __global__ void __launch_bounds__(32, SMALL ? 28 : 1) dec_o1_kernel(DecWork* W, 
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
 
-    // The first round is assigned statically (CTA i takes jobs i*G ..), which spreads a batch that
-    // fits in one wave evenly over the SMs; later rounds are claimed from an atomic cursor.
-    for (uint32_t round = 0;; round++) {
-        uint32_t j0 = blockIdx.x * C::G;
-        if (round) {
-            if (lane_id() == 0) j0 = gridDim.x * C::G + atomicAdd(&W->next[kind], (uint32_t)C::G);
-            j0 = __shfl_sync(0xffffffffu, j0, 0);
-        }
+    // Jobs are claimed from an atomic cursor.  The host shapes the launch so that every SM holds the
+    // same number of CTAs (shaped_launch below): a batch that fits in one wave is then spread evenly.
+    for (;;) {
+        uint32_t j0 = 0;
+        if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], (uint32_t)C::G);
+        j0 = __shfl_sync(0xffffffffu, j0, 0);
         if (j0 >= njobs) break;
         const uint32_t ji = j0 + G.g;
         const bool active = ji < njobs;
@@ -1524,30 +1718,48 @@ __global__ void __launch_bounds__(256) unstripe_kernel(DecWork* W, int32_t* stat
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int g_grid[JK_NKINDS];
+static int g_cap[JK_NKINDS];        // resident CTAs per SM of each persistent kernel at its own shared-memory size
+static int g_smem[JK_NKINDS];
 static int g_sms = 0;
+constexpr int SM_SMEM = 233472, CTA_RESERVE = 1024, MAX_DYN = 232448;
 
 template <typename K>
-static int persistent_grid(K kernel, int smem, int threads, int sms) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+static void persistent_setup(uint32_t kind, K kernel, int smem, int threads) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
-    if (per_sm < 1) per_sm = 1;
-    return per_sm * sms;
+    g_cap[kind] = per_sm < 1 ? 1 : per_sm;
+    g_smem[kind] = smem;
 }
 
 int decode_init(int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
     g_sms = prop.multiProcessorCount;
-    g_grid[JK_O0_32] = persistent_grid(dec_o0_kernel<32, false>, O0Smem<32>::TOTAL, 32, g_sms);
-    g_grid[JK_O0_4]  = persistent_grid(dec_o0_kernel<4, false>,  O0Smem<4>::TOTAL, 32, g_sms);
-    g_grid[JK_R8_O0] = persistent_grid(dec_o0_kernel<4, true>,   O0Smem<4>::TOTAL, 32, g_sms);
-    g_grid[JK_O1_32] = persistent_grid(dec_o1_kernel<32, false, false>, O1Smem<32>::TOTAL, 32, g_sms);
-    g_grid[JK_O1_32S] = persistent_grid(dec_o1_kernel<32, false, true>, O1Smem<32, true>::TOTAL, 32, g_sms);
-    g_grid[JK_O1_4]  = persistent_grid(dec_o1_kernel<4, false, false>,  O1Smem<4>::TOTAL, 32, g_sms);
-    g_grid[JK_R8_O1] = persistent_grid(dec_o1_kernel<4, true, false>,   O1Smem<4>::TOTAL, 32, g_sms);
+    persistent_setup(JK_O0_32, dec_o0_kernel<32, false>, O0Smem<32>::TOTAL, 32);
+    persistent_setup(JK_O0_4,  dec_o0_kernel<4, false>,  O0Smem<4>::TOTAL, 32);
+    persistent_setup(JK_R8_O0, dec_o0_kernel<4, true>,   O0Smem<4>::TOTAL, 32);
+    persistent_setup(JK_O0_4C,  dec_o0c_kernel<false>, O0CSmem::TOTAL, 32);
+    persistent_setup(JK_R8_O0C, dec_o0c_kernel<true>,  O0CSmem::TOTAL, 32);
+    persistent_setup(JK_O1_32,  dec_o1_kernel<32, false, false>, O1Smem<32>::TOTAL, 32);
+    persistent_setup(JK_O1_32S, dec_o1_kernel<32, false, true>,  O1Smem<32, true>::TOTAL, 32);
+    persistent_setup(JK_O1_4,   dec_o1_kernel<4, false, false>,  O1Smem<4>::TOTAL, 32);
+    persistent_setup(JK_R8_O1,  dec_o1_kernel<4, true, false>,   O1Smem<4>::TOTAL, 32);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// A persistent kernel gives one warp (CTA) to a group of G streams, and the CTA scheduler fills one
+// SM to capacity before it moves to the next: a batch smaller than one full wave would crowd a few
+// SMs and leave the rest idle.  So the launch is shaped: with `groups` work items expected, the
+// dynamic shared-memory request is padded until exactly c = ceil(groups / SMs) CTAs fit per SM and
+// the grid is SMs x c -- every SM then holds the same number of streams.
+struct Shape { int grid, smem; };
+static Shape shaped_launch(uint32_t kind, uint32_t groups) {
+    int c = (int)((groups + g_sms - 1) / g_sms);
+    c = std::max(1, std::min(c, g_cap[kind]));
+    int smem = g_smem[kind];
+    if (c < g_cap[kind]) smem = std::max(smem, std::min(MAX_DYN, (SM_SMEM / c - CTA_RESERVE) & ~127));
+    return Shape{g_sms * c, smem};
 }
 
 // The per-batch header travels as a kernel argument (copied at launch), so the host may reuse
@@ -1564,13 +1776,22 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     work_init_kernel<<<1, 1, 0, st>>>(b.work, *b.hdr); launches++;
     plan_kernel<<<(b.nblk + 127) / 128, 128, 0, st>>>(A); launches++;
     auto want = [&](uint32_t k) { return (b.kinds >> k) & 1u; };
-    if (want(JK_O0_32)) { dec_o0_kernel<32, false><<<g_grid[JK_O0_32], 32, O0Smem<32>::TOTAL, st>>>(b.work, b.status, JK_O0_32); launches++; }
-    if (want(JK_O0_4))  { dec_o0_kernel<4, false><<<g_grid[JK_O0_4], 32, O0Smem<4>::TOTAL, st>>>(b.work, b.status, JK_O0_4); launches++; }
-    if (want(JK_O1_32S)) { dec_o1_kernel<32, false, true><<<g_grid[JK_O1_32S], 32, O1Smem<32, true>::TOTAL, st>>>(b.work, b.status, JK_O1_32S); launches++; }
-    if (want(JK_O1_32)) { dec_o1_kernel<32, false, false><<<g_grid[JK_O1_32], 32, O1Smem<32>::TOTAL, st>>>(b.work, b.status, JK_O1_32); launches++; }
-    if (want(JK_O1_4))  { dec_o1_kernel<4, false, false><<<g_grid[JK_O1_4], 32, O1Smem<4>::TOTAL, st>>>(b.work, b.status, JK_O1_4); launches++; }
-    if (want(JK_R8_O0)) { dec_o0_kernel<4, true><<<g_grid[JK_R8_O0], 32, O0Smem<4>::TOTAL, st>>>(b.work, b.status, JK_R8_O0); launches++; }
-    if (want(JK_R8_O1)) { dec_o1_kernel<4, true, false><<<g_grid[JK_R8_O1], 32, O1Smem<4>::TOTAL, st>>>(b.work, b.status, JK_R8_O1); launches++; }
+    // expected work items per kind: the host only knows the block count (the planner decides kinds on
+    // the device), which is exact for the common single-kind batch and an upper bound otherwise
+    auto shape = [&](uint32_t k, uint32_t per_cta) { return shaped_launch(k, (b.nblk + per_cta - 1) / per_cta); };
+    Shape sh;
+#define LAUNCH_DEC(K, KERNEL, PER)                                                             \
+    if (want(K)) { sh = shape(K, PER); KERNEL<<<sh.grid, 32, sh.smem, st>>>(b.work, b.status, K); launches++; }
+    LAUNCH_DEC(JK_O0_32, (dec_o0_kernel<32, false>), 1)
+    LAUNCH_DEC(JK_O0_4, (dec_o0_kernel<4, false>), 8)
+    LAUNCH_DEC(JK_O0_4C, (dec_o0c_kernel<false>), 8)
+    LAUNCH_DEC(JK_R8_O0C, (dec_o0c_kernel<true>), 8)
+    LAUNCH_DEC(JK_O1_32S, (dec_o1_kernel<32, false, true>), 1)
+    LAUNCH_DEC(JK_O1_32, (dec_o1_kernel<32, false, false>), 1)
+    LAUNCH_DEC(JK_O1_4, (dec_o1_kernel<4, false, false>), 8)
+    LAUNCH_DEC(JK_R8_O0, (dec_o0_kernel<4, true>), 8)
+    LAUNCH_DEC(JK_R8_O1, (dec_o1_kernel<4, true, false>), 8)
+#undef LAUNCH_DEC
     if (want(JK_COPY))  { copy_kernel<<<g_sms * 4, 256, 0, st>>>(b.work); launches++; }
     if (b.post & 1u) { rle_kernel<<<g_sms * 4, RLE_T, 0, st>>>(b.work, b.status, b.out_len); launches++; }
     if (b.post & 2u) { unpack_kernel<<<g_sms * 4, 256, 0, st>>>(b.work, b.status, b.out_len); launches++; }

@@ -18,6 +18,7 @@ struct DecodeBatch {
     int nblk;
     uint32_t kinds;             // bit k set: job kind k may occur (host hint; ~0u = unknown)
     uint32_t post;              // bit0 RLE, bit1 PACK, bit2 STRIPE may occur
+    bool big_batch = false;     // route small-alphabet 4-way order-0 streams to the compact-table kernels
 };
 
 int decode_init(int device);

@@ -1161,14 +1161,12 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
     uint32_t gt_mask;
     asm("mov.u32 %0, %%lanemask_gt;" : "=r"(gt_mask));
 
-    // streams are claimed EG::G at a time (first round statically by CTA index, which spreads a batch
-    // that fits in one wave evenly over the SMs); those of another nway/order/size class are skipped
-    for (uint32_t round = 0;; round++) {
-        uint32_t s0 = blockIdx.x * EG::G;
-        if (round) {
-            if (lane_id() == 0) s0 = gridDim.x * EG::G + atomicAdd(cursor, (uint32_t)EG::G);
-            s0 = __shfl_sync(0xffffffffu, s0, 0);
-        }
+    // streams are claimed EG::G at a time from an atomic cursor (the launch is shaped so that every SM
+    // holds the same number of CTAs); those of another nway/order/size class are skipped
+    for (;;) {
+        uint32_t s0 = 0;
+        if (lane_id() == 0) s0 = atomicAdd(cursor, (uint32_t)EG::G);
+        s0 = __shfl_sync(0xffffffffu, s0, 0);
         if (s0 >= nstreams) break;
         const uint32_t si = s0 + G.g;
         bool act_s = si < nstreams;
@@ -1538,7 +1536,7 @@ constexpr int ORDER_LEGACY_4x8 = 0x40000000;                    // HTS_B200_ORDE
 size_t up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 template <typename K> int occ_grid(K kernel, int smem, int sms) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);   // launches may pad (shaping)
     int per = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, 32, smem);
     return std::max(per, 1) * sms;
@@ -1573,12 +1571,10 @@ int encode_init(int device) {
     cudaFuncSetAttribute(enc_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM);
     g_grid_enc[0][0] = occ_grid(enc_rans_kernel<4, 0, 16>, SM_O0_4, g_sms_enc);
     g_grid_enc[1][0] = occ_grid(enc_rans_kernel<32, 0, 16>, SM_O0_32, g_sms_enc);
-    cudaFuncSetAttribute(enc_rans_kernel<32, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7168);
     g_grid_o1_4_s = occ_grid(enc_rans_kernel<4, 1, 16>, SM_O1_4_S, g_sms_enc);
     occ_grid(enc_rans_kernel<4, 0, 16, true>, SM_O0_4, g_sms_enc);
     occ_grid(enc_rans_kernel<4, 1, 16, true>, SM_O1_4_S, g_sms_enc);
     g_grid_o1_32_s = occ_grid(enc_rans_kernel<32, 1, 16>, SM_O1_32_S, g_sms_enc);
-    cudaFuncSetAttribute(enc_rans_kernel<32, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7168);
     g_grid_o1_32_l = occ_grid(enc_rans_kernel<32, 1, 48>, SM_O1_32_L, g_sms_enc);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1779,14 +1775,24 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
         // shared memory at high occupancy) or the large one (ns > 16: shared up to 48 symbols, else global)
         if (any4[0])  { enc_rans_kernel<4, 0, 16><<<g_grid_enc[0][0], 32, SM_O0_4, st>>>(dW, 0, 0, 256); launches++; }
         if (any4[1])  { enc_rans_kernel<4, 1, 16><<<g_grid_o1_4_s, 32, SM_O1_4_S, st>>>(dW, 1, 0, 256); launches++; }
-        // A batch that fits in one wave of 28 warps per SM runs ~12 % faster when the kernel is held to
-        // 28 resident warps (the CTA scheduler does not spread a 32-per-SM grid evenly): pad the request.
-        const int pad32 = (streams.size() <= (size_t)28 * g_sms_enc) ? 7168 : 0;
-        if (any32[0]) { enc_rans_kernel<32, 0, 16><<<g_grid_enc[1][0], 32, std::max(SM_O0_32, pad32), st>>>(dW, 2, 0, 256); launches++; }
-        if (any32[1]) { enc_rans_kernel<32, 1, 16><<<g_grid_o1_32_s, 32, std::max(SM_O1_32_S, pad32), st>>>(dW, 3, 0, 16); launches++;
-                        enc_rans_kernel<32, 1, 48><<<g_grid_o1_32_l, 32, SM_O1_32_L, st>>>(dW, 4, 16, 256); launches++; }
-        if (any8[0])  { enc_rans_kernel<4, 0, 16, true><<<g_grid_enc[0][0], 32, SM_O0_4, st>>>(dW, 5, 0, 256); launches++; }
-        if (any8[1])  { enc_rans_kernel<4, 1, 16, true><<<g_grid_o1_4_s, 32, SM_O1_4_S, st>>>(dW, 6, 0, 256); launches++; }
+        // Shaped launches: a persistent kernel gives a warp to EG::G streams and the CTA scheduler fills
+        // one SM before the next, so the dynamic shared-memory request is padded until exactly
+        // c = ceil(groups / SMs) CTAs fit per SM and the grid is SMs x c (every SM holds the same load).
+        const uint32_t ngroups32 = (uint32_t)streams.size(), ngroups4 = ((uint32_t)streams.size() + 7) / 8;
+        auto shaped = [&](int cap, int smem, uint32_t groups, int* grid) {
+            int c = (int)((groups + g_sms_enc - 1) / g_sms_enc);
+            c = std::max(1, std::min(c, cap));
+            *grid = g_sms_enc * c;
+            return c < cap ? std::max(smem, std::min(232448, (233472 / c - 1024) & ~127)) : smem;
+        };
+        int grid = 0, sm = 0;
+        if (any4[0])  { sm = shaped(g_grid_enc[0][0] / g_sms_enc, SM_O0_4, ngroups4, &grid); enc_rans_kernel<4, 0, 16><<<grid, 32, sm, st>>>(dW, 0, 0, 256); launches++; }
+        if (any4[1])  { sm = shaped(g_grid_o1_4_s / g_sms_enc, SM_O1_4_S, ngroups4, &grid); enc_rans_kernel<4, 1, 16><<<grid, 32, sm, st>>>(dW, 1, 0, 256); launches++; }
+        if (any32[0]) { sm = shaped(g_grid_enc[1][0] / g_sms_enc, SM_O0_32, ngroups32, &grid); enc_rans_kernel<32, 0, 16><<<grid, 32, sm, st>>>(dW, 2, 0, 256); launches++; }
+        if (any32[1]) { sm = shaped(g_grid_o1_32_s / g_sms_enc, SM_O1_32_S, ngroups32, &grid); enc_rans_kernel<32, 1, 16><<<grid, 32, sm, st>>>(dW, 3, 0, 16); launches++;
+                        sm = shaped(g_grid_o1_32_l / g_sms_enc, SM_O1_32_L, ngroups32, &grid); enc_rans_kernel<32, 1, 48><<<grid, 32, sm, st>>>(dW, 4, 16, 256); launches++; }
+        if (any8[0])  { sm = shaped(g_grid_enc[0][0] / g_sms_enc, SM_O0_4, ngroups4, &grid); enc_rans_kernel<4, 0, 16, true><<<grid, 32, sm, st>>>(dW, 5, 0, 256); launches++; }
+        if (any8[1])  { sm = shaped(g_grid_o1_4_s / g_sms_enc, SM_O1_4_S, ngroups4, &grid); enc_rans_kernel<4, 1, 16, true><<<grid, 32, sm, st>>>(dW, 6, 0, 256); launches++; }
         enc_finish_kernel<<<g, 256, 0, st>>>(dW); launches++;
     }
     enc_block_kernel<<<g, 256, 0, st>>>(dW, b.out_len, b.status); launches++;

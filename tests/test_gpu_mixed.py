@@ -102,3 +102,38 @@ def test_dropin_calls_from_many_host_threads(oracle):
 
     with ThreadPoolExecutor(max_workers=6) as ex:
         assert sum(ex.map(work, range(6))) == 0
+
+
+def test_large_batch_routes_to_compact_order0_kernels(ctx, oracle, reflib):
+    """More than 5000 blocks in one device-resident call: small-alphabet 4-way / 4x8 order-0 streams
+    are decoded by the compact-table kernels (a different code path from every other test)."""
+    import torch
+    kinds = [("qual", 0, 0), ("acgt", 0, 0), ("wide", 0, 0), ("tag", 0x40, 0), ("random", 0, 0), ("qual", 0, 1),
+             ("wide", 0, 1), ("qual", 1, 0), ("qual", 4, 0)]
+    uniq, comp, meth = [], [], []
+    for i, (gen, f, m) in enumerate(kinds):
+        for n in (4096 + 37 * i, 3, 700):
+            d = synth.GENERATORS[gen](i, n).tobytes()
+            uniq.append(d); meth.append(m)
+            comp.append(reflib.compress_4x8(d, f) if m else oracle.compress(d, f))
+    nblk = 5400
+    idx = [i % len(uniq) for i in range(nblk)]
+    in_len = np.array([len(comp[i]) for i in idx], np.uint32)
+    in_off = np.zeros(nblk, np.uint64); in_off[1:] = np.cumsum((in_len[:-1].astype(np.uint64) + 15) // 16 * 16)
+    out_cap = np.array([len(uniq[i]) for i in idx], np.uint32)
+    out_off = np.zeros(nblk, np.uint64); out_off[1:] = np.cumsum((out_cap[:-1].astype(np.uint64) + 15) // 16 * 16)
+    ib = np.zeros(int(in_off[-1] + in_len[-1]) + 16, np.uint8)
+    for k, i in enumerate(idx):
+        ib[int(in_off[k]): int(in_off[k]) + len(comp[i])] = np.frombuffer(comp[i], np.uint8)
+    d_in = torch.from_numpy(ib).cuda()
+    d_out = torch.zeros(int(out_off[-1] + out_cap[-1]) + 16, dtype=torch.uint8, device="cuda")
+    d_len = torch.from_numpy(out_cap.view(np.int32).copy()).cuda()
+    d_st = torch.zeros(nblk, dtype=torch.int32, device="cuda")
+    ctx.uncompress_batch_dev(nblk, d_in, torch.from_numpy(in_off.view(np.int64)).cuda(),
+                             torch.from_numpy(in_len.view(np.int32)).cuda(), d_out,
+                             torch.from_numpy(out_off.view(np.int64)).cuda(), d_len, d_st,
+                             torch.from_numpy(np.array([meth[i] for i in idx], np.uint8)).cuda())
+    assert int((d_st != 0).sum()) == 0
+    ob = d_out.cpu().numpy()
+    for k in list(range(0, 60)) + list(range(nblk - 60, nblk)):
+        assert bytes(ob[int(out_off[k]): int(out_off[k]) + int(out_cap[k])]) == uniq[idx[k]], k
