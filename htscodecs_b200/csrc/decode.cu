@@ -78,6 +78,7 @@ __device__ int unpack_meta(const uint8_t* d, uint32_t len, uint8_t* map, uint32_
 // budget of the small-alphabet X_32 kernel variant
 __host__ __device__ constexpr uint32_t o1_compact_bytes(uint32_t ns) { return ns * 64 + ns * 4 * (ns + 3); }
 constexpr uint32_t O1_SMALL_TAB = 4608;
+constexpr uint32_t O1_SMALL4_NS = 9;    // alphabet limit of the small 4-way order-1 variant (9 * 64 + 9 * 12 * 4 = 1008 B)
 
 // bounded reader over global-memory bytes
 struct GRd {
@@ -251,10 +252,13 @@ __device__ int32_t plan_chain(DecWork* W, const uint8_t* in, uint32_t in_len, ui
                 if (!push_job(W, JK_O0_4, make_job(p, csz, j.aux, usz, blk))) return ST_ARENA;
             }
             uint32_t kind = x32 ? JK_O1_32 : JK_O1_4;
-            if (x32 && !j.aux && in_len > 1) {                       // uncompressed table: count the alphabet to pick
+            if ((x32 || W->big_batch) && !j.aux && in_len > 1) {     // uncompressed table: count the alphabet to pick
                 GRd ar{in + 1, end};                                 // the kernel variant (small alphabets run at
-                uint32_t ns = 0;                                     // twice the occupancy)
-                if (count_alphabet(ar, &ns) && o1_compact_bytes(ns) <= O1_SMALL_TAB) kind = JK_O1_32S;
+                uint32_t ns = 0;                                     // two to three times the occupancy)
+                if (count_alphabet(ar, &ns)) {
+                    if (x32 && o1_compact_bytes(ns) <= O1_SMALL_TAB) kind = JK_O1_32S;
+                    if (!x32 && ns <= O1_SMALL4_NS) kind = JK_O1_4S;
+                }
             }
             if (!push_job(W, kind, j)) return ST_ARENA;
         } else {
@@ -1024,16 +1028,18 @@ __global__ void __launch_bounds__(32, 32) dec_o0c_kernel(DecWork* W, int32_t* st
 // scratch, the word ring, then TAB bytes of compact tables.
 template <int NWAY, bool SMALL = false> struct O1Smem {
     static constexpr int UNRANK = 0, RANK = 256;
-    // X_32: the frequency scratch is only live during set-up and shares its 1 KB with the word ring
-    static constexpr int FTMP = 512, RINGO = (NWAY == 32) ? 512 : 1536;
+    // the frequency scratch is only live during set-up; X_32 (1 KB ring) and the small 4-way variant
+    // (alphabets of <= 9 symbols, 256-byte ring) let it share the word ring's memory
+    static constexpr bool OVERLAY = (NWAY == 32) || SMALL;
+    static constexpr int FTMP = 512, RINGO = OVERLAY ? 512 : 1536;
     static constexpr int TABO = RINGO + GroupCfg<NWAY>::RING;
-    // X_32: 12992 B (<= 48 symbols, 15 warps / SM) or, SMALL, 4608 B (<= 25 symbols, 32 warps / SM);
-    // 4-way: 3072 B per group (<= 19 symbols, 40 groups / SM)
-    static constexpr int TAB = (NWAY == 32) ? (SMALL ? (int)O1_SMALL_TAB : 12992) : 3072;
+    // X_32: 12992 B (<= 48 symbols, 15 warps / SM) or, SMALL, 4608 B (<= 25 symbols, 28 warps / SM);
+    // 4-way: 3072 B per group (<= 19 symbols, 40 groups / SM) or, SMALL, 1024 B (<= 9 symbols, 120 groups / SM)
+    static constexpr int TAB = (NWAY == 32) ? (SMALL ? (int)O1_SMALL_TAB : 12992) : (SMALL ? 1024 : 3072);
+    static constexpr int FTMP_ENTRIES = OVERLAY ? GroupCfg<NWAY>::RING / 4 : 256;
     static constexpr int STRIDE = TABO + TAB;                        // multiple of 16
     static constexpr int TOTAL = STRIDE * GroupCfg<NWAY>::G;
 };
-
 struct O1Tables {
     uint32_t compact;       // 1: compact form in shared memory
     uint32_t tabs;          // compact: shared address of context 0's block [64 B coarse | 4 * (ns + 3) B entries]
@@ -1158,7 +1164,7 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     }
     G.sync();
     err = G.bcast(err); ns = G.bcast(ns); shift = G.bcast(shift);
-    if (err) return ST_FORMAT;
+    if (err || ns > (uint32_t)S::FTMP_ENTRIES) return ST_FORMAT;     // (the planner only routes fitting alphabets)
     const uint32_t M = 1u << shift;
 
     // ---- table storage
@@ -1397,7 +1403,7 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
 }
 
 template <int NWAY, bool BYTE, bool SMALL>
-__global__ void __launch_bounds__(32, SMALL ? 28 : 1) dec_o1_kernel(DecWork* W, int32_t* status, uint32_t kind) {
+__global__ void __launch_bounds__(32, (SMALL && NWAY == 32) ? 28 : 1) dec_o1_kernel(DecWork* W, int32_t* status, uint32_t kind) {
     using C = GroupCfg<NWAY>;
     using S = O1Smem<NWAY, SMALL>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -1744,6 +1750,7 @@ int decode_init(int device) {
     persistent_setup(JK_O1_32,  dec_o1_kernel<32, false, false>, O1Smem<32>::TOTAL, 32);
     persistent_setup(JK_O1_32S, dec_o1_kernel<32, false, true>,  O1Smem<32, true>::TOTAL, 32);
     persistent_setup(JK_O1_4,   dec_o1_kernel<4, false, false>,  O1Smem<4>::TOTAL, 32);
+    persistent_setup(JK_O1_4S,  dec_o1_kernel<4, false, true>,   O1Smem<4, true>::TOTAL, 32);
     persistent_setup(JK_R8_O1,  dec_o1_kernel<4, true, false>,   O1Smem<4>::TOTAL, 32);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1789,6 +1796,7 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     LAUNCH_DEC(JK_O1_32S, (dec_o1_kernel<32, false, true>), 1)
     LAUNCH_DEC(JK_O1_32, (dec_o1_kernel<32, false, false>), 1)
     LAUNCH_DEC(JK_O1_4, (dec_o1_kernel<4, false, false>), 8)
+    LAUNCH_DEC(JK_O1_4S, (dec_o1_kernel<4, false, true>), 8)
     LAUNCH_DEC(JK_R8_O0, (dec_o0_kernel<4, true>), 8)
     LAUNCH_DEC(JK_R8_O1, (dec_o1_kernel<4, true, false>), 8)
 #undef LAUNCH_DEC

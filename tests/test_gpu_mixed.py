@@ -106,10 +106,12 @@ def test_dropin_calls_from_many_host_threads(oracle):
 
 def test_large_batch_routes_to_compact_order0_kernels(ctx, oracle, reflib):
     """More than 5000 blocks in one device-resident call: small-alphabet 4-way / 4x8 order-0 streams
-    are decoded by the compact-table kernels (a different code path from every other test)."""
+    and <= 9-symbol 4-way order-1 streams are decoded by the high-occupancy kernel variants (code
+    paths no other test reaches)."""
     import torch
     kinds = [("qual", 0, 0), ("acgt", 0, 0), ("wide", 0, 0), ("tag", 0x40, 0), ("random", 0, 0), ("qual", 0, 1),
-             ("wide", 0, 1), ("qual", 1, 0), ("qual", 4, 0)]
+             ("wide", 0, 1), ("qual", 1, 0), ("qual", 4, 0), ("acgt", 1, 0), ("wide", 1, 0), ("tag", 0x41, 0),
+             ("qual", 1, 1)]
     uniq, comp, meth = [], [], []
     for i, (gen, f, m) in enumerate(kinds):
         for n in (4096 + 37 * i, 3, 700):
