@@ -155,7 +155,7 @@ def run_reference(args, rank, world):
     }))
 
 
-def path_sweep(ctx, torch, hb, blocks, nblk, reps=3):
+def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None):
     """Device-resident GB/s (uncompressed) of the other hot-path legs on the same 1 MiB quality
     blocks: encode and decode x order-0/1 x X_32/4-way.  Decode inputs come from the encoder under
     test; every leg is checked by a device-side round-trip comparison."""
@@ -169,8 +169,11 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3):
     d_out = torch.empty(nblk * n, dtype=torch.uint8, device="cuda")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res = {}
-    for name, f in (("o0_x32", 4), ("o1_x32", 5), ("o0_4way", 0), ("o1_4way", 1),
-                    ("r4x8_o0", hb.ORDER_RANS4x8), ("r4x8_o1", hb.ORDER_RANS4x8 | 1)):
+    all_legs = (("o0_x32", 4), ("o1_x32", 5), ("o0_4way", 0), ("o1_4way", 1),
+                ("r4x8_o0", hb.ORDER_RANS4x8), ("r4x8_o1", hb.ORDER_RANS4x8 | 1))
+    for name, f in all_legs:
+        if legs is not None and name not in legs:
+            continue
         legacy = bool(f & hb.ORDER_RANS4x8)
         bound = hb.load_library().hts_b200_compress_bound_4x8(n) if legacy else hb.rans_compress_bound_4x16(n, f)
         cap = (bound + 15) // 16 * 16
@@ -345,6 +348,12 @@ def run_ours(args, rank, world, local_rank):
         del d_in, d_out
         torch.cuda.empty_cache()
         paths = path_sweep(ctx, torch, hb, blocks, min(nblk, 4096))
+        # a 4-way stream is 4 lanes of serial work, so its throughput grows with the batch until the SMs
+        # are full: the same legs at 16384 blocks (above ~5000 blocks the planner switches small-alphabet
+        # 4-way streams to the high-occupancy kernel variants)
+        if torch.cuda.get_device_properties(local_rank).total_memory > 100 * 2**30:
+            big = path_sweep(ctx, torch, hb, blocks, 16384, reps=2, legs=("o0_4way", "o1_4way"))
+            paths.update({k + "_16384blk": v for k, v in big.items()})
 
     if rank != 0:
         if dist is not None:
