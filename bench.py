@@ -162,7 +162,9 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None):
     import numpy as np
     n, distinct = BLOCK, len(blocks)
     stream = torch.cuda.ExternalStream(ctx.stream)
-    d_raw = torch.from_numpy(np.concatenate([blocks[i % distinct] for i in range(nblk)])).cuda()
+    d_one = torch.from_numpy(np.concatenate(blocks)).cuda()              # the distinct blocks, tiled on the device
+    d_raw = d_one.repeat((nblk + distinct - 1) // distinct)[: nblk * n].contiguous()
+    del d_one
     raw_off = torch.arange(nblk, dtype=torch.int64, device="cuda") * n
     raw_len = torch.full((nblk,), n, dtype=torch.int32, device="cuda")
     status = torch.zeros(nblk, dtype=torch.int32, device="cuda")
