@@ -304,6 +304,34 @@ class Context:
                for i in range(n)]
         return res, status
 
+    def uncompress_many_dev(self, streams, sizes, methods=None):
+        """As uncompress_many, through the device-resident entry point (one call, whatever the batch
+        size: large batches reach the high-occupancy kernel variants).  Needs torch."""
+        import torch
+        n = len(streams)
+        caps = np.array(sizes, np.uint32)
+        in_len = np.array([len(s) for s in streams], np.uint32)
+        in_off = np.zeros(n, np.uint64)
+        out_off = np.zeros(n, np.uint64)
+        if n > 1:
+            in_off[1:] = np.cumsum((in_len[:-1].astype(np.uint64) + 15) // 16 * 16)
+            out_off[1:] = np.cumsum((caps[:-1].astype(np.uint64) + 15) // 16 * 16)
+        ib = np.zeros(int(in_off[-1] + in_len[-1]) + 16, np.uint8)
+        for i, s in enumerate(streams):
+            ib[int(in_off[i]): int(in_off[i]) + len(s)] = np.frombuffer(bytes(s), np.uint8)
+        d_in = torch.from_numpy(ib).cuda()
+        d_out = torch.zeros(int(out_off[-1] + caps[-1]) + 16, dtype=torch.uint8, device="cuda")
+        d_len = torch.from_numpy(caps.view(np.int32).copy()).cuda()
+        d_st = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_m = None if methods is None else torch.from_numpy(np.array(methods, np.uint8)).cuda()
+        self.uncompress_batch_dev(n, d_in, torch.from_numpy(in_off.view(np.int64)).cuda(),
+                                  torch.from_numpy(in_len.view(np.int32)).cuda(), d_out,
+                                  torch.from_numpy(out_off.view(np.int64)).cuda(), d_len, d_st, d_m)
+        ob, out_len, status = d_out.cpu().numpy(), d_len.cpu().numpy().view(np.uint32), d_st.cpu().numpy()
+        res = [bytes(ob[int(out_off[i]): int(out_off[i]) + int(min(out_len[i], caps[i]))]) if status[i] == 0 else None
+               for i in range(n)]
+        return res, status
+
     def compress_many(self, blocks, orders):
         n = len(blocks)
         if n == 0:

@@ -187,3 +187,32 @@ def test_fuzz_no_crash(ctx, oracle):
     data = synth.qual_block(2, 10000).tobytes()
     out, status = ctx.uncompress_many([oracle.compress(data, 5)], [len(data)])
     assert out[0] == data
+
+
+def test_fuzz_large_batch_all_codecs(ctx, oracle):
+    """Damaged streams of every codec (4x16 families, X_32, rANS 4x8, compressed order-1 tables) in
+    batches large enough for the high-occupancy kernel variants, through both batch entry points.
+    The device must not fault (tools/fuzz.py is the long-running form of this test)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from fuzz import damage
+    rng = np.random.default_rng(11)
+    base = []
+    for i in range(60):
+        gen = ["qual", "wide", "tag", "acgt", "u32", "random"][i % 6]
+        n = int(rng.integers(1, 5000))
+        d = synth.GENERATORS[gen](i, n).tobytes()
+        base.append((oracle.compress(d, (ALL_FLAGS + X32_FLAGS)[i % len(ALL_FLAGS + X32_FLAGS)]), n, 0))
+        base.append((oracle.compress_4x8(d, i & 1), n, 1))
+    d2 = bytes(rng.permutation(np.arange(256).repeat(8)).astype(np.uint8))
+    base.append((oracle.compress(d2, 1), len(d2), 0))
+    base.append((oracle.compress(d2, 5), len(d2), 0))
+    for it in range(2):
+        streams, sizes, methods = [], [], []
+        for _ in range(5600):
+            c, n, m = base[int(rng.integers(0, len(base)))]
+            streams.append(damage(rng, c)); sizes.append(n); methods.append(m)
+        (ctx.uncompress_many_dev if it else ctx.uncompress_many)(streams, sizes, methods)
+        data = synth.qual_block(2, 10000).tobytes()
+        out, status = ctx.uncompress_many([oracle.compress(data, 5)], [len(data)])
+        assert status[0] == 0 and out[0] == data
