@@ -1215,25 +1215,33 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
             // from here on every lane of the warp codes rows full-1 .. 0 of its stream
             constexpr int B = 8;
             const uint8_t* ip = in + G.glane;
+            uint8_t* const obase = act_s ? S->out : nullptr;         // (kept in registers: the asm steps clobber memory)
             uint32_t r = full;                                       // rows left
             uint32_t nb[B];
 #pragma unroll
             for (int u = 0; u < B; u++) nb[u] = (r > (uint32_t)u) ? __ldg(ip + (size_t)(r - 1 - u) * NWAY) : 0u;
+            const uint8_t* pp = ip + (size_t)r * NWAY;               // one row past the first row of the current batch
             while (r >= B) {
                 uint32_t b[B];
 #pragma unroll
                 for (int u = 0; u < B; u++) b[u] = nb[u];
                 r -= B;
+                pp -= B * NWAY;                                      // rows r-1-u sit at pp - (u+1)*NWAY
+                if (r >= B) {
 #pragma unroll
-                for (int u = 0; u < B; u++) nb[u] = (r > (uint32_t)u) ? __ldg(ip + (size_t)(r - 1 - u) * NWAY) : 0u;
+                    for (int u = 0; u < B; u++) nb[u] = __ldg(pp - (u + 1) * NWAY);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < B; u++) nb[u] = (r > (uint32_t)u) ? __ldg(pp - (u + 1) * NWAY) : 0u;
+                }
                 EncSym sy[B];
 #pragma unroll
                 for (int u = 0; u < B; u++) sy[u] = ssym[b[u]];
                 if (NWAY == 32 && !BYTE) {
-                    uint32_t wpo = (uint32_t)(wp - S->out);
+                    uint32_t wpo = (uint32_t)(wp - obase);
 #pragma unroll
-                    for (int u = 0; u < B; u++) x = enc_put_x32(x, sy[u], wpo, S->out, gt_mask);
-                    wp = S->out + wpo;
+                    for (int u = 0; u < B; u++) x = enc_put_x32(x, sy[u], wpo, obase, gt_mask);
+                    wp = obase + wpo;
                 } else {
 #pragma unroll
                     for (int u = 0; u < B; u++) x = enc_step<NWAY, BYTE>(x, true, sy[u], wp, G);
@@ -1257,6 +1265,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
             ByteSrc src;
             src.init(in + (size_t)G.glane * seg, in + (size_t)G.glane * seg + my_n);
             const bool sm_syms = (syms == ssym);                     // this group's symbols are in shared memory
+            uint8_t* const obase1 = act_s ? S->out : nullptr;
             uint32_t rs = 0;                                         // rank of the symbol to code next
             if (my_n) rs = srank[src.get()];
             uint32_t left = my_n;                                    // symbols this lane still has to code
@@ -1289,10 +1298,10 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                     rs = rc;
                 }
                 if (NWAY == 32 && !BYTE) {
-                    uint32_t wpo = (uint32_t)(wp - S->out);
+                    uint32_t wpo = (uint32_t)(wp - obase1);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) x = enc_put_x32(x, sy[u], wpo, S->out, gt_mask);
-                    wp = S->out + wpo;
+                    for (int u = 0; u < 4; u++) x = enc_put_x32(x, sy[u], wpo, obase1, gt_mask);
+                    wp = obase1 + wpo;
                 } else {
 #pragma unroll
                     for (int u = 0; u < 4; u++) x = enc_step<NWAY, BYTE>(x, true, sy[u], wp, G);
