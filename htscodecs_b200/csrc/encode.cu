@@ -530,22 +530,29 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
         {
             for (uint32_t i = tid; i < head; i += HT) atomicAdd(&h[in[i]], 1u);
             for (uint32_t i = head + nv * 16 + tid; i < n; i += HT) atomicAdd(&h[in[i]], 1u);
+            // PF chunks per thread are kept in flight: with 12 warps per SM a single 16-byte load each
+            // would leave the kernel bound by memory latency (bytes in flight), not by its counters
+            constexpr int PF = 4;
             uint32_t since = 0;
-            uint4 nq = make_uint4(0, 0, 0, 0);
-            if (tid < nv) nq = __ldg(v + tid);                       // one chunk ahead
-            for (uint32_t i0 = 0; i0 < nv; i0 += HT) {
-                const uint32_t i = i0 + tid;
-                const uint4 q = nq;
-                if (i + HT < nv) nq = __ldg(v + i + HT);
-                if (i < nv) {
-                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            uint4 nq[PF];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
+            for (int d = 0; d < PF; d++) nq[d] = (tid + d * HT < nv) ? __ldg(v + tid + d * HT) : make_uint4(0, 0, 0, 0);
+            for (uint32_t i0 = 0; i0 < nv; i0 += PF * HT) {
 #pragma unroll
-                        for (int bb = 0; bb < 4; bb++) (*hist_ctr(myarea, (w[k] >> (8 * bb)) & 0xffu, lane))++;
+                for (int d = 0; d < PF; d++) {
+                    const uint32_t i = i0 + d * HT + tid;
+                    const uint4 q = nq[d];
+                    if (i + PF * HT < nv) nq[d] = __ldg(v + i + PF * HT);
+                    if (i < nv) {
+                        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+#pragma unroll
+                            for (int bb = 0; bb < 4; bb++) (*hist_ctr(myarea, (w[k] >> (8 * bb)) & 0xffu, lane))++;
+                        }
                     }
                 }
-                since += 16;
+                since += 16 * PF;
                 if (since >= HT_TILE) { hist_fold(cnt, h, 256); since = 0; }          // block-uniform
             }
             hist_fold(cnt, h, 256);
@@ -576,33 +583,42 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
             for (uint32_t i = head + nv * 16 + tid; i < n; i += HT) atomicAdd(&ptot[rank[i ? in[i - 1] : 0u] * ns + rank[in[i]]], 1u);
             // the segment starts are coded in context 0 (:720-723, with 4 -> nway)
             for (uint32_t k = 1 + tid; k < nway; k += HT) atomicAdd(&ptot[rank[0] * ns + rank[in[k * seg]]], 1u);
+            constexpr int PF = 4;                                    // chunks per thread in flight (see the order-0 pass)
             uint32_t since = 0;
-            uint4 nq = make_uint4(0, 0, 0, 0);
-            uint32_t nc = 0;                                         // byte preceding the prefetched chunk
-            if (tid < nv) { nq = __ldg(v + tid); const uint32_t at = head + tid * 16; nc = at ? in[at - 1] : 0u; }
-            for (uint32_t i0 = 0; i0 < nv; i0 += HT) {
-                const uint32_t i = i0 + tid;
-                const uint4 q = nq;
-                const uint32_t c0 = nc;
-                if (i + HT < nv) { nq = __ldg(v + i + HT); nc = in[head + (i + HT) * 16 - 1]; }
-                if (i < nv) {
-                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                    // all 17 rank look-ups first (the counter stores below could alias the rank table as far
-                    // as the compiler knows, which would serialise look-up and update per byte)
-                    uint32_t rk[16];
+            uint4 nq[PF];
+            uint32_t nc[PF];                                         // byte preceding each prefetched chunk
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
+            for (int d = 0; d < PF; d++) {
+                const uint32_t i = tid + d * HT;
+                nq[d] = make_uint4(0, 0, 0, 0); nc[d] = 0;
+                if (i < nv) { nq[d] = __ldg(v + i); const uint32_t at = head + i * 16; nc[d] = at ? in[at - 1] : 0u; }
+            }
+            for (uint32_t i0 = 0; i0 < nv; i0 += PF * HT) {
 #pragma unroll
-                        for (int bb = 0; bb < 4; bb++) rk[4 * k + bb] = rank[(w[k] >> (8 * bb)) & 0xffu];
-                    }
-                    uint32_t rc = rank[c0] * ns;                     // context of the chunk's first byte
+                for (int d = 0; d < PF; d++) {
+                    const uint32_t i = i0 + d * HT + tid;
+                    const uint4 q = nq[d];
+                    const uint32_t c0 = nc[d];
+                    if (i + PF * HT < nv) { nq[d] = __ldg(v + i + PF * HT); nc[d] = in[head + (i + PF * HT) * 16 - 1]; }
+                    if (i < nv) {
+                        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                        // all 17 rank look-ups first (the counter stores below could alias the rank table as far
+                        // as the compiler knows, which would serialise look-up and update per byte)
+                        uint32_t rk[16];
 #pragma unroll
-                    for (int t = 0; t < 16; t++) {
-                        (*hist_ctr(myarea, rc + rk[t], lane))++;
-                        rc = rk[t] * ns;
+                        for (int k = 0; k < 4; k++) {
+#pragma unroll
+                            for (int bb = 0; bb < 4; bb++) rk[4 * k + bb] = rank[(w[k] >> (8 * bb)) & 0xffu];
+                        }
+                        uint32_t rc = rank[c0] * ns;                 // context of the chunk's first byte
+#pragma unroll
+                        for (int t = 0; t < 16; t++) {
+                            (*hist_ctr(myarea, rc + rk[t], lane))++;
+                            rc = rk[t] * ns;
+                        }
                     }
                 }
-                since += 16;
+                since += 16 * PF;
                 if (since >= HT_TILE) { hist_fold(cnt, ptot, ns * ns); since = 0; }
             }
             hist_fold(cnt, ptot, ns * ns);
