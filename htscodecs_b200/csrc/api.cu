@@ -258,12 +258,12 @@ extern "C" int hts_b200_uncompress_batch_dev(hts_b200_ctx* ctx, int nblk, const 
     DecodeBatch b;
     b.work = nullptr; b.hdr = nullptr; b.in_base = in_base; b.in_off = in_off; b.in_len = in_len;
     b.out_base = out_base; b.out_off = out_off; b.out_len = out_len; b.status = status; b.method = method;
-    b.nblk = nblk; b.kinds = method ? ~0u : ~((1u << JK_R8_O0) | (1u << JK_R8_O1) | (1u << JK_R8_O0C)); b.post = 7u;
+    b.nblk = nblk; b.kinds = method ? ~0u : ~((1u << JK_R8_O0) | (1u << JK_R8_O1) | (1u << JK_R8_O0C) | (1u << JK_R8_O1S)); b.post = 7u;
     // more 4-way streams than the LUT kernels keep resident (40 per SM): let the planner route
     // small-alphabet order-0 streams to the compact-table kernels (256 per SM)
     static const int compact_min = getenv("HTSCODECS_B200_COMPACT_MIN") ? atoi(getenv("HTSCODECS_B200_COMPACT_MIN")) : 5000;
     const bool big = nblk > compact_min;
-    if (!big) b.kinds &= ~((1u << JK_O0_4C) | (1u << JK_R8_O0C) | (1u << JK_O1_4S));
+    if (!big) b.kinds &= ~((1u << JK_O0_4C) | (1u << JK_R8_O0C) | (1u << JK_O1_4S) | (1u << JK_R8_O1S));
     b.big_batch = big;
     for (int attempt = 0; attempt < 8; attempt++) {
         if (dec_prepare(ctx, s, nblk, arena_bytes)) return -1;
@@ -396,7 +396,7 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
                 if (!in_len[a + i]) continue;
                 uint8_t f = in_base[in_off[a + i]];
                 if (method && method[a + i] == 1) { kinds |= f ? (1u << JK_R8_O1) : (1u << JK_R8_O0); continue; }
-                if (f & F_STRIPE) { kinds |= ~((1u << JK_R8_O0) | (1u << JK_R8_O1) | (1u << JK_O0_4C) | (1u << JK_R8_O0C) | (1u << JK_O1_4S)); post |= 7u; continue; }
+                if (f & F_STRIPE) { kinds |= ~((1u << JK_R8_O0) | (1u << JK_R8_O1) | (1u << JK_O0_4C) | (1u << JK_R8_O0C) | (1u << JK_O1_4S) | (1u << JK_R8_O1S)); post |= 7u; continue; }
                 bool x32 = f & F_X32;
                 if (f & F_CAT) kinds |= 1u << JK_COPY;
                 else if (f & F_ORDER1) kinds |= (x32 ? (1u << JK_O1_32) | (1u << JK_O1_32S) : (1u << JK_O1_4)) | (1u << JK_O0_4);   // O0_4: compressed tables

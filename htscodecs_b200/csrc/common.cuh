@@ -24,7 +24,7 @@ enum : int32_t {
 enum JobKind : uint32_t {
     JK_O0_4 = 0, JK_O0_32, JK_O1_4, JK_O1_32, JK_R8_O0, JK_R8_O1, JK_COPY,
     JK_O1_32S,             // X_32 order-1 streams with a small alphabet: the high-occupancy kernel variant
-    JK_O1_4S,              // 4-way order-1 streams with <= 9 symbols in large batches: 120 resident streams per SM
+    JK_O1_4S, JK_R8_O1S,   // 4-way / 4x8 order-1 streams with <= 9 symbols in large batches: 120 resident streams per SM
     JK_O0_4C, JK_R8_O0C,   // 4-way / 4x8 order-0 streams on compact tables: 256 resident streams per SM, used
                            // for batches too large for one wave of the 4 KB-LUT kernels
     JK_NKINDS

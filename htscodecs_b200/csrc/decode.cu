@@ -317,6 +317,23 @@ __global__ void plan_kernel(PlanArgs A) {
             else if (n > cap) st = ST_SIZE;
             else {
                 uint32_t kind = in[0] ? JK_R8_O1 : JK_R8_O0;
+                if (in[0] && W->big_batch) {
+                    // count the byte values named by the order-1 tables (contexts and symbols, plus 0);
+                    // the scan stops as soon as the small variant's limit is exceeded
+                    GRd ar{in + 9, in + in_len};
+                    uint32_t seen[8] = {1u, 0, 0, 0, 0, 0, 0, 0}, ns = 1, run_i = 0, c = ar.get(), dummy;
+                    bool ok = in_len >= 27;
+                    auto mark = [&](uint32_t j) { if (!((seen[j >> 5] >> (j & 31)) & 1u)) { seen[j >> 5] |= 1u << (j & 31); ns++; } };
+                    while (ok) {
+                        mark(c);
+                        if (!parse_table_4x8(ar, [&](uint32_t j, uint32_t) { mark(j); }, &dummy, true) || ns > O1_SMALL4_NS) { ok = false; break; }
+                        if (!run_i && c + 1 == ar.peek()) { ar.get(); c++; run_i = ar.get(); }
+                        else if (run_i) { run_i--; if (++c > 255) { ok = false; break; } }
+                        else c = ar.get();
+                        if (!c) break;
+                    }
+                    if (ok && ns <= O1_SMALL4_NS) kind = JK_R8_O1S;
+                }
                 if (!in[0] && W->big_batch) {
                     GRd ar{in + 9, in + in_len};
                     uint32_t ns = 0, sum = 0;
@@ -1751,6 +1768,7 @@ int decode_init(int device) {
     persistent_setup(JK_O1_32S, dec_o1_kernel<32, false, true>,  O1Smem<32, true>::TOTAL, 32);
     persistent_setup(JK_O1_4,   dec_o1_kernel<4, false, false>,  O1Smem<4>::TOTAL, 32);
     persistent_setup(JK_O1_4S,  dec_o1_kernel<4, false, true>,   O1Smem<4, true>::TOTAL, 32);
+    persistent_setup(JK_R8_O1S, dec_o1_kernel<4, true, true>,    O1Smem<4, true>::TOTAL, 32);
     persistent_setup(JK_R8_O1,  dec_o1_kernel<4, true, false>,   O1Smem<4>::TOTAL, 32);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1799,6 +1817,7 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     LAUNCH_DEC(JK_O1_4S, (dec_o1_kernel<4, false, true>), 8)
     LAUNCH_DEC(JK_R8_O0, (dec_o0_kernel<4, true>), 8)
     LAUNCH_DEC(JK_R8_O1, (dec_o1_kernel<4, true, false>), 8)
+    LAUNCH_DEC(JK_R8_O1S, (dec_o1_kernel<4, true, true>), 8)
 #undef LAUNCH_DEC
     if (want(JK_COPY))  { copy_kernel<<<g_sms * 4, 256, 0, st>>>(b.work); launches++; }
     if (b.post & 1u) { rle_kernel<<<g_sms * 4, RLE_T, 0, st>>>(b.work, b.status, b.out_len); launches++; }
