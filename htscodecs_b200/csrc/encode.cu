@@ -98,7 +98,7 @@ struct EncBlock {
 struct EncWork {
     EncLeaf* leaves; EncStream* streams; EncBlock* blocks;
     uint32_t nleaves, nstreams, nblocks;
-    uint32_t next_misc[8];         // persistent-kernel cursors, one per enc_rans_kernel launch
+    uint32_t next_misc[12];        // persistent-kernel cursors, one per enc_rans_kernel launch
 };
 
 __constant__ double c_log10[257];   // log(1024 + k)  (host libm, see encode_init)
@@ -893,6 +893,9 @@ __global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
                 if (legacy) table_4x8_o0(reinterpret_cast<int*>(Fs), n, S.out, S.syms, &tab);
                 else if (build_o0_tables_enc(Fs, n, S.out, S.syms, &tab) < 0) S.size = 0xffffffffu;
                 S.tab_len = tab;
+                uint32_t present = 0;
+                for (int j = 0; j < 256; j++) present += S.F0[j] != 0;
+                S.ns = present;                              // picks the order-0 coder variant (compact symbol table or not)
             }
             continue;
         }
@@ -1168,10 +1171,13 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
     using EG = EGrp<NWAY>;
     extern __shared__ __align__(16) uint8_t esm[];
     const EG G;
-    constexpr uint32_t PER_GROUP = ORDER ? (NSCAP * NSCAP * 16 + 256) : ENC_O0_SMEM_PER_GROUP;
+    // order 0, NSCAP 48: symbol table compacted over the alphabet ([256 B byte -> rank][NSCAP x 16 B]), 1 KB per
+    // stream instead of 4 KB -- the 4-way variant for batches too large for one wave of the 4 KB kernel
+    constexpr bool O0C = ORDER == 0 && NSCAP == 48;
+    constexpr uint32_t PER_GROUP = ORDER ? (NSCAP * NSCAP * 16 + 256) : (O0C ? (256 + NSCAP * 16) : ENC_O0_SMEM_PER_GROUP);
     uint8_t* gsm = esm + G.g * PER_GROUP;
-    EncSym* ssym = reinterpret_cast<EncSym*>(gsm);
-    uint8_t* srank = gsm + NSCAP * NSCAP * 16;                      // order-1 only
+    EncSym* ssym = reinterpret_cast<EncSym*>(O0C ? gsm + 256 : gsm);
+    uint8_t* srank = O0C ? gsm : gsm + NSCAP * NSCAP * 16;          // byte -> rank (order 1, compact order 0)
     uint32_t* cursor = &W->next_misc[cursor_id];
     const uint32_t nstreams = W->nstreams;
     uint32_t gt_mask;
@@ -1189,7 +1195,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
         EncStream* S = act_s ? &W->streams[si] : nullptr;
         if (act_s && (S->nway != NWAY || S->order_eff != ORDER || S->n == 0 || S->size == 0xffffffffu ||
                       (S->codec != 0) != BYTE)) act_s = false;
-        if (ORDER && act_s && (S->ns <= ns_lo || S->ns > ns_hi)) act_s = false;    // another variant's alphabet class
+        if (act_s && (S->ns <= ns_lo || S->ns > ns_hi)) act_s = false;             // another variant's alphabet class
         if (!__any_sync(0xffffffffu, act_s)) continue;
 
         const uint8_t* in = act_s ? S->src : nullptr;
@@ -1197,7 +1203,11 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
         uint32_t ns = 1;
         const EncSym* syms = ssym;
         if (ORDER == 0) {
-            if (act_s) for (uint32_t k = G.glane; k < 256; k += NWAY) ssym[k] = S->syms[k];
+            if (act_s && !O0C) for (uint32_t k = G.glane; k < 256; k += NWAY) ssym[k] = S->syms[k];
+            if (act_s && O0C) {                                      // ranks over the present symbols, their entries packed
+                uint32_t r = 0;
+                if (G.glane == 0) for (int sy = 0; sy < 256; sy++) if (S->F0[sy] != 0) { srank[sy] = (uint8_t)r; ssym[r] = S->syms[sy]; r++; }
+            }
         } else if (act_s) {
             ns = S->ns;
             // symbol -> rank
@@ -1210,6 +1220,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
 
         uint8_t* wp = act_s ? S->out + S->cap : nullptr;             // payload grows down from the end
         uint32_t x = BYTE ? (1u << 23) : (1u << 15);                 // RansEncInit, rANS_word.h:69-72 / rANS_byte.h:68-71
+        auto symidx = [&](uint32_t byte) -> uint32_t { return O0C ? (uint32_t)srank[byte] : byte; };
         if (ORDER == 0) {
             // symbol i belongs to state i % NWAY; rows are coded from the last to the first (:442-480).
             // The symbol bytes do not depend on the coder state, so they are fetched a batch of rows
@@ -1225,7 +1236,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                 const uint32_t kk = k - (maxrows - rows);
                 const uint32_t pos = in_rows ? (rows - 1 - kk) * NWAY + G.glane : 0;
                 const bool act = in_rows && pos < n;
-                EncSym s = ssym[act ? __ldg(in + pos) : 0];
+                EncSym s = ssym[act ? symidx(__ldg(in + pos)) : 0];
                 x = enc_step<NWAY, BYTE>(x, act, s, wp, G);
             }
             // from here on every lane of the warp codes rows full-1 .. 0 of its stream
@@ -1252,7 +1263,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                 }
                 EncSym sy[B];
 #pragma unroll
-                for (int u = 0; u < B; u++) sy[u] = ssym[b[u]];
+                for (int u = 0; u < B; u++) sy[u] = ssym[symidx(b[u])];
                 if (NWAY == 32 && !BYTE) {
                     uint32_t wpo = (uint32_t)(wp - obase);
 #pragma unroll
@@ -1267,7 +1278,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                 uint32_t bsel = nb[0];
 #pragma unroll
                 for (int q = 1; q < B; q++) if (u == (uint32_t)q) bsel = nb[q];
-                x = enc_step<NWAY, BYTE>(x, true, ssym[bsel], wp, G);
+                x = enc_step<NWAY, BYTE>(x, true, ssym[symidx(bsel)], wp, G);
             }
         } else {
             // state z owns in[z*seg, (z+1)*seg), the last state also the tail; coded last-to-first
@@ -1570,6 +1581,9 @@ template <typename K> int occ_grid(K kernel, int smem, int sms) {
 constexpr int SM_O0_32 = ENC_O0_SMEM_PER_GROUP, SM_O0_4 = ENC_O0_SMEM_PER_GROUP * 8;
 constexpr int SM_O1_32_S = 16 * 16 * 16 + 256, SM_O1_32_L = 48 * 48 * 16 + 256;     // small / large alphabet variants
 constexpr int SM_O1_4_S = (16 * 16 * 16 + 256) * 8;                                  // 4-way: small only (larger: global)
+constexpr int SM_O0_4_C = (256 + 48 * 16) * 8;                                       // 4-way order 0, compact symbol tables
+constexpr int SM_O1_4_T = (9 * 9 * 16 + 256) * 8;                                    // 4-way order 1, <= 9 symbols
+int g_grid_o0_4_c = 0, g_grid_o1_4_t = 0, g_grid_o0_8_c = 0, g_grid_o1_8_t = 0;
 int g_grid_o1_32_s = 0, g_grid_o1_32_l = 0, g_grid_o1_4_s = 0;
 
 }  // namespace
@@ -1598,6 +1612,10 @@ int encode_init(int device) {
     g_grid_enc[1][0] = occ_grid(enc_rans_kernel<32, 0, 16>, SM_O0_32, g_sms_enc);
     g_grid_o1_4_s = occ_grid(enc_rans_kernel<4, 1, 16>, SM_O1_4_S, g_sms_enc);
     occ_grid(enc_rans_kernel<4, 0, 16, true>, SM_O0_4, g_sms_enc);
+    g_grid_o0_4_c = occ_grid(enc_rans_kernel<4, 0, 48>, SM_O0_4_C, g_sms_enc);
+    g_grid_o1_4_t = occ_grid(enc_rans_kernel<4, 1, 9>, SM_O1_4_T, g_sms_enc);
+    g_grid_o0_8_c = occ_grid(enc_rans_kernel<4, 0, 48, true>, SM_O0_4_C, g_sms_enc);
+    g_grid_o1_8_t = occ_grid(enc_rans_kernel<4, 1, 9, true>, SM_O1_4_T, g_sms_enc);
     occ_grid(enc_rans_kernel<4, 1, 16, true>, SM_O1_4_S, g_sms_enc);
     g_grid_o1_32_s = occ_grid(enc_rans_kernel<32, 1, 16>, SM_O1_32_S, g_sms_enc);
     g_grid_o1_32_l = occ_grid(enc_rans_kernel<32, 1, 48>, SM_O1_32_L, g_sms_enc);
@@ -1798,8 +1816,6 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
         // an order-1 request can fall back to order 0 on the device, so the order-0 kernels always run
         // cursors: next_misc[0..4]; order-1 streams go to the small-alphabet variant (ns <= 16, tables in
         // shared memory at high occupancy) or the large one (ns > 16: shared up to 48 symbols, else global)
-        if (any4[0])  { enc_rans_kernel<4, 0, 16><<<g_grid_enc[0][0], 32, SM_O0_4, st>>>(dW, 0, 0, 256); launches++; }
-        if (any4[1])  { enc_rans_kernel<4, 1, 16><<<g_grid_o1_4_s, 32, SM_O1_4_S, st>>>(dW, 1, 0, 256); launches++; }
         // Shaped launches: a persistent kernel gives a warp to EG::G streams and the CTA scheduler fills
         // one SM before the next, so the dynamic shared-memory request is padded until exactly
         // c = ceil(groups / SMs) CTAs fit per SM and the grid is SMs x c (every SM holds the same load).
@@ -1811,13 +1827,22 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
             return c < cap ? std::max(smem, std::min(232448, (233472 / c - 1024) & ~127)) : smem;
         };
         int grid = 0, sm = 0;
-        if (any4[0])  { sm = shaped(g_grid_enc[0][0] / g_sms_enc, SM_O0_4, ngroups4, &grid); enc_rans_kernel<4, 0, 16><<<grid, 32, sm, st>>>(dW, 0, 0, 256); launches++; }
-        if (any4[1])  { sm = shaped(g_grid_o1_4_s / g_sms_enc, SM_O1_4_S, ngroups4, &grid); enc_rans_kernel<4, 1, 16><<<grid, 32, sm, st>>>(dW, 1, 0, 256); launches++; }
+        // 4-way streams of a batch too large for one wave of the 4 KB-table kernels (48 streams per SM) go to
+        // variants with compacted tables by alphabet size: order 0 with <= 48 symbols (1 KB per stream),
+        // order 1 with <= 9 symbols (1.5 KB); next_misc cursors 7..10
+        const bool big4 = ngroups4 > (uint32_t)(g_grid_enc[0][0]);
+        const uint32_t o0_lo = big4 ? 48u : 0u, o1_lo = big4 ? 9u : 0u;
+        if (any4[0])  { sm = shaped(g_grid_enc[0][0] / g_sms_enc, SM_O0_4, ngroups4, &grid); enc_rans_kernel<4, 0, 16><<<grid, 32, sm, st>>>(dW, 0, o0_lo, 256); launches++;
+                        if (big4) { sm = shaped(g_grid_o0_4_c / g_sms_enc, SM_O0_4_C, ngroups4, &grid); enc_rans_kernel<4, 0, 48><<<grid, 32, sm, st>>>(dW, 7, 0, 48); launches++; } }
+        if (any4[1])  { sm = shaped(g_grid_o1_4_s / g_sms_enc, SM_O1_4_S, ngroups4, &grid); enc_rans_kernel<4, 1, 16><<<grid, 32, sm, st>>>(dW, 1, o1_lo, 256); launches++;
+                        if (big4) { sm = shaped(g_grid_o1_4_t / g_sms_enc, SM_O1_4_T, ngroups4, &grid); enc_rans_kernel<4, 1, 9><<<grid, 32, sm, st>>>(dW, 8, 0, 9); launches++; } }
         if (any32[0]) { sm = shaped(g_grid_enc[1][0] / g_sms_enc, SM_O0_32, ngroups32, &grid); enc_rans_kernel<32, 0, 16><<<grid, 32, sm, st>>>(dW, 2, 0, 256); launches++; }
         if (any32[1]) { sm = shaped(g_grid_o1_32_s / g_sms_enc, SM_O1_32_S, ngroups32, &grid); enc_rans_kernel<32, 1, 16><<<grid, 32, sm, st>>>(dW, 3, 0, 16); launches++;
                         sm = shaped(g_grid_o1_32_l / g_sms_enc, SM_O1_32_L, ngroups32, &grid); enc_rans_kernel<32, 1, 48><<<grid, 32, sm, st>>>(dW, 4, 16, 256); launches++; }
-        if (any8[0])  { sm = shaped(g_grid_enc[0][0] / g_sms_enc, SM_O0_4, ngroups4, &grid); enc_rans_kernel<4, 0, 16, true><<<grid, 32, sm, st>>>(dW, 5, 0, 256); launches++; }
-        if (any8[1])  { sm = shaped(g_grid_o1_4_s / g_sms_enc, SM_O1_4_S, ngroups4, &grid); enc_rans_kernel<4, 1, 16, true><<<grid, 32, sm, st>>>(dW, 6, 0, 256); launches++; }
+        if (any8[0])  { sm = shaped(g_grid_enc[0][0] / g_sms_enc, SM_O0_4, ngroups4, &grid); enc_rans_kernel<4, 0, 16, true><<<grid, 32, sm, st>>>(dW, 5, o0_lo, 256); launches++;
+                        if (big4) { sm = shaped(g_grid_o0_8_c / g_sms_enc, SM_O0_4_C, ngroups4, &grid); enc_rans_kernel<4, 0, 48, true><<<grid, 32, sm, st>>>(dW, 9, 0, 48); launches++; } }
+        if (any8[1])  { sm = shaped(g_grid_o1_4_s / g_sms_enc, SM_O1_4_S, ngroups4, &grid); enc_rans_kernel<4, 1, 16, true><<<grid, 32, sm, st>>>(dW, 6, o1_lo, 256); launches++;
+                        if (big4) { sm = shaped(g_grid_o1_8_t / g_sms_enc, SM_O1_4_T, ngroups4, &grid); enc_rans_kernel<4, 1, 9, true><<<grid, 32, sm, st>>>(dW, 10, 0, 9); launches++; } }
         enc_finish_kernel<<<g, 256, 0, st>>>(dW); launches++;
     }
     enc_block_kernel<<<g, 256, 0, st>>>(dW, b.out_len, b.status); launches++;

@@ -154,3 +154,37 @@ def test_dropin_encode_contract(oracle):
     # capacity below the bound is refused (the reference's sub-encoders refuse too, ...4x16pr.c:396)
     assert hb.rans_compress_to_4x16(data, 0, capacity=100) is None
     assert hb.rans_compress_4x16(b"", 0) == bytes([0x20, 0x00])           # n=0 -> CAT
+
+
+def test_large_batch_encode_variants(ctx, oracle):
+    """More 4-way streams than one wave of the 4 KB-table coders: the compact-table encoder variants
+    (order 0 <= 48 symbols, order 1 <= 9 symbols, and their rANS 4x8 twins) must produce the same bytes."""
+    L = hb.ORDER_RANS4x8
+    cases = [("qual", 0), ("qual", 1), ("acgt", 0), ("acgt", 1), ("wide", 0), ("wide", 1), ("random", 0), ("tag", 0x40),
+             ("qual", L), ("qual", L | 1), ("wide", L), ("wide", L | 1), ("qual", 4), ("qual", 5)]
+    uniq = [(synth.GENERATORS[g](i, 2500 + 61 * i).tobytes(), f) for i, (g, f) in enumerate(cases)]
+    want = [oracle.compress_4x8(d, f & 1) if f & L else oracle.compress(d, f) for d, f in uniq]
+    n = 7400                                            # > 8 streams x 6 CTAs x 148 SMs
+    blocks = [uniq[i % len(uniq)][0] for i in range(n)]
+    orders = [uniq[i % len(uniq)][1] for i in range(n)]
+    import torch
+    in_len = np.array([len(b) for b in blocks], np.uint32)
+    in_off = np.zeros(n, np.uint64); in_off[1:] = np.cumsum((in_len[:-1].astype(np.uint64) + 15) // 16 * 16)
+    caps = np.array([hb.load_library().hts_b200_compress_bound_4x8(len(b)) if o & L else hb.rans_compress_bound_4x16(len(b), o)
+                     for b, o in zip(blocks, orders)], np.uint32)
+    out_off = np.zeros(n, np.uint64); out_off[1:] = np.cumsum((caps[:-1].astype(np.uint64) + 15) // 16 * 16)
+    ib = np.zeros(int(in_off[-1] + in_len[-1]) + 16, np.uint8)
+    for k, b in enumerate(blocks):
+        ib[int(in_off[k]): int(in_off[k]) + len(b)] = np.frombuffer(b, np.uint8)
+    d_out = torch.zeros(int(out_off[-1] + caps[-1]) + 16, dtype=torch.uint8, device="cuda")
+    d_len = torch.from_numpy(caps.view(np.int32).copy()).cuda()
+    d_st = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ctx.compress_batch_dev(n, torch.from_numpy(ib).cuda(), torch.from_numpy(in_off.view(np.int64)).cuda(),
+                           torch.from_numpy(in_len.view(np.int32)).cuda(), d_out,
+                           torch.from_numpy(out_off.view(np.int64)).cuda(), d_len, d_st,
+                           torch.from_numpy(np.array(orders, np.int32)).cuda())
+    assert int((d_st != 0).sum()) == 0
+    ob, ol = d_out.cpu().numpy(), d_len.cpu().numpy()
+    for k in list(range(0, 3 * len(uniq))) + list(range(n - 2 * len(uniq), n)):
+        got = bytes(ob[int(out_off[k]): int(out_off[k]) + int(ol[k])])
+        assert got == want[k % len(uniq)], (k, cases[k % len(uniq)])
