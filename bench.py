@@ -220,6 +220,73 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None):
     return res
 
 
+def mixed_leg(ctx, torch, hb, nblk, distinct=128, reps=2):
+    """BASELINE configs[4] scaled to one GPU's share: a mixed-flag corpus (40 % o0, 30 % o1, 10 % X_32 o0,
+    10 % X_32 o1, 5 % PACK/RLE/STRIPE variants, 5 % legacy rANS 4x8; synth.mixed_corpus) of nblk x 1 MiB
+    blocks, encoded and decoded in ONE batched device-resident call per direction."""
+    import numpy as np
+    from htscodecs_b200 import synth
+    n = BLOCK
+    spec = synth.mixed_corpus(distinct, seed=5, size=n, ragged=False)
+    blocks = [synth.GENERATORS[g](b, m) for g, b, m, _, _ in spec]
+    orders1 = np.array([f | (hb.ORDER_RANS4x8 if meth else 0) for _, _, _, f, meth in spec], dtype=np.int64)
+    meth1 = np.array([meth for *_, meth in spec], dtype=np.uint8)
+    lib = hb.load_library()
+    cap = max(lib.hts_b200_compress_bound_4x8(n), max(hb.rans_compress_bound_4x16(n, int(f)) for f in set(orders1[meth1 == 0])))
+    cap = (cap + 15) // 16 * 16
+    reps_t = (nblk + distinct - 1) // distinct
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    d_one = torch.from_numpy(np.concatenate(blocks)).cuda()
+    d_raw = d_one.repeat(reps_t)[: nblk * n].contiguous()
+    del d_one
+    order = torch.from_numpy(np.tile(orders1, reps_t)[:nblk].astype(np.int32)).cuda()
+    method = torch.from_numpy(np.tile(meth1, reps_t)[:nblk].copy()).cuda()
+    raw_off = torch.arange(nblk, dtype=torch.int64, device="cuda") * n
+    raw_len = torch.full((nblk,), n, dtype=torch.int32, device="cuda")
+    status = torch.zeros(nblk, dtype=torch.int32, device="cuda")
+    d_out = torch.empty(nblk * n, dtype=torch.uint8, device="cuda")
+    d_comp = torch.empty(nblk * cap, dtype=torch.uint8, device="cuda")
+    comp_off = torch.arange(nblk, dtype=torch.int64, device="cuda") * cap
+    comp_len = torch.full((nblk,), cap, dtype=torch.int32, device="cuda")
+    out_len = torch.full((nblk,), n, dtype=torch.int32, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def enc():
+        comp_len.fill_(cap)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        ctx.compress_batch_dev(nblk, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    enc()
+    assert int((status != 0).sum()) == 0, "mixed corpus: encode failed"
+    t_enc = min(enc() for _ in range(reps))
+    in_len = comp_len.clone()
+    csz = int(in_len.to(torch.int64).sum())
+
+    def dec():
+        out_len.fill_(n)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, method, sync=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    # first call synchronous: it sizes the context's scratch arena (transform temporaries, large order-1 tables),
+    # which an asynchronous call cannot grow (include/htscodecs_b200.h: sync == 0)
+    ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, method, sync=True)
+    dec()
+    assert int((status != 0).sum()) == 0, "mixed corpus: decode failed"
+    assert torch.equal(d_out, d_raw), "mixed corpus: round trip mismatch"
+    t_dec = min(dec() for _ in range(reps))
+    gb = nblk * n / 1e9
+    return {"encode_GBs": round(gb / (t_enc * 1e-3), 1), "decode_GBs": round(gb / (t_dec * 1e-3), 1),
+            "ratio": round(csz / (nblk * n), 4), "blocks": nblk, "distinct_blocks": distinct}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import htscodecs_b200 as hb
@@ -356,6 +423,7 @@ def run_ours(args, rank, world, local_rank):
         if torch.cuda.get_device_properties(local_rank).total_memory > 100 * 2**30:
             big = path_sweep(ctx, torch, hb, blocks, 16384, reps=2, legs=("o0_4way", "o1_4way"))
             paths.update({k + "_16384blk": v for k, v in big.items()})
+        paths["mixed_corpus"] = mixed_leg(ctx, torch, hb, min(nblk, 4096))
 
     if rank != 0:
         if dist is not None:

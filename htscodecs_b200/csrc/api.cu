@@ -80,6 +80,7 @@ struct Stage {
     PinBuf<uint8_t> h_method;
     DecSlot dec;
     EncSlot enc;
+    SideStreams side;           // the chunk's kernels of different kinds run side by side
     cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
     cudaStream_t s_compute = nullptr;   // one per stage: a block is decoded by ONE warp, so a chunk's kernels
                                         // last as long as its slowest block; chunks must overlap on the SMs
@@ -96,7 +97,7 @@ struct Stage {
     void release() {
         if (s_compute) cudaStreamDestroy(s_compute);
         d_in.release(); d_out.release(); d_off.release(); d_u32.release(); d_method.release();
-        h_off.release(); h_u32.release(); h_method.release(); dec.release(); enc.release();
+        h_off.release(); h_u32.release(); h_method.release(); dec.release(); enc.release(); side.release();
         if (h2d_done) cudaEventDestroy(h2d_done);
         if (compute_done) cudaEventDestroy(compute_done);
         if (d2h_done) cudaEventDestroy(d2h_done);
@@ -104,6 +105,10 @@ struct Stage {
 };
 
 constexpr int NSTAGE = 3;
+
+// job-kind sets for the host's "which kernels can be needed" hint
+constexpr uint32_t K_R8 = (1u << JK_R8_O0) | (1u << JK_R8_O1) | (1u << JK_R8_O0C) | (1u << JK_R8_O1S) | (1u << JK_R8_O1M);
+constexpr uint32_t K_BIG = (1u << JK_O0_4C) | (1u << JK_R8_O0C) | (1u << JK_O1_4S) | (1u << JK_R8_O1S);   // large batches only
 
 }  // namespace
 
@@ -113,6 +118,7 @@ struct hts_b200_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     DecSlot dec;                        // device-resident API
     EncSlot enc;
+    SideStreams side_dec;
     std::vector<Stage> stage;           // NSTAGE slots reused round-robin (full duplex) or one per chunk (half duplex)
     cudaEvent_t all_h2d = nullptr;
     bool full_duplex = true;            // overlap host->device with device->host copies (see hts_b200_set_copy_duplex)
@@ -161,6 +167,7 @@ extern "C" void hts_b200_destroy(hts_b200_ctx* ctx) {
     cudaDeviceSynchronize();
     ctx->dec.release();
     ctx->enc.release();
+    ctx->side_dec.release();
     for (auto& st : ctx->stage) st.release();
     if (ctx->all_h2d) cudaEventDestroy(ctx->all_h2d);
     ctx->pin_in.release(); ctx->pin_out.release();
@@ -258,12 +265,13 @@ extern "C" int hts_b200_uncompress_batch_dev(hts_b200_ctx* ctx, int nblk, const 
     DecodeBatch b;
     b.work = nullptr; b.hdr = nullptr; b.in_base = in_base; b.in_off = in_off; b.in_len = in_len;
     b.out_base = out_base; b.out_off = out_off; b.out_len = out_len; b.status = status; b.method = method;
-    b.nblk = nblk; b.kinds = method ? ~0u : ~((1u << JK_R8_O0) | (1u << JK_R8_O1) | (1u << JK_R8_O0C) | (1u << JK_R8_O1S)); b.post = 7u;
+    b.nblk = nblk; b.kinds = method ? ~0u : ~K_R8; b.post = 7u;
     // more 4-way streams than the LUT kernels keep resident (40 per SM): let the planner route
     // small-alphabet order-0 streams to the compact-table kernels (256 per SM)
     static const int compact_min = getenv("HTSCODECS_B200_COMPACT_MIN") ? atoi(getenv("HTSCODECS_B200_COMPACT_MIN")) : 5000;
     const bool big = nblk > compact_min;
-    if (!big) b.kinds &= ~((1u << JK_O0_4C) | (1u << JK_R8_O0C) | (1u << JK_O1_4S) | (1u << JK_R8_O1S));
+    if (!big) b.kinds &= ~K_BIG;
+    if (ctx->side_dec.init() == 0) b.side = &ctx->side_dec;
     b.big_batch = big;
     for (int attempt = 0; attempt < 8; attempt++) {
         if (dec_prepare(ctx, s, nblk, arena_bytes)) return -1;
@@ -395,16 +403,17 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
             for (int i = 0; i < n; i++) {
                 if (!in_len[a + i]) continue;
                 uint8_t f = in_base[in_off[a + i]];
-                if (method && method[a + i] == 1) { kinds |= f ? (1u << JK_R8_O1) : (1u << JK_R8_O0); continue; }
-                if (f & F_STRIPE) { kinds |= ~((1u << JK_R8_O0) | (1u << JK_R8_O1) | (1u << JK_O0_4C) | (1u << JK_R8_O0C) | (1u << JK_O1_4S) | (1u << JK_R8_O1S)); post |= 7u; continue; }
+                if (method && method[a + i] == 1) { kinds |= f ? (1u << JK_R8_O1) | (1u << JK_R8_O1M) : (1u << JK_R8_O0); continue; }
+                if (f & F_STRIPE) { kinds |= ~(K_R8 | K_BIG); post |= 7u; continue; }
                 bool x32 = f & F_X32;
                 if (f & F_CAT) kinds |= 1u << JK_COPY;
-                else if (f & F_ORDER1) kinds |= (x32 ? (1u << JK_O1_32) | (1u << JK_O1_32S) : (1u << JK_O1_4)) | (1u << JK_O0_4);   // O0_4: compressed tables
+                else if (f & F_ORDER1) kinds |= (x32 ? (1u << JK_O1_32) | (1u << JK_O1_32S) : (1u << JK_O1_4) | (1u << JK_O1_4M)) | (1u << JK_TAB);   // TAB: compressed tables
                 else kinds |= 1u << (x32 ? JK_O0_32 : JK_O0_4);
                 if (f & F_RLE) { post |= 1u; kinds |= 1u << (x32 ? JK_O0_32 : JK_O0_4); }
                 if (f & F_PACK) post |= 2u;
             }
             db.kinds = kinds; db.post = post;
+            if (S.side.init() == 0) db.side = &S.side;
             if (dec_enqueue(ctx, S.dec, db, cs)) return -1;
         } else {
             EncodeBatch eb;

@@ -27,6 +27,10 @@ enum JobKind : uint32_t {
     JK_O1_4S, JK_R8_O1S,   // 4-way / 4x8 order-1 streams with <= 9 symbols in large batches: 120 resident streams per SM
     JK_O0_4C, JK_R8_O0C,   // 4-way / 4x8 order-0 streams on compact tables: 256 resident streams per SM, used
                            // for batches too large for one wave of the 4 KB-LUT kernels
+    JK_O1_4M, JK_R8_O1M,   // 4-way / 4x8 order-1 streams of 20-47 symbols (q40-style qualities): 12.5 KB of compact
+                           // tables per stream in shared memory, 16 resident streams per SM
+    JK_TAB,                // order-0 (4-way) jobs that expand an order-1 stream's compressed table: they run before
+                           // every other kind, which then run side by side
     JK_NKINDS
 };
 
@@ -157,5 +161,17 @@ __device__ __forceinline__ uint32_t ld_u32_le(const uint8_t* p) {
 __device__ __forceinline__ void set_status(int32_t* status, uint32_t blk, int32_t code) {
     atomicMin(&status[blk], code);
 }
+
+// One side stream per job kind (decode) or kernel variant (encode): the entropy kernels of a batch that mixes
+// codecs run side by side (each is latency-bound -- one warp per stream or per eight 4-way streams -- so a mixed
+// batch then costs its slowest kind, not the sum over kinds).  Every kind's launch is shaped for the whole batch
+// (c CTAs per SM), so the kinds settle on disjoint groups of SMs, c CTAs each.  Owned by the caller, reused across batches.
+struct SideStreams {
+    static constexpr int N = 16;
+    cudaStream_t s[N] = {};
+    cudaEvent_t fork = nullptr, join[N] = {};
+    int init();
+    void release();
+};
 
 }  // namespace hb

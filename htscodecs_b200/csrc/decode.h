@@ -19,6 +19,7 @@ struct DecodeBatch {
     uint32_t kinds;             // bit k set: job kind k may occur (host hint; ~0u = unknown)
     uint32_t post;              // bit0 RLE, bit1 PACK, bit2 STRIPE may occur
     bool big_batch = false;     // route small-alphabet 4-way order-0 streams to the compact-table kernels
+    SideStreams* side = nullptr;   // nullptr: every kernel on the caller's stream, one after the other
 };
 
 int decode_init(int device);

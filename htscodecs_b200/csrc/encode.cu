@@ -98,7 +98,12 @@ struct EncBlock {
 struct EncWork {
     EncLeaf* leaves; EncStream* streams; EncBlock* blocks;
     uint32_t nleaves, nstreams, nblocks;
-    uint32_t next_misc[12];        // persistent-kernel cursors, one per enc_rans_kernel launch
+    uint32_t next_misc[16];        // persistent-kernel cursors, one per enc_rans_kernel launch
+    // Streams bucketed by coder variant once their tables are known (enc_bucket_kernel): vlist[v * nstreams + k] is
+    // the k-th stream of variant v (= its cursor index), so every warp of a variant's launch holds a full group.
+    uint32_t vcount[16];
+    uint32_t* vlist;
+    uint32_t o0_lo, o1_lo;         // large batches: 4-way alphabets up to these sizes go to the compact-table variants
 };
 
 __constant__ double c_log10[257];   // log(1024 + k)  (host libm, see encode_init)
@@ -1163,6 +1168,25 @@ struct ByteSrc {
     }
 };
 
+// One thread per stream: which enc_rans_kernel variant codes it (the cursor indices of encode_run).
+__global__ void enc_bucket_kernel(EncWork* W) {
+    const uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= W->nstreams) return;
+    const EncStream& S = W->streams[si];
+    if (S.n == 0 || S.size == 0xffffffffu) return;
+    const bool x32 = S.nway == 32, legacy = S.codec != 0;
+    uint32_t v;
+    if (S.order_eff == 0) {
+        if (x32) v = 2;
+        else if (S.ns <= W->o0_lo) v = legacy ? 9 : 7;
+        else v = legacy ? 5 : 0;
+    } else if (x32) v = S.ns <= 16 ? 3 : 4;
+    else if (S.ns <= W->o1_lo) v = legacy ? 10 : 8;
+    else if (S.ns <= 16) v = legacy ? 6 : 1;
+    else v = legacy ? 12 : 11;
+    W->vlist[(size_t)v * W->nstreams + atomicAdd(&W->vcount[v], 1u)] = si;
+}
+
 // Order-1 symbol tables live in shared memory when the alphabet has at most NSCAP symbols; two
 // kernel variants (NSCAP 16: 4 KB per group, many resident warps; NSCAP 48: 36 KB) split the
 // streams between them by alphabet size, larger alphabets read the table from global memory.
@@ -1179,24 +1203,20 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
     EncSym* ssym = reinterpret_cast<EncSym*>(O0C ? gsm + 256 : gsm);
     uint8_t* srank = O0C ? gsm : gsm + NSCAP * NSCAP * 16;          // byte -> rank (order 1, compact order 0)
     uint32_t* cursor = &W->next_misc[cursor_id];
-    const uint32_t nstreams = W->nstreams;
+    const uint32_t nstreams = W->vcount[cursor_id];
+    const uint32_t* vlist = W->vlist + (size_t)cursor_id * W->nstreams;
     uint32_t gt_mask;
     asm("mov.u32 %0, %%lanemask_gt;" : "=r"(gt_mask));
 
-    // streams are claimed EG::G at a time from an atomic cursor (the launch is shaped so that every SM
-    // holds the same number of CTAs); those of another nway/order/size class are skipped
+    // this variant's streams (enc_bucket_kernel) are claimed EG::G at a time from an atomic cursor (the launch is
+    // shaped so that every SM holds the same number of CTAs)
     for (;;) {
         uint32_t s0 = 0;
         if (lane_id() == 0) s0 = atomicAdd(cursor, (uint32_t)EG::G);
         s0 = __shfl_sync(0xffffffffu, s0, 0);
         if (s0 >= nstreams) break;
-        const uint32_t si = s0 + G.g;
-        bool act_s = si < nstreams;
-        EncStream* S = act_s ? &W->streams[si] : nullptr;
-        if (act_s && (S->nway != NWAY || S->order_eff != ORDER || S->n == 0 || S->size == 0xffffffffu ||
-                      (S->codec != 0) != BYTE)) act_s = false;
-        if (act_s && (S->ns <= ns_lo || S->ns > ns_hi)) act_s = false;             // another variant's alphabet class
-        if (!__any_sync(0xffffffffu, act_s)) continue;
+        const bool act_s = s0 + G.g < nstreams;
+        EncStream* S = act_s ? &W->streams[vlist[s0 + G.g]] : nullptr;
 
         const uint8_t* in = act_s ? S->src : nullptr;
         const uint32_t n = act_s ? S->n : 0;
@@ -1545,6 +1565,7 @@ struct EncImpl {
     bool pending = false;
     std::vector<uint32_t> h_len;
     std::vector<int32_t> h_order;
+    SideStreams side;                                          // the rANS kernel variants run side by side
 };
 
 int g_sms_enc = 0;
@@ -1573,6 +1594,8 @@ size_t up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 template <typename K> int occ_grid(K kernel, int smem, int sms) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);   // launches may pad (shaping)
+    // kernels of different variants / chunks share SMs: one L1 / shared-memory split for all of them
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, 32, smem);
     return std::max(per, 1) * sms;
@@ -1595,6 +1618,7 @@ void EncSlot::release() {
     if (I->d_desc) cudaFree(I->d_desc);
     if (I->h_desc) cudaFreeHost(I->h_desc);
     if (I->uploaded) cudaEventDestroy(I->uploaded);
+    I->side.release();
     delete I;
     impl = nullptr;
 }
@@ -1608,6 +1632,9 @@ int encode_init(int device) {
     if (cudaMemcpyToSymbol(c_log10, l10, sizeof(l10)) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(c_log12, l12, sizeof(l12)) != cudaSuccess) return -1;
     cudaFuncSetAttribute(enc_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM);
+    auto carve = [](auto kernel) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); };
+    carve(enc_hist_kernel); carve(enc_fix_kernel); carve(enc_stripe_kernel); carve(enc_transform_kernel);
+    carve(enc_table_kernel); carve(enc_finish_kernel); carve(enc_block_kernel);
     g_grid_enc[0][0] = occ_grid(enc_rans_kernel<4, 0, 16>, SM_O0_4, g_sms_enc);
     g_grid_enc[1][0] = occ_grid(enc_rans_kernel<32, 0, 16>, SM_O0_32, g_sms_enc);
     g_grid_o1_4_s = occ_grid(enc_rans_kernel<4, 1, 16>, SM_O1_4_S, g_sms_enc);
@@ -1740,7 +1767,7 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
 
     // ---- device memory
     const size_t desc_bytes = up(sizeof(EncWork)) + up(sizeof(EncBlock) * blocks.size()) + up(sizeof(EncLeaf) * leaves.size()) +
-                              up(sizeof(EncStream) * streams.size()) + 256;
+                              up(sizeof(EncStream) * streams.size()) + up(4 * 16 * streams.size()) + 256;
     if (I->pending) { ECK(cudaEventSynchronize(I->uploaded)); I->pending = false; }
     if (scratch + 256 > I->scratch_cap) {
         if (I->d_scratch) cudaFree(I->d_scratch);
@@ -1784,10 +1811,17 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     const size_t o_blocks = o; o += up(sizeof(EncBlock) * blocks.size());
     const size_t o_leaves = o; o += up(sizeof(EncLeaf) * leaves.size());
     const size_t o_streams = o; o += up(sizeof(EncStream) * streams.size());
+    const size_t o_vlist = o;                                    // device-only, not uploaded
     hw.blocks = reinterpret_cast<EncBlock*>(I->d_desc + o_blocks);
     hw.leaves = reinterpret_cast<EncLeaf*>(I->d_desc + o_leaves);
     hw.streams = reinterpret_cast<EncStream*>(I->d_desc + o_streams);
+    hw.vlist = reinterpret_cast<uint32_t*>(I->d_desc + o_vlist);
     hw.nblocks = (uint32_t)blocks.size(); hw.nleaves = (uint32_t)leaves.size(); hw.nstreams = (uint32_t)streams.size();
+    // 4-way streams of a batch too large for one wave of the 4 KB-table kernels (48 streams per SM) go to
+    // variants with compacted tables by alphabet size: order 0 with <= 48 symbols (1 KB per stream),
+    // order 1 with <= 9 symbols (1.5 KB)
+    const bool big4 = (streams.size() + 7) / 8 > (size_t)g_grid_enc[0][0];
+    hw.o0_lo = big4 ? 48u : 0u; hw.o1_lo = big4 ? 9u : 0u;
     memcpy(I->h_desc + o_work, &hw, sizeof(hw));
     memcpy(I->h_desc + o_blocks, blocks.data(), sizeof(EncBlock) * blocks.size());
     if (!leaves.empty()) memcpy(I->h_desc + o_leaves, leaves.data(), sizeof(EncLeaf) * leaves.size());
@@ -1813,6 +1847,7 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     if (!streams.empty()) {
         enc_hist_kernel<<<g_sms_enc * 3, HT, HIST_SMEM, st>>>(dW); launches++;
         enc_table_kernel<<<g * 2, KT, 0, st>>>(dW); launches++;
+        enc_bucket_kernel<<<((unsigned)streams.size() + 255) / 256, 256, 0, st>>>(dW); launches++;
         // an order-1 request can fall back to order 0 on the device, so the order-0 kernels always run
         // cursors: next_misc[0..4]; order-1 streams go to the small-alphabet variant (ns <= 16, tables in
         // shared memory at high occupancy) or the large one (ns > 16: shared up to 48 symbols, else global)
@@ -1827,22 +1862,42 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
             return c < cap ? std::max(smem, std::min(232448, (233472 / c - 1024) & ~127)) : smem;
         };
         int grid = 0, sm = 0;
-        // 4-way streams of a batch too large for one wave of the 4 KB-table kernels (48 streams per SM) go to
-        // variants with compacted tables by alphabet size: order 0 with <= 48 symbols (1 KB per stream),
-        // order 1 with <= 9 symbols (1.5 KB); next_misc cursors 7..10
-        const bool big4 = ngroups4 > (uint32_t)(g_grid_enc[0][0]);
-        const uint32_t o0_lo = big4 ? 48u : 0u, o1_lo = big4 ? 9u : 0u;
-        if (any4[0])  { sm = shaped(g_grid_enc[0][0] / g_sms_enc, SM_O0_4, ngroups4, &grid); enc_rans_kernel<4, 0, 16><<<grid, 32, sm, st>>>(dW, 0, o0_lo, 256); launches++;
-                        if (big4) { sm = shaped(g_grid_o0_4_c / g_sms_enc, SM_O0_4_C, ngroups4, &grid); enc_rans_kernel<4, 0, 48><<<grid, 32, sm, st>>>(dW, 7, 0, 48); launches++; } }
-        if (any4[1])  { sm = shaped(g_grid_o1_4_s / g_sms_enc, SM_O1_4_S, ngroups4, &grid); enc_rans_kernel<4, 1, 16><<<grid, 32, sm, st>>>(dW, 1, o1_lo, 256); launches++;
-                        if (big4) { sm = shaped(g_grid_o1_4_t / g_sms_enc, SM_O1_4_T, ngroups4, &grid); enc_rans_kernel<4, 1, 9><<<grid, 32, sm, st>>>(dW, 8, 0, 9); launches++; } }
-        if (any32[0]) { sm = shaped(g_grid_enc[1][0] / g_sms_enc, SM_O0_32, ngroups32, &grid); enc_rans_kernel<32, 0, 16><<<grid, 32, sm, st>>>(dW, 2, 0, 256); launches++; }
-        if (any32[1]) { sm = shaped(g_grid_o1_32_s / g_sms_enc, SM_O1_32_S, ngroups32, &grid); enc_rans_kernel<32, 1, 16><<<grid, 32, sm, st>>>(dW, 3, 0, 16); launches++;
-                        sm = shaped(g_grid_o1_32_l / g_sms_enc, SM_O1_32_L, ngroups32, &grid); enc_rans_kernel<32, 1, 48><<<grid, 32, sm, st>>>(dW, 4, 16, 256); launches++; }
-        if (any8[0])  { sm = shaped(g_grid_enc[0][0] / g_sms_enc, SM_O0_4, ngroups4, &grid); enc_rans_kernel<4, 0, 16, true><<<grid, 32, sm, st>>>(dW, 5, o0_lo, 256); launches++;
-                        if (big4) { sm = shaped(g_grid_o0_8_c / g_sms_enc, SM_O0_4_C, ngroups4, &grid); enc_rans_kernel<4, 0, 48, true><<<grid, 32, sm, st>>>(dW, 9, 0, 48); launches++; } }
-        if (any8[1])  { sm = shaped(g_grid_o1_4_s / g_sms_enc, SM_O1_4_S, ngroups4, &grid); enc_rans_kernel<4, 1, 16, true><<<grid, 32, sm, st>>>(dW, 6, o1_lo, 256); launches++;
-                        if (big4) { sm = shaped(g_grid_o1_8_t / g_sms_enc, SM_O1_4_T, ngroups4, &grid); enc_rans_kernel<4, 1, 9, true><<<grid, 32, sm, st>>>(dW, 10, 0, 9); launches++; } }
+        const uint32_t o0_lo = hw.o0_lo, o1_lo = hw.o1_lo;
+        static const bool side_on = !(getenv("HTSCODECS_B200_SIDE") && atoi(getenv("HTSCODECS_B200_SIDE")) == 0);
+        SideStreams* side = (side_on && I->side.init() == 0) ? &I->side : nullptr;
+        int nside = 0;
+        cudaStream_t ks = st;
+        if (side) cudaEventRecord(side->fork, st);
+#define LAUNCH_ENC(CAP, SMEM, GROUPS, KERNEL, ...)                                             \
+        {                                                                                          \
+            if (side) { ks = side->s[nside]; cudaStreamWaitEvent(ks, side->fork, 0); }             \
+            sm = shaped((CAP) / g_sms_enc, SMEM, GROUPS, &grid);                                   \
+            KERNEL<<<grid, 32, sm, ks>>>(dW, __VA_ARGS__); launches++;                             \
+            if (side) { cudaEventRecord(side->join[nside], ks); nside++; }                         \
+        }
+#define K(...) enc_rans_kernel<__VA_ARGS__>
+        // the long-latency (4-way, order-1) variants first
+        // (alphabets beyond 16 symbols read their tables from global memory at twice the step time: a launch of
+        // their own, cursors 11 / 12, so that no warp mixes the two speeds)
+        if (any4[1]) { LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16), 11, 16, 256)
+                       LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16), 1, o1_lo, 16)
+                       if (big4) LAUNCH_ENC(g_grid_o1_4_t, SM_O1_4_T, ngroups4, K(4, 1, 9), 8, 0, 9) }
+        if (any8[1]) { LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16, true), 12, 16, 256)
+                       LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16, true), 6, o1_lo, 16)
+                       if (big4) LAUNCH_ENC(g_grid_o1_8_t, SM_O1_4_T, ngroups4, K(4, 1, 9, true), 10, 0, 9) }
+        if (any4[0]) { LAUNCH_ENC(g_grid_enc[0][0], SM_O0_4, ngroups4, K(4, 0, 16), 0, o0_lo, 256)
+                       if (big4) LAUNCH_ENC(g_grid_o0_4_c, SM_O0_4_C, ngroups4, K(4, 0, 48), 7, 0, 48) }
+        if (any8[0]) { LAUNCH_ENC(g_grid_enc[0][0], SM_O0_4, ngroups4, K(4, 0, 16, true), 5, o0_lo, 256)
+                       if (big4) LAUNCH_ENC(g_grid_o0_8_c, SM_O0_4_C, ngroups4, K(4, 0, 48, true), 9, 0, 48) }
+        if (any32[1]) { LAUNCH_ENC(g_grid_o1_32_l, SM_O1_32_L, ngroups32, K(32, 1, 48), 4, 16, 256)
+                        LAUNCH_ENC(g_grid_o1_32_s, SM_O1_32_S, ngroups32, K(32, 1, 16), 3, 0, 16) }
+        if (any32[0]) {                                              // the throughput-bound variant stays on the caller's stream
+            sm = shaped(g_grid_enc[1][0] / g_sms_enc, SM_O0_32, ngroups32, &grid);
+            enc_rans_kernel<32, 0, 16><<<grid, 32, sm, st>>>(dW, 2, 0, 256); launches++;
+        }
+#undef K
+#undef LAUNCH_ENC
+        for (int i = 0; i < nside; i++) cudaStreamWaitEvent(st, side->join[i], 0);
         enc_finish_kernel<<<g, 256, 0, st>>>(dW); launches++;
     }
     enc_block_kernel<<<g, 256, 0, st>>>(dW, b.out_len, b.status); launches++;

@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 import htscodecs_b200 as hb
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -62,3 +64,21 @@ def test_product_does_not_touch_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in text.replace("no CPU fallback", ""), os.path.join(dirpath, fn)
+
+
+def test_reference_test_programs_link_against_the_library():
+    """oracle/Makefile `dropin` compiles the reference's own test programs against
+    libhtscodecs_b200.so; every rans_* symbol they import must be one the library defines."""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    for prog in ("rans4x16pr_b200", "rans4x8_b200"):
+        exe = os.path.join(ref, prog)
+        if not os.path.exists(exe):
+            pytest.skip("drop-in programs not built (reference tree absent at build time)")
+        und = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True, check=True).stdout
+        wanted = {ln.split()[-1] for ln in und.splitlines() if " rans_" in ln}
+        assert wanted, prog
+        lib = subprocess.run(["nm", "-D", "--defined-only", hb.LIB_PATH], capture_output=True, text=True,
+                             check=True).stdout
+        have = {ln.split()[-1] for ln in lib.splitlines()}
+        assert wanted <= have, wanted - have
