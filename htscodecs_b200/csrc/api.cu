@@ -66,7 +66,11 @@ struct DecSlot {
     DevBuf<uint32_t> cap_save;  // copy of the caller's capacities, for retries
     PinBuf<DecWork> h_work;     // header as sent / as read back
     uint32_t job_cap = 0, chain_cap = 0, stripe_cap = 0;
-    void release() { work.release(); lists.release(); arena.release(); cap_save.release(); h_work.release(); }
+    // Did the previous batch use more than one entropy kernel kind?  (Read from its header once that has arrived.)
+    // A single-kind batch predicts another one, which is launched on the caller's stream alone -- measured 13 %
+    // faster than from a side stream; -1 = not known yet.
+    cudaEvent_t hdr_ready = nullptr; bool hdr_pending = false; int mixed = -1;
+    void release() { work.release(); lists.release(); arena.release(); cap_save.release(); h_work.release(); if (hdr_ready) cudaEventDestroy(hdr_ready); hdr_ready = nullptr; }
 };
 
 // Staging for the host-resident API: one pipeline stage.
@@ -227,12 +231,23 @@ static int dec_prepare(hts_b200_ctx* ctx, DecSlot& s, int nblk, size_t arena_byt
 // Enqueue one decode attempt on `st` (header upload, kernels, header download into h_work[1]).
 static int dec_enqueue(hts_b200_ctx* ctx, DecSlot& s, const DecodeBatch& b, cudaStream_t st) {
     DecodeBatch bb = b;
+    if (s.hdr_pending && cudaEventQuery(s.hdr_ready) == cudaSuccess) {
+        const DecWork& r = s.h_work.p[1];
+        int used = 0;
+        for (int k = 0; k < JK_NKINDS; k++) used += (k != JK_COPY && k != JK_TAB && r.njobs[k] != 0);
+        s.mixed = used > 1;
+        s.hdr_pending = false;
+    }
+    if (s.mixed == 0) bb.side = nullptr;
     bb.work = reinterpret_cast<DecWork*>(s.work.p);
     s.h_work.p[0].big_batch = b.big_batch ? 1u : 0u;
     bb.hdr = &s.h_work.p[0];
     ctx->launches += decode_launch(bb, st);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&s.h_work.p[1], s.work.p, sizeof(DecWork), cudaMemcpyDeviceToHost, st));
+    if (!s.hdr_ready) CK(cudaEventCreateWithFlags(&s.hdr_ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(s.hdr_ready, st));                        // (a query succeeds only once the LATEST copy has landed)
+    s.hdr_pending = true;
     return 0;
 }
 

@@ -1756,16 +1756,9 @@ static int g_smem[JK_NKINDS];
 static int g_sms = 0;
 constexpr int SM_SMEM = 233472, CTA_RESERVE = 1024, MAX_DYN = 232448;
 
-// Kernels of different kinds (and of different chunks of the host pipeline) share SMs: every kernel asks for the
-// same L1 / shared-memory split, so that an SM never has to drain before it can change it.
-template <typename K> static void max_carveout(K kernel) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
-
 template <typename K>
 static void persistent_setup(uint32_t kind, K kernel, int smem, int threads) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN);
-    max_carveout(kernel);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     g_cap[kind] = per_sm < 1 ? 1 : per_sm;
@@ -1812,8 +1805,6 @@ int decode_init(int device) {
     persistent_setup(JK_O1_4M,  dec_o1_kernel<4, false, 2>,  O1Smem<4, 2>::TOTAL, 32);
     persistent_setup(JK_R8_O1M, dec_o1_kernel<4, true, 2>,   O1Smem<4, 2>::TOTAL, 32);
     persistent_setup(JK_TAB,    dec_o0_kernel<4, false>,  O0Smem<4>::TOTAL, 32);
-    max_carveout(work_init_kernel); max_carveout(plan_kernel); max_carveout(copy_kernel); max_carveout(rle_kernel);
-    max_carveout(unpack_kernel); max_carveout(unstripe_kernel);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
