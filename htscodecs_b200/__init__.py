@@ -27,7 +27,7 @@ EXPORTS = [
     "hts_b200_create", "hts_b200_destroy", "hts_b200_last_error", "hts_b200_launch_count",
     "hts_b200_stream", "hts_b200_uncompress_batch_dev", "hts_b200_uncompress_batch_host",
     "hts_b200_compress_batch_dev", "hts_b200_compress_batch_host", "rans4x16_uncompress_batch",
-    "rans4x16_compress_batch", "hts_b200_peek_size", "hts_b200_host_alloc", "hts_b200_host_free",
+    "rans4x16_compress_batch", "rans4x16_compress_best_batch", "hts_b200_peek_size", "hts_b200_host_alloc", "hts_b200_host_free",
     "hts_b200_set_copy_duplex",
 ]
 
@@ -79,6 +79,7 @@ def load_library():
     lib.hts_b200_compress_batch_host.argtypes = batch
     lib.rans4x16_uncompress_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
     lib.rans4x16_compress_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.rans4x16_compress_best_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp]
     lib.hts_b200_peek_size.argtypes = [vp, u32, C.c_int, _u32p]
     lib.hts_b200_host_alloc.restype = vp
     lib.hts_b200_host_alloc.argtypes = [C.c_size_t]
@@ -331,6 +332,30 @@ class Context:
         res = [bytes(ob[int(out_off[i]): int(out_off[i]) + int(min(out_len[i], caps[i]))]) if status[i] == 0 else None
                for i in range(n)]
         return res, status
+
+    def compress_best_many(self, blocks, methods):
+        """Try-all-methods encode (the selection loop of tokenise_name3.c:1246-1299): every block is
+        coded with every order in `methods` in one batched pass and the first strictly smallest
+        stream is kept.  Returns (streams, best_orders, status)."""
+        n = len(blocks)
+        if n == 0:
+            return [], np.zeros(0, np.int32), np.zeros(0, np.int32)
+        lib = self.lib
+        bufs = [np.frombuffer(bytes(b), np.uint8) if len(b) else np.zeros(1, np.uint8) for b in blocks]
+        in_size = np.array([len(b) for b in blocks], np.uint32)
+        meth = np.array(methods, np.int32)
+        caps = np.array([max(lib.rans_compress_bound_4x16(int(in_size[i]), int(m)) for m in meth) for i in range(n)], np.uint32)
+        outs = [np.zeros(int(c), np.uint8) for c in caps]
+        in_ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        out_ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        out_size = caps.copy()
+        best = np.full(n, -1, np.int32)
+        status = np.zeros(n, np.int32)
+        self._check(lib.rans4x16_compress_best_batch(
+            self.h, n, C.cast(in_ptrs, C.c_void_p), _ptr(in_size), C.cast(out_ptrs, C.c_void_p), _ptr(out_size),
+            _ptr(meth), len(meth), _ptr(best), _ptr(status)))
+        res = [bytes(outs[i][: int(out_size[i])]) if status[i] == 0 else None for i in range(n)]
+        return res, best, status
 
     def compress_many(self, blocks, orders):
         n = len(blocks)

@@ -127,6 +127,11 @@ struct hts_b200_ctx {
     cudaEvent_t all_h2d = nullptr;
     bool full_duplex = true;            // overlap host->device with device->host copies (see hts_b200_set_copy_duplex)
     PinBuf<uint8_t> pin_in, pin_out;    // pointer-array wrappers
+    DevBuf<uint8_t> best_in, best_cand, best_out;   // rans4x16_compress_best_batch: inputs, candidates, winners
+    DevBuf<uint64_t> best_off;          // [in_off | cand_off] per candidate, then [src_off | dst_off] per winner
+    DevBuf<uint32_t> best_u32;          // [in_len | cand_len | status | order] per candidate
+    PinBuf<uint64_t> best_hoff;
+    PinBuf<uint32_t> best_hu32;
     size_t arena_hint = 0;
     unsigned long long launches = 0;
     char err[256] = {0};
@@ -175,6 +180,8 @@ extern "C" void hts_b200_destroy(hts_b200_ctx* ctx) {
     for (auto& st : ctx->stage) st.release();
     if (ctx->all_h2d) cudaEventDestroy(ctx->all_h2d);
     ctx->pin_in.release(); ctx->pin_out.release();
+    ctx->best_in.release(); ctx->best_cand.release(); ctx->best_out.release(); ctx->best_off.release();
+    ctx->best_u32.release(); ctx->best_hoff.release(); ctx->best_hu32.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -577,6 +584,123 @@ extern "C" int rans4x16_compress_batch(hts_b200_ctx* ctx, int nblk, const unsign
                                        unsigned int* out_size, const int* order, int* status) {
     if (!order) return -1;
     return run_ptr_batch(ctx, true, nblk, in, in_size, out, out_size, order, status, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// try-all-methods encode (tokenise_name3.c:1246-1299)
+// ------------------------------------------------------------------------------------------
+// Winner i: len[i] bytes from src + src_off[i] to dst + dst_off[i]; offsets and slot sizes are multiples of 16.
+__global__ void gather_kernel(const uint8_t* src, const uint64_t* src_off, const uint32_t* len, uint8_t* dst,
+                              const uint64_t* dst_off, int n) {
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint4* s = reinterpret_cast<const uint4*>(src + src_off[i]);
+        uint4* d = reinterpret_cast<uint4*>(dst + dst_off[i]);
+        const uint32_t nv = (len[i] + 15) / 16;
+        for (uint32_t t = threadIdx.x; t < nv; t += blockDim.x) d[t] = s[t];
+    }
+}
+
+extern "C" int rans4x16_compress_best_batch(hts_b200_ctx* ctx, int nblk, const unsigned char* const* in,
+                                            const unsigned int* in_size, unsigned char* const* out,
+                                            unsigned int* out_size, const int* methods, int nmethods, int* best,
+                                            int* status) {
+    if (!ctx || nblk < 0 || nmethods <= 0 || !methods || !status) return -1;
+    if (nblk == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t cand_budget = (size_t)1 << 30;                   // candidate bytes per pass
+    int a = 0;
+    while (a < nblk) {
+        // ---- blocks [a, b) of this pass and their candidates
+        size_t in_bytes = 0, cand_bytes = 0, ncand = 0;
+        int b = a;
+        for (; b < nblk; b++) {
+            size_t cb = 0, nc = 0;
+            for (int m = 0; m < nmethods; m++) {
+                if ((methods[m] & RANS_ORDER_STRIPE) && in_size[b] % 4) continue;        // :1269
+                cb += align_up(rans_compress_bound_4x16(in_size[b], methods[m]), 16); nc++;
+            }
+            if (b > a && cand_bytes + cb > cand_budget) break;
+            cand_bytes += cb; ncand += nc; in_bytes += align_up(in_size[b], 16);
+        }
+        const int nb = b - a;
+        if (ctx->pin_in.ensure(in_bytes + 16) || ctx->best_in.ensure(in_bytes + 16) || ctx->best_cand.ensure(cand_bytes + 16) ||
+            ctx->best_off.ensure(2 * ncand + 2 * (size_t)nb + 2) || ctx->best_u32.ensure(4 * ncand + nb + 4) ||
+            ctx->best_hoff.ensure(2 * ncand + 2 * (size_t)nb + 2) || ctx->best_hu32.ensure(4 * ncand + nb + 4)) {
+            snprintf(ctx->err, sizeof(ctx->err), "out of memory for the try-all-methods pass");
+            return -1;
+        }
+        uint64_t* h_in_off = ctx->best_hoff.p; uint64_t* h_c_off = h_in_off + ncand;
+        uint32_t* h_in_len = ctx->best_hu32.p; uint32_t* h_c_len = h_in_len + ncand;
+        uint32_t* h_st = h_c_len + ncand; uint32_t* h_ord = h_st + ncand;
+        size_t io = 0, co = 0, k = 0;
+        for (int i = a; i < b; i++) {
+            if (in_size[i]) memcpy(ctx->pin_in.p + io, in[i], in_size[i]);
+            for (int m = 0; m < nmethods; m++) {
+                if ((methods[m] & RANS_ORDER_STRIPE) && in_size[i] % 4) continue;
+                const uint32_t bound = rans_compress_bound_4x16(in_size[i], methods[m]);
+                h_in_off[k] = io; h_in_len[k] = in_size[i]; h_c_off[k] = co; h_c_len[k] = bound;
+                h_st[k] = 0; h_ord[k] = (uint32_t)methods[m];
+                co += align_up(bound, 16); k++;
+            }
+            io += align_up(in_size[i], 16);
+        }
+        cudaStream_t st = ctx->stream;
+        CK(cudaMemcpyAsync(ctx->best_in.p, ctx->pin_in.p, in_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->best_off.p, ctx->best_hoff.p, 16 * ncand, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->best_u32.p, ctx->best_hu32.p, 16 * ncand, cudaMemcpyHostToDevice, st));
+        uint32_t* d_in_len = ctx->best_u32.p; uint32_t* d_c_len = d_in_len + ncand;
+        uint32_t* d_st = d_c_len + ncand; uint32_t* d_ord = d_st + ncand;
+        // ---- every candidate of every block in one encode batch
+        if (ncand == 0) { for (int i = a; i < b; i++) status[i] = HTS_B200_ERR_INTERNAL; a = b; continue; }
+        EncodeBatch eb;
+        eb.in_base = ctx->best_in.p; eb.in_off = ctx->best_off.p; eb.in_len = d_in_len;
+        eb.out_base = ctx->best_cand.p; eb.out_off = ctx->best_off.p + ncand; eb.out_len = d_c_len;
+        eb.status = reinterpret_cast<int32_t*>(d_st); eb.order = reinterpret_cast<const int32_t*>(d_ord);
+        eb.nblk = (int)ncand;
+        int l = encode_run(ctx->enc, eb, h_in_len, reinterpret_cast<const int32_t*>(h_ord), st, ctx->err, sizeof(ctx->err));
+        if (l < 0) return -1;
+        ctx->launches += l;
+        CK(cudaMemcpyAsync(h_c_len, d_c_len, 8 * ncand, cudaMemcpyDeviceToHost, st));     // lengths + status
+        CK(cudaStreamSynchronize(st));
+        // ---- pick the winners (first strictly smallest, :1280), gather them densely, fetch
+        uint64_t* h_src = ctx->best_hoff.p + 2 * ncand; uint64_t* h_dst = h_src + nb;
+        std::vector<uint32_t> wlen(nb);
+        size_t dense = 0;
+        k = 0;
+        for (int i = a; i < b; i++) {
+            uint64_t best_sz = UINT64_MAX; int bm = -1; size_t bk = 0; int fail = 0;
+            for (int m = 0; m < nmethods; m++) {
+                if ((methods[m] & RANS_ORDER_STRIPE) && in_size[i] % 4) continue;
+                if ((int32_t)h_st[k] != 0) fail = (int32_t)h_st[k];                      // :1273 any failure fails the column
+                else if (h_c_len[k] < best_sz) { best_sz = h_c_len[k]; bm = m; bk = k; }
+                k++;
+            }
+            const int j = i - a;
+            if (fail || bm < 0) { status[i] = fail ? fail : HTS_B200_ERR_INTERNAL; wlen[j] = 0; h_src[j] = 0; h_dst[j] = dense; continue; }
+            if (best_sz > out_size[i]) { status[i] = HTS_B200_ERR_SIZE; wlen[j] = 0; h_src[j] = 0; h_dst[j] = dense; continue; }
+            status[i] = HTS_B200_OK;
+            if (best) best[i] = methods[bm];
+            out_size[i] = (unsigned int)best_sz;
+            wlen[j] = (uint32_t)best_sz; h_src[j] = h_c_off[bk]; h_dst[j] = dense;
+            dense += align_up(best_sz, 16);
+        }
+        if (dense) {
+            if (ctx->best_out.ensure(dense + 16) || ctx->pin_out.ensure(dense + 16)) { snprintf(ctx->err, sizeof(ctx->err), "out of memory for the winners"); return -1; }
+            uint32_t* h_wlen = ctx->best_hu32.p;                     // (candidate arrays are no longer needed)
+            memcpy(h_wlen, wlen.data(), 4 * (size_t)nb);
+            CK(cudaMemcpyAsync(ctx->best_off.p + 2 * ncand, h_src, 16 * (size_t)nb, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->best_u32.p, h_wlen, 4 * (size_t)nb, cudaMemcpyHostToDevice, st));
+            gather_kernel<<<std::min(nb, 148 * 8), 256, 0, st>>>(ctx->best_cand.p, ctx->best_off.p + 2 * ncand, ctx->best_u32.p,
+                                                                ctx->best_out.p, ctx->best_off.p + 2 * ncand + nb, nb);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(ctx->pin_out.p, ctx->best_out.p, dense, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (int j = 0; j < nb; j++) if (wlen[j]) memcpy(out[a + j], ctx->pin_out.p + h_dst[j], wlen[j]);
+        }
+        a = b;
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------

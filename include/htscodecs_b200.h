@@ -152,6 +152,20 @@ int rans4x16_compress_batch(hts_b200_ctx *ctx, int nblk,
                             unsigned char *const *out, unsigned int *out_size,
                             const int *order, int *status);
 
+/*
+ * Try-all-methods encode: the selection loop of the reference's name-tokeniser back end
+ * (tokenise_name3.c:1246-1299 `compress()`, whose level table :1254-1260 lists up to nine orders per
+ * byte column).  Block i is coded with every order in methods[0 .. nmethods) in ONE batched device
+ * pass -- orders carrying X_STRIPE are skipped for sizes that are not a multiple of 4 (:1269) -- and
+ * the first strictly smallest stream wins (:1280): it is written to out[i], its order to best[i]
+ * (may be NULL).  out_size[i]: capacity on entry (>= the largest rans_compress_bound_4x16(in_size[i], m)
+ * over the methods), stream length on return.  Only the winners leave the device.
+ */
+int rans4x16_compress_best_batch(hts_b200_ctx *ctx, int nblk,
+                                 const unsigned char *const *in, const unsigned int *in_size,
+                                 unsigned char *const *out, unsigned int *out_size,
+                                 const int *methods, int nmethods, int *best, int *status);
+
 /* Stored uncompressed size of a 4x16 (method 0) or 4x8 (method 1) stream held in HOST memory;
  * returns 0 and sets *ulen, or -1 (X_NOSZ stream / truncated header). */
 int hts_b200_peek_size(const uint8_t *in, uint32_t in_len, int method, uint32_t *ulen);
