@@ -1191,7 +1191,7 @@ __global__ void enc_bucket_kernel(EncWork* W) {
 // kernel variants (NSCAP 16: 4 KB per group, many resident warps; NSCAP 48: 36 KB) split the
 // streams between them by alphabet size, larger alphabets read the table from global memory.
 template <int NWAY, int ORDER, int NSCAP, bool BYTE = false>
-__global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t cursor_id, uint32_t ns_lo, uint32_t ns_hi) {
+__global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t cursor_id) {
     using EG = EGrp<NWAY>;
     extern __shared__ __align__(16) uint8_t esm[];
     const EG G;
@@ -1882,7 +1882,6 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
             return c < cap ? std::max(smem, std::min(232448, (233472 / c - 1024) & ~127)) : smem;
         };
         int grid = 0, sm = 0;
-        const uint32_t o0_lo = hw.o0_lo, o1_lo = hw.o1_lo;
         static const bool side_on = !(getenv("HTSCODECS_B200_SIDE") && atoi(getenv("HTSCODECS_B200_SIDE")) == 0);
         if (I->vc_pending && cudaEventQuery(I->vc_ready) == cudaSuccess) {
             int used = 0;
@@ -1894,32 +1893,33 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
         int nside = 0;
         cudaStream_t ks = st;
         if (side) cudaEventRecord(side->fork, st);
-#define LAUNCH_ENC(CAP, SMEM, GROUPS, KERNEL, ...)                                             \
+#define LAUNCH_ENC(CAP, SMEM, GROUPS, KERNEL, CURSOR)                                            \
         {                                                                                          \
             if (side) { ks = side->s[nside]; cudaStreamWaitEvent(ks, side->fork, 0); }             \
             sm = shaped((CAP) / g_sms_enc, SMEM, GROUPS, &grid);                                   \
-            KERNEL<<<grid, 32, sm, ks>>>(dW, __VA_ARGS__); launches++;                             \
+            KERNEL<<<grid, 32, sm, ks>>>(dW, CURSOR); launches++;                                  \
             if (side) { cudaEventRecord(side->join[nside], ks); nside++; }                         \
         }
 #define K(...) enc_rans_kernel<__VA_ARGS__>
         // the long-latency (4-way, order-1) variants first
         // (alphabets beyond 16 symbols read their tables from global memory at twice the step time: a launch of
         // their own, cursors 11 / 12, so that no warp mixes the two speeds)
-        if (any4[1]) { LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16), 11, 16, 256)
-                       LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16), 1, o1_lo, 16)
-                       if (big4) LAUNCH_ENC(g_grid_o1_4_t, SM_O1_4_T, ngroups4, K(4, 1, 9), 8, 0, 9) }
-        if (any8[1]) { LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16, true), 12, 16, 256)
-                       LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16, true), 6, o1_lo, 16)
-                       if (big4) LAUNCH_ENC(g_grid_o1_8_t, SM_O1_4_T, ngroups4, K(4, 1, 9, true), 10, 0, 9) }
-        if (any4[0]) { LAUNCH_ENC(g_grid_enc[0][0], SM_O0_4, ngroups4, K(4, 0, 16), 0, o0_lo, 256)
-                       if (big4) LAUNCH_ENC(g_grid_o0_4_c, SM_O0_4_C, ngroups4, K(4, 0, 48), 7, 0, 48) }
-        if (any8[0]) { LAUNCH_ENC(g_grid_enc[0][0], SM_O0_4, ngroups4, K(4, 0, 16, true), 5, o0_lo, 256)
-                       if (big4) LAUNCH_ENC(g_grid_o0_8_c, SM_O0_4_C, ngroups4, K(4, 0, 48, true), 9, 0, 48) }
-        if (any32[1]) { LAUNCH_ENC(g_grid_o1_32_l, SM_O1_32_L, ngroups32, K(32, 1, 48), 4, 16, 256)
-                        LAUNCH_ENC(g_grid_o1_32_s, SM_O1_32_S, ngroups32, K(32, 1, 16), 3, 0, 16) }
+        // variant (cursor): alphabet class, as bucketed by enc_bucket_kernel
+        if (any4[1]) { LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16), 11)                     // > 16 symbols
+                       LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16), 1)                      // <= 16
+                       if (big4) LAUNCH_ENC(g_grid_o1_4_t, SM_O1_4_T, ngroups4, K(4, 1, 9), 8) }           // <= 9, large batch
+        if (any8[1]) { LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16, true), 12)
+                       LAUNCH_ENC(g_grid_o1_4_s, SM_O1_4_S, ngroups4, K(4, 1, 16, true), 6)
+                       if (big4) LAUNCH_ENC(g_grid_o1_8_t, SM_O1_4_T, ngroups4, K(4, 1, 9, true), 10) }
+        if (any4[0]) { LAUNCH_ENC(g_grid_enc[0][0], SM_O0_4, ngroups4, K(4, 0, 16), 0)
+                       if (big4) LAUNCH_ENC(g_grid_o0_4_c, SM_O0_4_C, ngroups4, K(4, 0, 48), 7) }          // <= 48, large batch
+        if (any8[0]) { LAUNCH_ENC(g_grid_enc[0][0], SM_O0_4, ngroups4, K(4, 0, 16, true), 5)
+                       if (big4) LAUNCH_ENC(g_grid_o0_8_c, SM_O0_4_C, ngroups4, K(4, 0, 48, true), 9) }
+        if (any32[1]) { LAUNCH_ENC(g_grid_o1_32_l, SM_O1_32_L, ngroups32, K(32, 1, 48), 4)                 // > 16 symbols
+                        LAUNCH_ENC(g_grid_o1_32_s, SM_O1_32_S, ngroups32, K(32, 1, 16), 3) }
         if (any32[0]) {                                              // the throughput-bound variant stays on the caller's stream
             sm = shaped(g_grid_enc[1][0] / g_sms_enc, SM_O0_32, ngroups32, &grid);
-            enc_rans_kernel<32, 0, 16><<<grid, 32, sm, st>>>(dW, 2, 0, 256); launches++;
+            enc_rans_kernel<32, 0, 16><<<grid, 32, sm, st>>>(dW, 2); launches++;
         }
 #undef K
 #undef LAUNCH_ENC
