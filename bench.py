@@ -35,6 +35,24 @@ UNIT = "GB/s"
 BLOCK = 1 << 20
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout, but libraries print there too (NCCL's version banner on the
+    first collective): point fd 1 at stderr for the run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -144,7 +162,7 @@ def run_reference(args, rank, world):
         vals.append(v)
     total = time.perf_counter() - t0
     v = float(np.mean(vals))
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
@@ -450,7 +468,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         cpu_v, cpu_sample, cpu_kind = cpu_reference_decode(blocks, args.cpu_seconds, os.cpu_count() or 1)
 
-    print(json.dumps({
+    emit(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/u32", "data": "synthetic",
@@ -482,6 +500,7 @@ def run_ours(args, rank, world, local_rank):
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
