@@ -1168,23 +1168,41 @@ struct ByteSrc {
     }
 };
 
-// One thread per stream: which enc_rans_kernel variant codes it (the cursor indices of encode_run).
-__global__ void enc_bucket_kernel(EncWork* W) {
-    const uint32_t si = blockIdx.x * blockDim.x + threadIdx.x;
-    if (si >= W->nstreams) return;
-    const EncStream& S = W->streams[si];
-    if (S.n == 0 || S.size == 0xffffffffu) return;
+// Which enc_rans_kernel variant codes a stream (the cursor indices of encode_run); 0xff: nothing to code.
+__device__ __forceinline__ uint32_t enc_variant(const EncWork* W, const EncStream& S) {
+    if (S.n == 0 || S.size == 0xffffffffu) return 0xffu;
     const bool x32 = S.nway == 32, legacy = S.codec != 0;
-    uint32_t v;
     if (S.order_eff == 0) {
-        if (x32) v = 2;
-        else if (S.ns <= W->o0_lo) v = legacy ? 9 : 7;
-        else v = legacy ? 5 : 0;
-    } else if (x32) v = S.ns <= 16 ? 3 : 4;
-    else if (S.ns <= W->o1_lo) v = legacy ? 10 : 8;
-    else if (S.ns <= 16) v = legacy ? 6 : 1;
-    else v = legacy ? 12 : 11;
-    W->vlist[(size_t)v * W->nstreams + atomicAdd(&W->vcount[v], 1u)] = si;
+        if (x32) return 2;
+        if (S.ns <= W->o0_lo) return legacy ? 9 : 7;
+        return legacy ? 5 : 0;
+    }
+    if (x32) return S.ns <= 16 ? 3 : 4;
+    if (S.ns <= W->o1_lo) return legacy ? 10 : 8;
+    if (S.ns <= 16) return legacy ? 6 : 1;
+    return legacy ? 12 : 11;
+}
+
+// One CTA per variant: a stable partition of the stream list, so every variant codes its streams in batch order.
+__global__ void __launch_bounds__(256) enc_bucket_kernel(EncWork* W) {
+    const uint32_t v = blockIdx.x, w = threadIdx.x >> 5, l = threadIdx.x & 31, nstreams = W->nstreams;
+    __shared__ uint32_t s_warp[8], s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (uint32_t s0 = 0; s0 < nstreams; s0 += 256) {
+        const uint32_t si = s0 + threadIdx.x;
+        const bool mine = si < nstreams && enc_variant(W, W->streams[si]) == v;
+        const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+        if (l == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        uint32_t off = s_base;
+        for (uint32_t k = 0; k < w; k++) off += s_warp[k];
+        if (mine) W->vlist[(size_t)v * nstreams + off + __popc(bal & ((1u << l) - 1u))] = si;
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t t = 0; for (int k = 0; k < 8; k++) t += s_warp[k]; s_base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) W->vcount[v] = s_base;
 }
 
 // Order-1 symbol tables live in shared memory when the alphabet has at most NSCAP symbols; two
@@ -1867,7 +1885,7 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     if (!streams.empty()) {
         enc_hist_kernel<<<g_sms_enc * 3, HT, HIST_SMEM, st>>>(dW); launches++;
         enc_table_kernel<<<g * 2, KT, 0, st>>>(dW); launches++;
-        enc_bucket_kernel<<<((unsigned)streams.size() + 255) / 256, 256, 0, st>>>(dW); launches++;
+        enc_bucket_kernel<<<16, 256, 0, st>>>(dW); launches++;
         // an order-1 request can fall back to order 0 on the device, so the order-0 kernels always run
         // cursors: next_misc[0..4]; order-1 streams go to the small-alphabet variant (ns <= 16, tables in
         // shared memory at high occupancy) or the large one (ns > 16: shared up to 48 symbols, else global)
