@@ -304,9 +304,7 @@ __device__ __forceinline__ bool reserve_chains(DecWork* W, uint32_t n, uint32_t*
     return true;
 }
 
-__global__ void plan_kernel(PlanArgs A) {
-    int blk = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blk >= A.nblk) return;
+__device__ void plan_block(const PlanArgs& A, int blk) {
     DecWork* W = A.W;
     const uint8_t* in = A.in_base + A.in_off[blk];
     uint32_t in_len = A.in_len[blk];
@@ -404,6 +402,10 @@ __global__ void plan_kernel(PlanArgs A) {
         else st = plan_chain(W, in, in_len, out, cap, 0xffffffffu, blk, &A.out_len[blk], ci);
     }
     A.status[blk] = st;
+}
+
+__global__ void plan_kernel(PlanArgs A) {
+    for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < A.nblk; blk += gridDim.x * blockDim.x) plan_block(A, blk);
 }
 
 // ------------------------------------------------------------------------------------------
