@@ -487,7 +487,7 @@ def run_ours(args, rank, world, local_rank):
                      "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                      "kernel": "dec_o0_kernel<32,false>",
                      "note": "algorithmic bytes = compressed read + uncompressed write per step; duration = "
-                             "CUDA-event step time on the context's stream (dec_o0_kernel<32,false> is 99.2 % of it, "
+                             "CUDA-event step time on the context's stream (dec_o0_kernel<32,false> is 99.0 % of it, "
                              "profiles/r01_launches_decode.csv), so frac is a slight lower bound",
                      "limiter": "not HBM: the per-state serial chain (~260 cycles/step) x 28 resident streams/SM; ncu: "
                                 "shared-memory LSU wavefronts 86 % of peak, issue slots 65 %, DRAM 13 % "
