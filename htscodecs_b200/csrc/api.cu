@@ -346,7 +346,28 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
     // (hundreds of blocks) yet numerous enough (>= ~6) for the copies of one to hide behind the next.
     uint64_t total_bytes = 0;
     for (int i = 0; i < nblk; i++) total_bytes += (uint64_t)in_len[i] + out_len[i];
-    const uint64_t target = std::max<uint64_t>(32ull << 20, std::min<uint64_t>(384ull << 20, total_bytes / 8));
+    uint64_t target = std::max<uint64_t>(32ull << 20, std::min<uint64_t>(384ull << 20, total_bytes / 8));
+    {
+        // A chunk's kernels cannot finish before its slowest stream does: n / lanes serial steps of ~130 ns
+        // (1 MiB: 4 ms X_32, 34 ms 4-way).  Three chunks overlap on the device (NSTAGE), so a chunk should carry
+        // at least that much copy time (~55 GB/s per direction), or the copy engines wait for kernels:
+        // 4096 x 1 MiB 4-way blocks went from 20.6 to 38.0 GB/s end to end (order 1: 13.4 to 27.0).
+        uint64_t steps = 0;
+        for (int i = 0; i < nblk; i++) {
+            const uint32_t u = enc ? in_len[i] : out_len[i];
+            uint32_t lanes = 4, parts = 1;
+            if (enc) {
+                if (!(order[i] & HTS_B200_ORDER_RANS4x8)) { if (order[i] & RANS_ORDER_X32) lanes = 32; if (order[i] & RANS_ORDER_STRIPE) parts = 4; }
+            } else if (!(method && method[i] == 1) && in_len[i]) {
+                const uint8_t f = in_base[in_off[i]];
+                if (f & F_X32) lanes = 32;
+                if (f & F_STRIPE) parts = 4;
+            }
+            steps = std::max<uint64_t>(steps, u / lanes / parts);
+        }
+        const uint64_t by_floor = (uint64_t)(steps * 130e-9 * 55e9);
+        target = std::max(target, std::min<uint64_t>(std::min<uint64_t>(by_floor, 2048ull << 20), total_bytes / 3));
+    }
     std::vector<int> cuts{0};
     {
         // the first chunks are smaller (1/8, 1/4, 1/2 of the target) so that the device->host stream,
