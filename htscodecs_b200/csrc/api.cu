@@ -90,6 +90,7 @@ struct Stage {
                                         // last as long as its slowest block; chunks must overlap on the SMs
     // what the device->host half of a chunk needs (it may be enqueued later than the first half)
     int c_a = 0, c_n = 0; bool c_dense = false; uint64_t c_lo = 0, c_bytes = 0;
+    uint64_t c_w = 0;           // encode: leading bytes of every block already fetched (0 = whole regions)
     int init() {
         if (s_compute) return 0;
         if (cudaEventCreateWithFlags(&h2d_done, cudaEventDisableTiming) != cudaSuccess ||
@@ -133,6 +134,7 @@ struct hts_b200_ctx {
     PinBuf<uint64_t> best_hoff;
     PinBuf<uint32_t> best_hu32;
     size_t arena_hint = 0;
+    double enc_frac = 0;                // encode: largest stream / capacity ratio seen lately (0 = none yet), see launch_out
     unsigned long long launches = 0;
     char err[256] = {0};
 };
@@ -391,7 +393,20 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
         const uint64_t* h_out_off = S.h_off.p + n;
         CK(cudaStreamWaitEvent(ctx->s_out, S.compute_done, 0));
         CK(cudaMemcpyAsync(S.h_u32.p + n, S.d_u32.p + n, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->s_out));   // out_len + status
-        if (S.c_dense) CK(cudaMemcpyAsync(out_base + S.c_lo, S.d_out.p, S.c_bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+        // Encode: a block's region is its capacity (~1.05 x the input) but its stream a fraction of that.  With equal,
+        // evenly spaced regions ONE strided copy fetches the leading W bytes of every block, W from the ratios the
+        // previous chunks ended with; a stream that turns out longer gets its tail in collect_chunk.
+        S.c_w = 0;
+        if (enc && S.c_dense && ctx->enc_frac > 0 && n > 1) {
+            const uint64_t stride = out_off[a + 1] - out_off[a];
+            bool regular = true;
+            for (int i = 1; i < n && regular; i++) regular = out_off[a + i] - out_off[a + i - 1] == stride && caps[a + i] == caps[a];
+            const uint64_t w = std::min<uint64_t>(caps[a], align_up((uint64_t)(caps[a] * std::min(1.0, ctx->enc_frac * 1.15 + 0.02)), 256));
+            if (regular && w < caps[a] && stride >= w) S.c_w = w;
+        }
+        if (S.c_w) CK(cudaMemcpy2DAsync(out_base + S.c_lo, out_off[a + 1] - out_off[a], S.d_out.p, out_off[a + 1] - out_off[a], S.c_w, n,
+                                        cudaMemcpyDeviceToHost, ctx->s_out));
+        else if (S.c_dense) CK(cudaMemcpyAsync(out_base + S.c_lo, S.d_out.p, S.c_bytes, cudaMemcpyDeviceToHost, ctx->s_out));
         else for (int i = 0; i < n; i++)
             CK(cudaMemcpyAsync(out_base + out_off[a + i], S.d_out.p + h_out_off[i], caps[a + i], cudaMemcpyDeviceToHost, ctx->s_out));
         CK(cudaEventRecord(S.d2h_done, ctx->s_out));
@@ -482,6 +497,24 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
             else ctx->arena_hint = std::max(ctx->arena_hint, (size_t)S.dec.h_work.p[1].arena_used);
         }
         if (retry) { redo.push_back(k); return 0; }
+        if (enc) {
+            const uint32_t* len = S.h_u32.p + n;
+            const int32_t* stt = reinterpret_cast<const int32_t*>(S.h_u32.p + 2 * (size_t)n);
+            const uint64_t* h_out_off = S.h_off.p + n;
+            double frac = 0;
+            bool tails = false;
+            for (int i = 0; i < n; i++) {
+                if (stt[i] != 0 || !caps[a + i]) continue;
+                frac = std::max(frac, (double)len[i] / caps[a + i]);
+                if (S.c_w && len[i] > S.c_w) {                       // longer than predicted: fetch the rest now
+                    CK(cudaMemcpyAsync(out_base + out_off[a + i] + S.c_w, S.d_out.p + h_out_off[i] + S.c_w, len[i] - S.c_w,
+                                       cudaMemcpyDeviceToHost, ctx->s_out));
+                    tails = true;
+                }
+            }
+            if (tails) CK(cudaStreamSynchronize(ctx->s_out));
+            ctx->enc_frac = ctx->enc_frac > 0 ? std::max(frac, 0.5 * (ctx->enc_frac + frac)) : frac;
+        }
         memcpy(out_len + a, S.h_u32.p + n, 4 * (size_t)n);
         memcpy(status + a, S.h_u32.p + 2 * (size_t)n, 4 * (size_t)n);
         return 0;

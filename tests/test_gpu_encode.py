@@ -188,3 +188,22 @@ def test_large_batch_encode_variants(ctx, oracle):
     for k in list(range(0, 3 * len(uniq))) + list(range(n - 2 * len(uniq), n)):
         got = bytes(ob[int(out_off[k]): int(out_off[k]) + int(ol[k])])
         assert got == want[k % len(uniq)], (k, cases[k % len(uniq)])
+
+
+def test_host_encode_fetches_predicted_lengths_then_tails(oracle):
+    """The host-buffer encoder fetches the leading W bytes of every (equal, evenly spaced) output region in one
+    strided copy, W predicted from the previous chunks' stream / capacity ratios; a stream that comes out longer
+    than predicted gets its tail afterwards.  First call: compressible blocks set a small W; second call on the
+    same context: every other block is incompressible."""
+    ctx = hb.Context(0)
+    n = 1 << 16
+    easy = [synth.tag_block(i, n).tobytes() for i in range(48)]
+    got, st = ctx.compress_many(easy, [0] * len(easy))
+    assert (st == 0).all() and all(g == oracle.compress(d, 0) for g, d in zip(got, easy))
+    hard = [(synth.random_block(i, n) if i & 1 else synth.tag_block(100 + i, n)).tobytes() for i in range(48)]
+    for order in (0, 4, 1):
+        got, st = ctx.compress_many(hard, [order] * len(hard))
+        assert (st == 0).all()
+        for g, d in zip(got, hard):
+            assert g == oracle.compress(d, order), order
+    ctx.close()
