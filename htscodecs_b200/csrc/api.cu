@@ -250,6 +250,7 @@ static int dec_enqueue(hts_b200_ctx* ctx, DecSlot& s, const DecodeBatch& b, cuda
     if (s.mixed == 0) bb.side = nullptr;
     bb.work = reinterpret_cast<DecWork*>(s.work.p);
     s.h_work.p[0].big_batch = b.big_batch ? 1u : 0u;
+    s.h_work.p[0].kinds = b.kinds;
     bb.hdr = &s.h_work.p[0];
     ctx->launches += decode_launch(bb, st);
     CK(cudaGetLastError());

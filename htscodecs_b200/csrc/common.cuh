@@ -83,6 +83,7 @@ struct DecWork {
     // capacities and pointers (host-written)
     uint32_t job_cap, chain_cap, stripe_cap;
     uint32_t big_batch;                // host hint: more 4-way streams than the LUT kernels hold in one wave
+    uint32_t kinds;                    // job kinds whose kernels this batch launches: a job of any other kind is refused
     unsigned long long arena_cap;
     DecJob* jobs[JK_NKINDS];
     Chain* chains;

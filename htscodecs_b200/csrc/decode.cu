@@ -35,6 +35,9 @@ __device__ __forceinline__ uint8_t* arena_alloc(DecWork* W, uint64_t bytes) {
 }
 
 __device__ __forceinline__ bool push_job(DecWork* W, uint32_t kind, const DecJob& j) {
+    // the host launches only the kinds its hint names: a job outside the hint would never run, so its block fails
+    // (status ST_ARENA without the overflow flag: no retry) rather than report success over unwritten output
+    if (!((W->kinds >> kind) & 1u)) return false;
     uint32_t at = atomicAdd(&W->njobs[kind], 1u);
     if (at >= W->job_cap) { W->overflow = 1; return false; }
     W->jobs[kind][at] = j;
