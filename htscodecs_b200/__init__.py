@@ -28,7 +28,7 @@ EXPORTS = [
     "hts_b200_stream", "hts_b200_uncompress_batch_dev", "hts_b200_uncompress_batch_host",
     "hts_b200_compress_batch_dev", "hts_b200_compress_batch_host", "rans4x16_uncompress_batch",
     "rans4x16_compress_batch", "rans4x16_compress_best_batch", "hts_b200_peek_size", "hts_b200_host_alloc", "hts_b200_host_free",
-    "hts_b200_set_copy_duplex",
+    "hts_b200_set_copy_duplex", "hts_b200_plan_chunks",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def load_library():
     lib.hts_b200_host_alloc.argtypes = [C.c_size_t]
     lib.hts_b200_host_free.argtypes = [vp]
     lib.hts_b200_set_copy_duplex.argtypes = [vp, C.c_int]
+    lib.hts_b200_plan_chunks.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int]
     _libc = C.CDLL(None)
     _libc.free.argtypes = [vp]
     lib._free = _libc.free

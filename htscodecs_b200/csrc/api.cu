@@ -337,13 +337,11 @@ Range span_of(const uint64_t* off, const uint32_t* len, int a, int b) {
 
 }  // namespace
 
-// One direction-agnostic driver: `enc` selects compress (order != NULL) or uncompress.
-static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* in_base, const uint64_t* in_off,
-                          const uint32_t* in_len, uint8_t* out_base, const uint64_t* out_off, uint32_t* out_len,
-                          int32_t* status, const uint8_t* method, const int32_t* order) {
-    if (!ctx || nblk < 0) return -1;
-    if (nblk == 0) return 0;
-    CK(cudaSetDevice(ctx->device));
+// Chunk boundaries of a host-buffer call: blocks [cuts[k], cuts[k+1]) travel and run together.  Pure host logic
+// (exported as hts_b200_plan_chunks for the CPU tests).
+static std::vector<int> plan_chunks(bool enc, int nblk, const uint8_t* in_base, const uint64_t* in_off,
+                                    const uint32_t* in_len, const uint32_t* out_len, const uint8_t* method,
+                                    const int32_t* order) {
     // ---- chunking.  The entropy kernels give one warp (or 4 lanes) to a block, so a chunk's kernel time is
     // its slowest block's time however few blocks it holds: chunks must be big enough to fill the SMs
     // (hundreds of blocks) yet numerous enough (>= ~6) for the copies of one to hide behind the next.
@@ -383,8 +381,21 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
             if (acc && acc + w > lim) { cuts.push_back(i); acc = 0; if (ramp) ramp--; }
             acc += w;
         }
+        // a small remainder would still cost a whole kernel round (its slowest stream): it joins the previous chunk
+        if (cuts.size() > 1 && acc < target / 4) cuts.pop_back();
         cuts.push_back(nblk);
     }
+    return cuts;
+}
+
+// One direction-agnostic driver: `enc` selects compress (order != NULL) or uncompress.
+static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* in_base, const uint64_t* in_off,
+                          const uint32_t* in_len, uint8_t* out_base, const uint64_t* out_off, uint32_t* out_len,
+                          int32_t* status, const uint8_t* method, const int32_t* order) {
+    if (!ctx || nblk < 0) return -1;
+    if (nblk == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const std::vector<int> cuts = plan_chunks(enc, nblk, in_base, in_off, in_len, out_len, method, order);
     const int nchunk = (int)cuts.size() - 1;
     std::vector<int> redo;
     std::vector<uint32_t> caps(out_len, out_len + nblk);           // capacities, for retries
@@ -566,6 +577,15 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
     }
     if (!redo.empty()) { snprintf(ctx->err, sizeof(ctx->err), "work area kept overflowing"); return -1; }
     return 0;
+}
+
+extern "C" int hts_b200_plan_chunks(int enc, int nblk, const uint8_t* in_base, const uint64_t* in_off,
+                                    const uint32_t* in_len, const uint32_t* out_len, const uint8_t* method,
+                                    const int32_t* order, int* cuts, int max_cuts) {
+    if (nblk <= 0 || (enc && !order) || (!enc && !in_base)) return -1;
+    const std::vector<int> c = plan_chunks(enc != 0, nblk, in_base, in_off, in_len, out_len, method, order);
+    for (size_t k = 0; k < c.size() && (int)k < max_cuts; k++) cuts[k] = c[k];
+    return (int)c.size();
 }
 
 extern "C" int hts_b200_uncompress_batch_host(hts_b200_ctx* ctx, int nblk, const uint8_t* in_base,

@@ -176,6 +176,13 @@ int hts_b200_peek_size(const uint8_t *in, uint32_t in_len, int method, uint32_t 
  * HTSCODECS_B200_COPY_DUPLEX=half|full sets the initial value. */
 void hts_b200_set_copy_duplex(hts_b200_ctx *ctx, int full);
 
+/* Diagnostics: the chunk boundaries hts_b200_{un,}compress_batch_host would use for this batch (same arguments,
+ * HOST pointers; no device work).  Writes up to max_cuts boundaries -- blocks [cuts[k], cuts[k+1]) form chunk k --
+ * and returns how many there are (chunks + 1), or -1. */
+int hts_b200_plan_chunks(int enc, int nblk, const uint8_t *in_base, const uint64_t *in_off,
+                         const uint32_t *in_len, const uint32_t *out_len, const uint8_t *method,
+                         const int32_t *order, int *cuts, int max_cuts);
+
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA runtime. */
 void *hts_b200_host_alloc(size_t bytes);
 void hts_b200_host_free(void *p);
