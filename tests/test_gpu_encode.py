@@ -207,3 +207,22 @@ def test_host_encode_fetches_predicted_lengths_then_tails(oracle):
         for g, d in zip(got, hard):
             assert g == oracle.compress(d, order), order
     ctx.close()
+
+
+def test_x32_pins_on_gpu():
+    """The GPU encoder against the committed X_32 pins (tests/golden/x32_pins.json) -- no CPU library involved --
+    and the GPU decoder on the same streams."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "x32_pins.json")) as f:
+        pins = json.load(f)
+    ctx = hb.Context(0)
+    blocks = [synth.GENERATORS[p["gen"]](p["block"], p["n"]).tobytes() for p in pins]
+    got, st = ctx.compress_many(blocks, [p["flags"] for p in pins])
+    assert (st == 0).all()
+    for p, c in zip(pins, got):
+        assert len(c) == p["clen"] and hashlib.md5(c).hexdigest() == p["out_md5"], (p["gen"], p["n"], hex(p["flags"]))
+    out, st = ctx.uncompress_many(got, [len(b) for b in blocks])
+    assert (st == 0).all() and out == blocks
+    ctx.close()

@@ -174,3 +174,18 @@ def test_4x8_encode_differential_vs_reference(oracle, reflib):
         for order in (0, 1):
             assert oracle.compress_4x8(data, order) == reflib.compress_4x8(data, order), (name, order)
     assert oracle.compress_4x8(b"", 0) is None
+
+
+def test_x32_pins(oracle):
+    """X_32 regression pins (tests/golden/x32_pins.json, made by make_x32_pins.py from THIS oracle: the
+    reference has no X_32, so they freeze our definition rather than prove parity)."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "x32_pins.json")) as f:
+        pins = json.load(f)
+    assert len(pins) >= 90
+    for p in pins:
+        data = synth.GENERATORS[p["gen"]](p["block"], p["n"]).tobytes()
+        assert hashlib.md5(data).hexdigest() == p["in_md5"], "generator drifted"
+        c = oracle.compress(data, p["flags"])
+        assert len(c) == p["clen"] and hashlib.md5(c).hexdigest() == p["out_md5"], (p["gen"], p["n"], hex(p["flags"]))
+        assert c[:24].hex() == p["head"]
