@@ -29,6 +29,9 @@ EXPORTS = [
     "hts_b200_compress_batch_dev", "hts_b200_compress_batch_host", "rans4x16_uncompress_batch",
     "rans4x16_compress_batch", "rans4x16_compress_best_batch", "hts_b200_peek_size", "hts_b200_host_alloc", "hts_b200_host_free",
     "hts_b200_set_copy_duplex", "hts_b200_plan_chunks",
+    "hts_b200_uncompress_batch_host_multi", "hts_b200_compress_batch_host_multi", "hts_b200_multi_set_phased",
+    "hts_b200_multi_last_stats", "hts_b200_multi_launch_count", "hts_b200_multi_last_error", "hts_b200_partition",
+    "hts_b200_frames_scan", "hts_b200_frames_write",
 ]
 
 _lib = None
@@ -86,6 +89,18 @@ def load_library():
     lib.hts_b200_host_free.argtypes = [vp]
     lib.hts_b200_set_copy_duplex.argtypes = [vp, C.c_int]
     lib.hts_b200_plan_chunks.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+    multi = [C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.hts_b200_uncompress_batch_host_multi.argtypes = multi
+    lib.hts_b200_compress_batch_host_multi.argtypes = multi
+    lib.hts_b200_multi_set_phased.argtypes = [C.c_int]
+    lib.hts_b200_multi_last_stats.argtypes = [vp, C.c_int]
+    lib.hts_b200_multi_launch_count.restype = C.c_ulonglong
+    lib.hts_b200_multi_last_error.restype = C.c_char_p
+    lib.hts_b200_partition.argtypes = [C.c_int, vp, C.c_int, vp]
+    lib.hts_b200_frames_scan.restype = C.c_long
+    lib.hts_b200_frames_scan.argtypes = [vp, C.c_size_t, C.c_int, C.c_long, vp, vp, vp, vp, vp, u32]
+    lib.hts_b200_frames_write.restype = C.c_size_t
+    lib.hts_b200_frames_write.argtypes = [vp, C.c_size_t, C.c_long, vp, vp, vp, vp]
     _libc = C.CDLL(None)
     _libc.free.argtypes = [vp]
     lib._free = _libc.free
@@ -212,6 +227,86 @@ class PinnedArray:
         if getattr(self, "ptr", None):
             self.lib.hts_b200_host_free(self.ptr)
             self.ptr = None
+
+
+class DevStats(C.Structure):
+    """hts_b200_dev_stats (include/htscodecs_b200.h)."""
+    _fields_ = [("device", C.c_int), ("first_blk", C.c_int), ("nblk", C.c_int), ("pad", C.c_int),
+                ("in_bytes", C.c_uint64), ("out_bytes", C.c_uint64),
+                ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("h2d_phase_ms", C.c_double), ("wait_ms", C.c_double), ("d2h_phase_ms", C.c_double),
+                ("wall_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: (round(getattr(self, k), 3) if isinstance(getattr(self, k), float) else getattr(self, k))
+                for k, _ in self._fields_ if k != "pad"}
+
+
+def _multi(fn, devices, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, last):
+    lib = load_library()
+    dev = np.ascontiguousarray(np.asarray(devices, np.int32))
+    rc = fn(len(dev), dev.ctypes.data, nblk, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
+            _ptr(out_len), _ptr(status), _ptr(last))
+    if rc != 0:
+        raise RuntimeError("htscodecs_b200 multi-device call failed: " + lib.hts_b200_multi_last_error().decode())
+
+
+def uncompress_batch_host_multi(devices, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, method=None):
+    """hts_b200_uncompress_batch_host_multi: one host-buffer batch over several GPUs of this process."""
+    _multi(load_library().hts_b200_uncompress_batch_host_multi, devices, nblk, in_base, in_off, in_len, out_base,
+           out_off, out_len, status, method)
+
+
+def compress_batch_host_multi(devices, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, order):
+    _multi(load_library().hts_b200_compress_batch_host_multi, devices, nblk, in_base, in_off, in_len, out_base,
+           out_off, out_len, status, order)
+
+
+def multi_set_phased(phased):
+    load_library().hts_b200_multi_set_phased(1 if phased else 0)
+
+
+def multi_last_stats():
+    """Per-device breakdown of the last multi-device call: list of dicts."""
+    lib = load_library()
+    arr = (DevStats * 64)()
+    n = lib.hts_b200_multi_last_stats(C.addressof(arr), 64)
+    return [arr[i].as_dict() for i in range(min(n, 64))]
+
+
+def multi_launch_count():
+    return int(load_library().hts_b200_multi_launch_count())
+
+
+def frames_scan(buf, method=RANS4x16, out_align=1):
+    """`[u32 clen][stream]...` (the reference test programs' file format) -> (in_off, in_len, out_off,
+    out_len, out_total) numpy arrays for the host-buffer decode calls; None when the buffer is malformed."""
+    lib = load_library()
+    b = np.frombuffer(bytes(buf), np.uint8) if not isinstance(buf, np.ndarray) else buf
+    addr = b.ctypes.data if b.size else None
+    n = lib.hts_b200_frames_scan(addr, b.size, method, 0, None, None, None, None, None, out_align)
+    if n < 0:
+        return None
+    in_off, out_off = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    in_len, out_len = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    total = C.c_uint64(0)
+    lib.hts_b200_frames_scan(addr, b.size, method, n, _ptr(in_off), _ptr(in_len), _ptr(out_off), _ptr(out_len),
+                             C.addressof(total), out_align)
+    return in_off, in_len, out_off, out_len, int(total.value)
+
+
+def frames_write(src, src_off, src_len, status=None):
+    """Encoded streams -> `[u32 clen][stream]...` bytes (failed blocks skipped)."""
+    lib = load_library()
+    n = len(src_len)
+    src_off = np.ascontiguousarray(src_off, np.uint64)
+    src_len = np.ascontiguousarray(src_len, np.uint32)
+    st = None if status is None else np.ascontiguousarray(status, np.int32)
+    need = lib.hts_b200_frames_write(None, 0, n, _ptr(src), _ptr(src_off), _ptr(src_len), _ptr(st))
+    dst = np.zeros(max(1, need), np.uint8)
+    got = lib.hts_b200_frames_write(_ptr(dst), need, n, _ptr(src), _ptr(src_off), _ptr(src_len), _ptr(st))
+    assert got == need
+    return dst[:need].tobytes()
 
 
 class Context:

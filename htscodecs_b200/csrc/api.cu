@@ -8,6 +8,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <map>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/htscodecs_b200.h"
@@ -86,16 +91,21 @@ struct Stage {
     EncSlot enc;
     SideStreams side;           // the chunk's kernels of different kinds run side by side
     cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+    // timing twins (busy time per stage of the pipeline, reported by the multi-device call)
+    cudaEvent_t t_h2d0 = nullptr, t_h2d1 = nullptr, t_k0 = nullptr, t_k1 = nullptr, t_d2h0 = nullptr, t_d2h1 = nullptr;
     cudaStream_t s_compute = nullptr;   // one per stage: a block is decoded by ONE warp, so a chunk's kernels
                                         // last as long as its slowest block; chunks must overlap on the SMs
     // what the device->host half of a chunk needs (it may be enqueued later than the first half)
-    int c_a = 0, c_n = 0; bool c_dense = false; uint64_t c_lo = 0, c_bytes = 0;
+    int c_a = 0, c_n = 0; int c_lay = 0; bool c_equal = false; uint64_t c_lo = 0, c_bytes = 0, c_stride = 0;
     uint64_t c_w = 0;           // encode: leading bytes of every block already fetched (0 = whole regions)
     int init() {
         if (s_compute) return 0;
         if (cudaEventCreateWithFlags(&h2d_done, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&compute_done, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&d2h_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreate(&t_h2d0) != cudaSuccess || cudaEventCreate(&t_h2d1) != cudaSuccess ||
+            cudaEventCreate(&t_k0) != cudaSuccess || cudaEventCreate(&t_k1) != cudaSuccess ||
+            cudaEventCreate(&t_d2h0) != cudaSuccess || cudaEventCreate(&t_d2h1) != cudaSuccess ||
             cudaStreamCreateWithFlags(&s_compute, cudaStreamNonBlocking) != cudaSuccess) return -1;
         return 0;
     }
@@ -106,6 +116,7 @@ struct Stage {
         if (h2d_done) cudaEventDestroy(h2d_done);
         if (compute_done) cudaEventDestroy(compute_done);
         if (d2h_done) cudaEventDestroy(d2h_done);
+        for (cudaEvent_t e : {t_h2d0, t_h2d1, t_k0, t_k1, t_d2h0, t_d2h1}) if (e) cudaEventDestroy(e);
     }
 };
 
@@ -196,7 +207,7 @@ extern "C" void* hts_b200_stream(const hts_b200_ctx* ctx) { return ctx ? (void*)
 extern "C" void hts_b200_set_copy_duplex(hts_b200_ctx* ctx, int full) { if (ctx) ctx->full_duplex = full != 0; }
 extern "C" void* hts_b200_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }   // pinned for every device
     return p;
 }
 extern "C" void hts_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
@@ -286,6 +297,13 @@ extern "C" int hts_b200_uncompress_batch_dev(hts_b200_ctx* ctx, int nblk, const 
     if (nblk == 0) return 0;
     CK(cudaSetDevice(ctx->device));
     DecSlot& s = ctx->dec;
+    // an asynchronous call cannot retry: what its batch header reported (arena need, list overflow) sizes this one
+    if (s.hdr_pending && cudaEventQuery(s.hdr_ready) == cudaSuccess) {
+        size_t ab = 0;
+        if (dec_needs_retry(s, &ab)) ctx->arena_hint = std::max(ctx->arena_hint, ab);
+        else ctx->arena_hint = std::max(ctx->arena_hint, (size_t)s.h_work.p[1].arena_used);
+    }
+    cudaGetLastError();
     size_t arena_bytes = std::max<size_t>(ctx->arena_hint, 64u << 20);
     DecodeBatch b;
     b.work = nullptr; b.hdr = nullptr; b.in_base = in_base; b.in_off = in_off; b.in_len = in_len;
@@ -319,20 +337,59 @@ extern "C" int hts_b200_uncompress_batch_dev(hts_b200_ctx* ctx, int nblk, const 
 // ------------------------------------------------------------------------------------------
 namespace {
 
-struct Range { uint64_t lo, hi; bool dense; };
+// How the blocks [a,b) of one direction sit in the caller's buffer.
+//   TILED    ascending and contiguous (off[i+1] == off[i] + len[i]): the span holds nothing but the blocks
+//   STRIDED  ascending, equal lengths, evenly spaced with stride >= length (padding between the blocks)
+//   LOOSE    neither, but the gaps are small (<= 64 B per block on average): fine to READ as one span
+//   SCATTER  anything else
+enum Layout { TILED, STRIDED, LOOSE, SCATTER };
+struct Range { uint64_t lo, hi, stride; Layout lay; };
 
-// Byte range covered by blocks [a,b) and whether they tile it without gaps or overlap.
 Range span_of(const uint64_t* off, const uint32_t* len, int a, int b) {
-    Range r{UINT64_MAX, 0, true};
+    Range r{UINT64_MAX, 0, 0, TILED};
+    if (a >= b) { r.lo = r.hi = 0; return r; }
     uint64_t sum = 0;
+    bool tiled = true, strided = b - a > 1;
+    const uint64_t stride = b - a > 1 ? off[a + 1] - off[a] : 0;
     for (int i = a; i < b; i++) {
         r.lo = std::min(r.lo, off[i]);
         r.hi = std::max(r.hi, off[i] + len[i]);
         sum += len[i];
+        if (i > a) {
+            if (off[i] != off[i - 1] + len[i - 1]) tiled = false;
+            if (off[i] <= off[i - 1] || off[i] - off[i - 1] != stride || len[i] != len[a]) strided = false;
+        }
     }
-    if (a >= b) { r.lo = r.hi = 0; }
-    r.dense = (r.hi - r.lo) <= sum + 64ull * (b - a);   // allow a little alignment padding between blocks
+    if (strided && (stride < len[a] || stride > 0x7fffffffull)) strided = false;
+    r.stride = stride;
+    if (tiled && r.lo == off[a]) r.lay = TILED;
+    else if (strided) r.lay = STRIDED;
+    else if (r.hi - r.lo <= sum + 64ull * (b - a)) r.lay = LOOSE;
+    else r.lay = SCATTER;
     return r;
+}
+
+// A rendezvous of the per-device threads of a multi-device call (see hts_b200_*_batch_host_multi): every device
+// finishes its host->device copies before any device starts copying results back.
+struct PhaseSync {
+    std::mutex mu;
+    std::condition_variable cv;
+    int want = 0, arrived = 0;
+    void arrive_and_wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        if (++arrived >= want) cv.notify_all();
+        else cv.wait(lk, [&] { return arrived >= want; });
+    }
+};
+
+struct HostRun {                 // optional extras of one host-buffer call
+    PhaseSync* phase = nullptr;  // non-null: phased copies with a cross-device rendezvous
+    bool arrived = false;
+    hts_b200_dev_stats* stats = nullptr;
+};
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 }  // namespace
@@ -389,38 +446,40 @@ static std::vector<int> plan_chunks(bool enc, int nblk, const uint8_t* in_base, 
 }
 
 // One direction-agnostic driver: `enc` selects compress (order != NULL) or uncompress.
-static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* in_base, const uint64_t* in_off,
-                          const uint32_t* in_len, uint8_t* out_base, const uint64_t* out_off, uint32_t* out_len,
-                          int32_t* status, const uint8_t* method, const int32_t* order) {
-    if (!ctx || nblk < 0) return -1;
-    if (nblk == 0) return 0;
+static int run_host_batch_body(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* in_base, const uint64_t* in_off,
+                               const uint32_t* in_len, uint8_t* out_base, const uint64_t* out_off, uint32_t* out_len,
+                               int32_t* status, const uint8_t* method, const int32_t* order, HostRun* hr) {
     CK(cudaSetDevice(ctx->device));
     const std::vector<int> cuts = plan_chunks(enc, nblk, in_base, in_off, in_len, out_len, method, order);
     const int nchunk = (int)cuts.size() - 1;
     std::vector<int> redo;
     std::vector<uint32_t> caps(out_len, out_len + nblk);           // capacities, for retries
+    hts_b200_dev_stats* stats = hr ? hr->stats : nullptr;
 
     auto launch_out = [&](Stage& S) -> int {                         // device->host half of a chunk
         const int a = S.c_a, n = S.c_n;
         const uint64_t* h_out_off = S.h_off.p + n;
         CK(cudaStreamWaitEvent(ctx->s_out, S.compute_done, 0));
+        CK(cudaEventRecord(S.t_d2h0, ctx->s_out));
         CK(cudaMemcpyAsync(S.h_u32.p + n, S.d_u32.p + n, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->s_out));   // out_len + status
+        // A block may only write its own region out_base[out_off[i] .. + capacity): a single copy of the span is
+        // used only when the regions tile it exactly; evenly spaced regions travel as one pitched copy of exactly
+        // `capacity` bytes per row; anything else block by block.
         // Encode: a block's region is its capacity (~1.05 x the input) but its stream a fraction of that.  With equal,
-        // evenly spaced regions ONE strided copy fetches the leading W bytes of every block, W from the ratios the
+        // evenly spaced regions the pitched copy fetches the leading W bytes of every block, W from the ratios the
         // previous chunks ended with; a stream that turns out longer gets its tail in collect_chunk.
         S.c_w = 0;
-        if (enc && S.c_dense && ctx->enc_frac > 0 && n > 1) {
-            const uint64_t stride = out_off[a + 1] - out_off[a];
-            bool regular = true;
-            for (int i = 1; i < n && regular; i++) regular = out_off[a + i] - out_off[a + i - 1] == stride && caps[a + i] == caps[a];
+        const bool rows = (S.c_lay == STRIDED || (S.c_lay == TILED && S.c_equal)) && n > 1;
+        if (enc && rows && ctx->enc_frac > 0) {
             const uint64_t w = std::min<uint64_t>(caps[a], align_up((uint64_t)(caps[a] * std::min(1.0, ctx->enc_frac * 1.15 + 0.02)), 256));
-            if (regular && w < caps[a] && stride >= w) S.c_w = w;
+            if (w < caps[a]) S.c_w = w;
         }
-        if (S.c_w) CK(cudaMemcpy2DAsync(out_base + S.c_lo, out_off[a + 1] - out_off[a], S.d_out.p, out_off[a + 1] - out_off[a], S.c_w, n,
-                                        cudaMemcpyDeviceToHost, ctx->s_out));
-        else if (S.c_dense) CK(cudaMemcpyAsync(out_base + S.c_lo, S.d_out.p, S.c_bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (S.c_w) CK(cudaMemcpy2DAsync(out_base + S.c_lo, S.c_stride, S.d_out.p, S.c_stride, S.c_w, n, cudaMemcpyDeviceToHost, ctx->s_out));
+        else if (S.c_lay == TILED) CK(cudaMemcpyAsync(out_base + S.c_lo, S.d_out.p, S.c_bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+        else if (S.c_lay == STRIDED) CK(cudaMemcpy2DAsync(out_base + S.c_lo, S.c_stride, S.d_out.p, S.c_stride, caps[a], n, cudaMemcpyDeviceToHost, ctx->s_out));
         else for (int i = 0; i < n; i++)
-            CK(cudaMemcpyAsync(out_base + out_off[a + i], S.d_out.p + h_out_off[i], caps[a + i], cudaMemcpyDeviceToHost, ctx->s_out));
+            if (caps[a + i]) CK(cudaMemcpyAsync(out_base + out_off[a + i], S.d_out.p + h_out_off[i], caps[a + i], cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaEventRecord(S.t_d2h1, ctx->s_out));
         CK(cudaEventRecord(S.d2h_done, ctx->s_out));
         return 0;
     };
@@ -428,39 +487,46 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
         const int a = cuts[k], b = cuts[k + 1], n = b - a;
         Range ri = span_of(in_off, in_len, a, b);
         Range ro = span_of(out_off, caps.data(), a, b);
-        // staging layout mirrors the host layout when dense, else blocks are packed 256-byte aligned
+        const bool in_mirror = ri.lay != SCATTER;                    // reading a few padding bytes along is harmless
+        const bool out_mirror = ro.lay == TILED || ro.lay == STRIDED;
+        // staging layout mirrors the host layout where one (pitched) copy moves it, else blocks are packed 256-byte aligned
         uint64_t in_bytes = 0, out_bytes = 0;
         if (S.h_off.ensure(2 * (size_t)n) || S.h_u32.ensure(4 * (size_t)n) || S.h_method.ensure(n) ||
             S.d_off.ensure(2 * (size_t)n) || S.d_u32.ensure(4 * (size_t)n) || S.d_method.ensure(n)) return -1;
         uint64_t* h_in_off = S.h_off.p; uint64_t* h_out_off = S.h_off.p + n;
         uint32_t* h_in_len = S.h_u32.p; uint32_t* h_out_len = S.h_u32.p + n;
         uint32_t* h_order = S.h_u32.p + 3 * (size_t)n;
+        bool equal = true;
         for (int i = 0; i < n; i++) {
             h_in_len[i] = in_len[a + i];
             h_out_len[i] = caps[a + i];
-            if (ri.dense) h_in_off[i] = in_off[a + i] - ri.lo; else { h_in_off[i] = in_bytes; in_bytes += align_up(in_len[a + i], 256); }
-            if (ro.dense) h_out_off[i] = out_off[a + i] - ro.lo; else { h_out_off[i] = out_bytes; out_bytes += align_up(caps[a + i], 256); }
+            if (caps[a + i] != caps[a]) equal = false;
+            if (in_mirror) h_in_off[i] = in_off[a + i] - ri.lo; else { h_in_off[i] = in_bytes; in_bytes += align_up(in_len[a + i], 256); }
+            if (out_mirror) h_out_off[i] = out_off[a + i] - ro.lo; else { h_out_off[i] = out_bytes; out_bytes += align_up(caps[a + i], 256); }
             if (method) S.h_method.p[i] = method[a + i];
             if (order) h_order[i] = (uint32_t)order[a + i];
         }
-        if (ri.dense) in_bytes = ri.hi - ri.lo;
-        if (ro.dense) out_bytes = ro.hi - ro.lo;
+        if (in_mirror) in_bytes = ri.hi - ri.lo;
+        if (out_mirror) out_bytes = ro.hi - ro.lo;
         if (S.d_in.ensure(in_bytes + 256) || S.d_out.ensure(out_bytes + 256)) {
             snprintf(ctx->err, sizeof(ctx->err), "out of device memory for staging");
             return -1;
         }
         // ---- H2D
         CK(cudaStreamWaitEvent(ctx->s_in, S.d2h_done, 0));           // previous user of this stage is done
-        if (ri.dense) CK(cudaMemcpyAsync(S.d_in.p, in_base + ri.lo, in_bytes, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(S.t_h2d0, ctx->s_in));
+        if (in_mirror) CK(cudaMemcpyAsync(S.d_in.p, in_base + ri.lo, in_bytes, cudaMemcpyHostToDevice, ctx->s_in));
         else for (int i = 0; i < n; i++)
-            CK(cudaMemcpyAsync(S.d_in.p + h_in_off[i], in_base + in_off[a + i], in_len[a + i], cudaMemcpyHostToDevice, ctx->s_in));
+            if (in_len[a + i]) CK(cudaMemcpyAsync(S.d_in.p + h_in_off[i], in_base + in_off[a + i], in_len[a + i], cudaMemcpyHostToDevice, ctx->s_in));
         CK(cudaMemcpyAsync(S.d_off.p, S.h_off.p, 16 * (size_t)n, cudaMemcpyHostToDevice, ctx->s_in));
         CK(cudaMemcpyAsync(S.d_u32.p, S.h_u32.p, 16 * (size_t)n, cudaMemcpyHostToDevice, ctx->s_in));
         if (method) CK(cudaMemcpyAsync(S.d_method.p, S.h_method.p, n, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(S.t_h2d1, ctx->s_in));
         CK(cudaEventRecord(S.h2d_done, ctx->s_in));
         // ---- kernels
         cudaStream_t cs = S.s_compute;
         CK(cudaStreamWaitEvent(cs, S.h2d_done, 0));
+        CK(cudaEventRecord(S.t_k0, cs));
         uint32_t* d_status = S.d_u32.p + 2 * (size_t)n;
         if (!enc) {
             if (dec_prepare(ctx, S.dec, n, std::max<size_t>(ctx->arena_hint, 64u << 20))) return -1;
@@ -496,12 +562,22 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
             if (l < 0) return -1;
             ctx->launches += l;
         }
+        CK(cudaEventRecord(S.t_k1, cs));
         CK(cudaEventRecord(S.compute_done, cs));
-        S.c_a = a; S.c_n = n; S.c_dense = ro.dense; S.c_lo = ro.dense ? ro.lo : 0; S.c_bytes = out_bytes;
+        S.c_a = a; S.c_n = n; S.c_lay = out_mirror ? ro.lay : SCATTER; S.c_equal = equal; S.c_stride = ro.lay == STRIDED ? ro.stride : caps[a];
+        S.c_lo = out_mirror ? ro.lo : 0; S.c_bytes = out_bytes;
+        if (stats) { for (int i = a; i < b; i++) { stats->in_bytes += in_len[i]; } }
         return defer_out ? 0 : launch_out(S);
     };
     auto collect_chunk = [&](int k, Stage& S) -> int {               // after S.d2h_done
         const int a = cuts[k], n = cuts[k + 1] - a;
+        if (stats) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, S.t_h2d0, S.t_h2d1) == cudaSuccess) stats->h2d_ms += ms;
+            if (cudaEventElapsedTime(&ms, S.t_k0, S.t_k1) == cudaSuccess) stats->kernel_ms += ms;
+            if (cudaEventElapsedTime(&ms, S.t_d2h0, S.t_d2h1) == cudaSuccess) stats->d2h_ms += ms;
+            cudaGetLastError();
+        }
         bool retry = false;
         if (!enc) {
             size_t ab = 0;
@@ -529,10 +605,12 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
         }
         memcpy(out_len + a, S.h_u32.p + n, 4 * (size_t)n);
         memcpy(status + a, S.h_u32.p + 2 * (size_t)n, 4 * (size_t)n);
+        if (stats) for (int i = 0; i < n; i++) if (status[a + i] == 0) stats->out_bytes += out_len[a + i];
         return 0;
     };
 
-    if (ctx->full_duplex || nchunk == 1) {
+    const bool phased = hr && hr->phase;
+    if (!phased && (ctx->full_duplex || nchunk == 1)) {
         // ---- software pipeline: chunk k uses stage k % NSTAGE; collect k - NSTAGE before reusing it
         for (int k = 0; k < nchunk; k++) {
             Stage& S = ctx->stage[k % NSTAGE];
@@ -549,20 +627,32 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
         }
     } else {
         // ---- half duplex: every chunk has its own stage; all host->device copies (and the kernels behind
-        // them) are enqueued first, the device->host copies start once the last input has landed.  Some
-        // hosts lose most of their device->host rate while any host->device traffic is in flight.
+        // them) are enqueued first, the device->host copies start once the last input has landed -- on every
+        // device of a multi-device call (PhaseSync).  Some hosts lose most of their device->host rate while
+        // any host->device traffic is in flight.
         if ((int)ctx->stage.size() < nchunk) ctx->stage.resize(nchunk);
+        const double t0 = now_ms();
         for (int k = 0; k < nchunk; k++) {
             if (ctx->stage[k].init()) { snprintf(ctx->err, sizeof(ctx->err), "cannot create a staging slot"); return -1; }
             if (launch_chunk(k, ctx->stage[k], true)) return -1;
         }
         CK(cudaEventRecord(ctx->all_h2d, ctx->s_in));
-        CK(cudaStreamWaitEvent(ctx->s_out, ctx->all_h2d, 0));
+        if (phased) {
+            CK(cudaEventSynchronize(ctx->all_h2d));
+            const double t1 = now_ms();
+            hr->arrived = true;
+            hr->phase->arrive_and_wait();
+            if (stats) { stats->h2d_phase_ms = t1 - t0; stats->wait_ms = now_ms() - t1; }
+        } else {
+            CK(cudaStreamWaitEvent(ctx->s_out, ctx->all_h2d, 0));
+        }
+        const double t2 = now_ms();
         for (int k = 0; k < nchunk; k++) if (launch_out(ctx->stage[k])) return -1;
         for (int k = 0; k < nchunk; k++) {
             CK(cudaEventSynchronize(ctx->stage[k].d2h_done));
             if (collect_chunk(k, ctx->stage[k])) return -1;
         }
+        if (stats) stats->d2h_phase_ms = now_ms() - t2;
     }
     // ---- rare: chunks whose scratch overflowed are redone one at a time with the grown arena
     for (int attempt = 0; !redo.empty() && attempt < 8; attempt++) {
@@ -577,6 +667,27 @@ static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* 
     }
     if (!redo.empty()) { snprintf(ctx->err, sizeof(ctx->err), "work area kept overflowing"); return -1; }
     return 0;
+}
+
+static int run_host_batch(hts_b200_ctx* ctx, bool enc, int nblk, const uint8_t* in_base, const uint64_t* in_off,
+                          const uint32_t* in_len, uint8_t* out_base, const uint64_t* out_off, uint32_t* out_len,
+                          int32_t* status, const uint8_t* method, const int32_t* order, HostRun* hr = nullptr) {
+    int rc = -1;
+    if (ctx && nblk >= 0) {
+        const double t0 = now_ms();
+        rc = nblk == 0 ? 0 : run_host_batch_body(ctx, enc, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, method, order, hr);
+        if (rc != 0) {
+            // no copy into the caller's buffers may still be in flight when the call returns
+            cudaSetDevice(ctx->device);
+            cudaStreamSynchronize(ctx->s_in);
+            for (auto& S : ctx->stage) if (S.s_compute) cudaStreamSynchronize(S.s_compute);
+            cudaStreamSynchronize(ctx->s_out);
+            cudaGetLastError();
+        }
+        if (hr && hr->stats) hr->stats->wall_ms = now_ms() - t0;
+    }
+    if (hr && hr->phase && !hr->arrived) { hr->arrived = true; hr->phase->arrive_and_wait(); }   // never strand the other devices
+    return rc;
 }
 
 extern "C" int hts_b200_plan_chunks(int enc, int nblk, const uint8_t* in_base, const uint64_t* in_off,
@@ -602,6 +713,115 @@ extern "C" int hts_b200_compress_batch_host(hts_b200_ctx* ctx, int nblk, const u
     if (!order) return -1;
     return run_host_batch(ctx, true, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, nullptr, order);
 }
+
+// ------------------------------------------------------------------------------------------
+// multi-device host-buffer calls: one thread + context per device, copy phases coordinated across devices
+// ------------------------------------------------------------------------------------------
+extern "C" int hts_b200_partition(int nblk, const uint32_t* weight, int nparts, int* cuts) {
+    if (nblk < 0 || nparts <= 0 || !cuts || (nblk && !weight)) return -1;
+    typedef unsigned __int128 u128;
+    uint64_t total = 0;
+    for (int i = 0; i < nblk; i++) total += weight[i];
+    // part k ends at the block boundary nearest to k / nparts of the total weight (all comparisons scaled by nparts)
+    cuts[0] = 0;
+    uint64_t before = 0;         // weight of blocks [0, i)
+    int i = 0;
+    for (int k = 1; k < nparts; k++) {
+        int c;
+        if (total == 0) c = (int)((long long)nblk * k / nparts);
+        else {
+            const u128 tgt = (u128)total * k;
+            while (i < nblk && (u128)(before + weight[i]) * nparts < tgt) before += weight[i++];
+            c = i;               // first block whose inclusive prefix reaches the target
+            if (c < nblk && (u128)(before + weight[c]) * nparts - tgt <= tgt - (u128)before * nparts) c++;
+        }
+        cuts[k] = std::min(std::max(c, cuts[k - 1]), nblk);
+    }
+    cuts[nparts] = nblk;
+    return 0;
+}
+
+namespace {
+std::mutex g_multi_mu;
+std::map<int, hts_b200_ctx*> g_multi_ctx;
+std::vector<hts_b200_dev_stats> g_multi_stats;
+char g_multi_err[320] = {0};
+int g_multi_phased = -1;     // -1: from the environment (default: phased when ndev > 1)
+struct MultiReaper { ~MultiReaper() { for (auto& kv : g_multi_ctx) hts_b200_destroy(kv.second); g_multi_ctx.clear(); } } g_multi_reaper;
+
+int run_multi(bool enc, int ndev, const int* devices, int nblk, const uint8_t* in_base, const uint64_t* in_off,
+              const uint32_t* in_len, uint8_t* out_base, const uint64_t* out_off, uint32_t* out_len,
+              int32_t* status, const uint8_t* method, const int32_t* order) {
+    if (ndev <= 0 || !devices || nblk < 0 || (enc && !order)) return -1;
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    g_multi_err[0] = 0;
+    g_multi_stats.assign(ndev, hts_b200_dev_stats{});
+    if (nblk == 0) return 0;
+    for (int d = 0; d < ndev; d++) {
+        for (int e = 0; e < d; e++) if (devices[e] == devices[d]) { snprintf(g_multi_err, sizeof(g_multi_err), "device %d listed twice", devices[d]); return -1; }
+        if (!g_multi_ctx.count(devices[d])) {
+            hts_b200_ctx* c = hts_b200_create(devices[d]);
+            if (!c) { snprintf(g_multi_err, sizeof(g_multi_err), "cannot create a context on device %d (no CPU fallback)", devices[d]); return -1; }
+            g_multi_ctx[devices[d]] = c;
+        }
+    }
+    int phased = g_multi_phased;
+    if (phased < 0) { const char* e = getenv("HTSCODECS_B200_MULTI_PHASED"); phased = e ? atoi(e) != 0 : 1; }
+    if (ndev == 1) phased = 0;
+    std::vector<int> cuts(ndev + 1);
+    hts_b200_partition(nblk, enc ? in_len : out_len, ndev, cuts.data());      // uncompressed bytes
+    PhaseSync ps;
+    ps.want = ndev;
+    std::vector<int> rcs(ndev, 0);
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; d++) {
+        th.emplace_back([&, d] {
+            const int a = cuts[d], n = cuts[d + 1] - a;
+            hts_b200_ctx* c = g_multi_ctx[devices[d]];
+            hts_b200_dev_stats& st = g_multi_stats[d];
+            st.device = devices[d]; st.first_blk = a; st.nblk = n;
+            HostRun hr;
+            hr.phase = phased ? &ps : nullptr;
+            hr.stats = &st;
+            rcs[d] = run_host_batch(c, enc, n, in_base, in_off + a, in_len + a, out_base, out_off + a, out_len + a,
+                                    status + a, method ? method + a : nullptr, order ? order + a : nullptr, &hr);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int d = 0; d < ndev; d++)
+        if (rcs[d] != 0) {
+            snprintf(g_multi_err, sizeof(g_multi_err), "device %d: %.250s", devices[d], g_multi_ctx[devices[d]]->err);
+            return -1;
+        }
+    return 0;
+}
+}  // namespace
+
+extern "C" int hts_b200_uncompress_batch_host_multi(int ndev, const int* devices, int nblk, const uint8_t* in_base,
+                                                    const uint64_t* in_off, const uint32_t* in_len, uint8_t* out_base,
+                                                    const uint64_t* out_off, uint32_t* out_len, int32_t* status,
+                                                    const uint8_t* method) {
+    return run_multi(false, ndev, devices, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, method, nullptr);
+}
+extern "C" int hts_b200_compress_batch_host_multi(int ndev, const int* devices, int nblk, const uint8_t* in_base,
+                                                  const uint64_t* in_off, const uint32_t* in_len, uint8_t* out_base,
+                                                  const uint64_t* out_off, uint32_t* out_len, int32_t* status,
+                                                  const int32_t* order) {
+    return run_multi(true, ndev, devices, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, nullptr, order);
+}
+extern "C" void hts_b200_multi_set_phased(int phased) { std::lock_guard<std::mutex> lk(g_multi_mu); g_multi_phased = phased ? 1 : 0; }
+extern "C" int hts_b200_multi_last_stats(hts_b200_dev_stats* out, int max) {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    for (int i = 0; i < (int)g_multi_stats.size() && i < max; i++) out[i] = g_multi_stats[i];
+    return (int)g_multi_stats.size();
+}
+extern "C" unsigned long long hts_b200_multi_launch_count(void) {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    unsigned long long n = 0;
+    for (auto& kv : g_multi_ctx) n += kv.second->launches;
+    return n;
+}
+extern "C" const char* hts_b200_multi_last_error(void) { return g_multi_err; }
 
 extern "C" int hts_b200_compress_batch_dev(hts_b200_ctx* ctx, int nblk, const uint8_t* in_base,
                                            const uint64_t* in_off, const uint32_t* in_len, uint8_t* out_base,
@@ -810,6 +1030,55 @@ extern "C" int hts_b200_peek_size(const uint8_t* in, uint32_t in_len, int method
     }
     if (in_len < 2 || ((in[0] & RANS_ORDER_NOSZ) && !(in[0] & RANS_ORDER_STRIPE))) return -1;
     return host_var_get_u32(in + 1, in + in_len, ulen) ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// container glue: [u32 clen][stream]... (tests/rANS_static4x16pr_test.c:261-296)
+// ------------------------------------------------------------------------------------------
+extern "C" long hts_b200_frames_scan(const uint8_t* buf, size_t len, int method, long max_blk, uint64_t* in_off,
+                                     uint32_t* in_len, uint64_t* out_off, uint32_t* out_len, uint64_t* out_total,
+                                     uint32_t out_align) {
+    if (!buf && len) return -1;
+    if (out_align == 0) out_align = 1;
+    size_t pos = 0;
+    long n = 0;
+    uint64_t out_pos = 0;
+    while (pos < len) {
+        if (len - pos < 4) return -1;
+        uint32_t clen;
+        memcpy(&clen, buf + pos, 4);                                 // native endian, like the reference's fwrite
+        pos += 4;
+        if (clen > len - pos) return -1;
+        uint32_t ulen = 0;
+        if (hts_b200_peek_size(buf + pos, clen, method, &ulen) != 0) return -1;
+        if (n < max_blk) {
+            if (in_off) in_off[n] = pos;
+            if (in_len) in_len[n] = clen;
+            if (out_off) out_off[n] = out_pos;
+            if (out_len) out_len[n] = ulen;
+        }
+        out_pos += ((uint64_t)ulen + out_align - 1) / out_align * out_align;
+        pos += clen;
+        n++;
+    }
+    if (out_total) *out_total = out_pos;
+    return n;
+}
+
+extern "C" size_t hts_b200_frames_write(uint8_t* dst, size_t dst_cap, long nblk, const uint8_t* src_base,
+                                        const uint64_t* src_off, const uint32_t* src_len, const int32_t* status) {
+    size_t need = 0;
+    for (long i = 0; i < nblk; i++) if (!status || status[i] == 0) need += 4 + (size_t)src_len[i];
+    if (!dst) return need;
+    if (need > dst_cap) return (size_t)-1;
+    size_t pos = 0;
+    for (long i = 0; i < nblk; i++) {
+        if (status && status[i] != 0) continue;
+        memcpy(dst + pos, &src_len[i], 4);
+        memcpy(dst + pos + 4, src_base + src_off[i], src_len[i]);
+        pos += 4 + (size_t)src_len[i];
+    }
+    return pos;
 }
 
 // rans_compress_bound_4x16, reference rANS_static4x16pr.c:360-372 (double arithmetic on purpose)

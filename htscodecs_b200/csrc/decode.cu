@@ -1822,6 +1822,9 @@ struct Shape { int grid, smem; };
 static Shape shaped_launch(uint32_t kind, uint32_t groups) {
     int c = (int)((groups + g_sms - 1) / g_sms);
     c = std::max(1, std::min(c, g_cap[kind]));
+    // experiments: HTSCODECS_B200_CAP_O0_32=<n> limits the X_32 order-0 kernel to n resident warps per SM
+    static const int cap32 = getenv("HTSCODECS_B200_CAP_O0_32") ? atoi(getenv("HTSCODECS_B200_CAP_O0_32")) : 0;
+    if (kind == JK_O0_32 && cap32 > 0) c = std::min(c, cap32);
     int smem = g_smem[kind];
     if (c < g_cap[kind]) smem = std::max(smem, std::min(MAX_DYN, (SM_SMEM / c - CTA_RESERVE) & ~127));
     return Shape{g_sms * c, smem};

@@ -1450,6 +1450,10 @@ __global__ void __launch_bounds__(256) enc_finish_kernel(EncWork* W) {
         __syncthreads();
         const EncStream& B = W->streams[L.body];
         uint8_t* out = L.out;
+        if (!out) {                                                  // the block's region is too small (enc_fix_kernel)
+            if (threadIdx.x == 0) { L.out_size = 0; L.status = ST_SIZE; }
+            continue;
+        }
         if (B.codec != 0) {
             // legacy rANS 4x8 block (rANS_static.c:197-215): [order][u32 size - 9][u32 n][table][payload]
             const bool bad = B.size == 0xffffffffu;
@@ -1576,18 +1580,22 @@ __global__ void __launch_bounds__(256) enc_block_kernel(EncWork* W, uint32_t* ou
 }
 
 // Patches the pointers that depend on the caller's device-resident offset arrays.
+// Also the capacity rule: like the reference's coders (rANS_static4x16pr.c:396-397, :706-707) a block whose output
+// region is smaller than rans_compress_bound_4x16(n, order) is refused (ST_SIZE) and nothing is written to it.
 __global__ void enc_fix_kernel(EncWork* W, const uint8_t* in_base, const uint64_t* in_off, uint8_t* out_base,
-                               const uint64_t* out_off) {
+                               const uint64_t* out_off, const uint32_t* out_cap) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= W->nblocks) return;
     EncBlock& B = W->blocks[b];
     B.in = in_base + in_off[b];
     B.out = out_base + out_off[b];
+    const bool fits = out_cap[b] >= B.cap;
     if (B.mode == 0 || B.mode == 4) {
         EncLeaf& L = W->leaves[B.leaf0];
-        L.src = B.in; L.out = B.out;
+        L.src = B.in; L.out = fits ? B.out : nullptr;
         W->streams[L.body].src = B.in;
     }
+    if (!fits) B.mode = 3;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1871,7 +1879,7 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     EncWork* dW = reinterpret_cast<EncWork*>(I->d_desc + o_work);
     int launches = 0;
     const int g = g_sms_enc * 4;
-    enc_fix_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(dW, b.in_base, b.in_off, b.out_base, b.out_off); launches++;
+    enc_fix_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(dW, b.in_base, b.in_off, b.out_base, b.out_off, b.out_len); launches++;
     bool any_stripe = false, any_tr = false, any32[2] = {false, false}, any4[2] = {false, false}, any8[2] = {false, false};
     for (auto& B : blocks) any_stripe |= B.mode == 1;
     for (auto& L : leaves) any_tr |= (L.flags & (F_PACK | F_RLE)) != 0;

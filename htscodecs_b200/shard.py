@@ -17,28 +17,19 @@ def partition_blocks(weights, world):
     """Split blocks [0, n) into `world` contiguous ranges balanced on `weights` (uncompressed
     bytes per block).  Returns a list of (lo, hi); ranges may be empty when n < world.
 
-    Greedy prefix cut: range r ends at the first block where the running total reaches
-    (r + 1) / world of the grand total, which keeps every range within one block of the ideal."""
-    w = np.asarray(weights, dtype=np.float64)
-    n = int(w.size)
+    This is the library's own rule (hts_b200_partition, the one the multi-device C calls use): range r
+    ends at the block boundary nearest to (r + 1) / world of the grand total, which keeps every range
+    within one block of the ideal.  Pure host arithmetic (no GPU needed)."""
+    import ctypes as C
+    from . import load_library
     if world <= 0:
         raise ValueError("world must be positive")
-    if n == 0:
-        return [(0, 0)] * world
-    csum = np.cumsum(w)
-    total = float(csum[-1])
-    cuts = [0]
-    for r in range(1, world):
-        if total <= 0:
-            c = (n * r) // world
-        else:
-            # first index whose inclusive prefix exceeds the target, choosing the nearer side
-            target = total * r / world
-            c = int(np.searchsorted(csum, target, side="left"))
-            if c < n and (csum[c] - target) <= (target - (csum[c - 1] if c else 0.0)):
-                c += 1
-        cuts.append(min(max(c, cuts[-1]), n))
-    cuts.append(n)
+    w = np.ascontiguousarray(np.asarray(weights, dtype=np.uint32))
+    n = int(w.size)
+    cuts = (C.c_int * (world + 1))()
+    rc = load_library().hts_b200_partition(n, w.ctypes.data if n else None, world, cuts)
+    if rc != 0:
+        raise ValueError("hts_b200_partition failed")
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 

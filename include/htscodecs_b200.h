@@ -83,6 +83,9 @@ unsigned int hts_b200_compress_bound_4x8(unsigned int size);
 #define HTS_B200_OK            0
 #define HTS_B200_ERR_FORMAT   (-1)   /* malformed stream (the reference returns NULL) */
 #define HTS_B200_ERR_SIZE     (-2)   /* output capacity too small / size mismatch */
+#define HTS_B200_ERR_SCRATCH  (-3)   /* device scratch (arena / work lists) too small: only reported by the
+                                        asynchronous device-resident calls (sync == 0), which cannot retry;
+                                        the next call on the context starts with the grown scratch */
 #define HTS_B200_ERR_NESTED   (-4)   /* X_STRIPE inside X_STRIPE: never written by the encoder */
 #define HTS_B200_ERR_INTERNAL (-5)
 
@@ -182,6 +185,68 @@ void hts_b200_set_copy_duplex(hts_b200_ctx *ctx, int full);
 int hts_b200_plan_chunks(int enc, int nblk, const uint8_t *in_base, const uint64_t *in_off,
                          const uint32_t *in_len, const uint32_t *out_len, const uint8_t *method,
                          const int32_t *order, int *cuts, int max_cuts);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Multi-device host-buffer calls (blocks are independent, so a batch is cut into
+ *    contiguous ranges balanced on uncompressed bytes, one host thread + context per device, and
+ *    the per-block sizes / status land in the caller's arrays -- no collective).  The reference's
+ *    own loop over blocks, tests/rANS_static4x16pr_test.c:190-215, becomes one call.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Same contract as hts_b200_{un,}compress_batch_host, spread over devices[0 .. ndev).  The library keeps
+ * one context per device (created on first use, reused, destroyed at exit); calls are serialised.
+ * Copy phases are coordinated ACROSS devices: every device sends its inputs first, the threads meet at
+ * a host-side barrier, then the results travel back (hosts whose device->host rate collapses while
+ * other devices' host->device copies are in flight: 304 GB/s vs 134 GB/s aggregate on an 8 x B200 box).
+ * hts_b200_multi_set_phased(0) lets every device run its own full-duplex pipeline instead; the
+ * default is phased for ndev > 1 (environment: HTSCODECS_B200_MULTI_PHASED=0|1). */
+int hts_b200_uncompress_batch_host_multi(int ndev, const int *devices, int nblk,
+                                         const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
+                                         uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
+                                         int32_t *status, const uint8_t *method);
+int hts_b200_compress_batch_host_multi(int ndev, const int *devices, int nblk,
+                                       const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
+                                       uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
+                                       int32_t *status, const int32_t *order);
+void hts_b200_multi_set_phased(int phased);
+
+/* Per-device breakdown of the last multi-device call (busy times from CUDA events on the copy and
+ * compute streams, wall times from the host clock). */
+typedef struct hts_b200_dev_stats {
+    int device, first_blk, nblk, pad;
+    uint64_t in_bytes, out_bytes;      /* bytes sent to / fetched from the device (payload) */
+    double h2d_ms, kernel_ms, d2h_ms;  /* summed busy time of the chunks' copies and kernels */
+    double h2d_phase_ms, wait_ms, d2h_phase_ms;   /* phased mode: send phase, barrier wait, fetch phase (host clock) */
+    double wall_ms;                    /* the device thread's whole call */
+} hts_b200_dev_stats;
+int hts_b200_multi_last_stats(hts_b200_dev_stats *out, int max);   /* returns the number of devices */
+unsigned long long hts_b200_multi_launch_count(void);              /* kernels launched by the multi-device contexts */
+const char *hts_b200_multi_last_error(void);
+
+/* The partition the multi-device calls use: cuts[0 .. nparts] with blocks [cuts[k], cuts[k+1]) going to part k,
+ * contiguous, balanced on the cumulative weights (uncompressed bytes).  Pure host arithmetic. */
+int hts_b200_partition(int nblk, const uint32_t *weight, int nparts, int *cuts);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. Container glue: the `[u32 clen][stream]...` framing written by the reference's test programs
+ *    (tests/rANS_static4x16pr_test.c:261-296, rANS_static_test.c; native-endian 32-bit length, then
+ *    the stream) and consumed by htslib-style callers that hold many CRAM blocks in one buffer.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Walks a framed buffer and fills the batch arrays of the host-buffer decode calls: in_off[i] / in_len[i]
+ * locate stream i inside `buf`, out_len[i] is its stored uncompressed size (hts_b200_peek_size), out_off[i]
+ * the running sum of the sizes rounded up to `out_align` (0 or 1: packed).  method: HTS_B200_RANS4x16 / 4x8.
+ * Returns the number of frames (which may exceed max_blk: only the first max_blk are written; pass
+ * max_blk = 0 to count), or -1 for a truncated frame / a stream without a stored size.  *out_total (may be
+ * NULL) receives the output bytes needed. */
+long hts_b200_frames_scan(const uint8_t *buf, size_t len, int method, long max_blk,
+                          uint64_t *in_off, uint32_t *in_len, uint64_t *out_off, uint32_t *out_len,
+                          uint64_t *out_total, uint32_t out_align);
+/* Writer twin: lays nblk encoded streams (src_base + src_off[i], src_len[i]; status[i] != 0 frames are
+ * skipped when status is not NULL) out as `[u32 clen][stream]...` into dst.  Returns the bytes written, or
+ * (size_t)-1 when dst_cap is too small.  dst == NULL: returns the size needed. */
+size_t hts_b200_frames_write(uint8_t *dst, size_t dst_cap, long nblk, const uint8_t *src_base,
+                             const uint64_t *src_off, const uint32_t *src_len, const int32_t *status);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA runtime. */
 void *hts_b200_host_alloc(size_t bytes);
