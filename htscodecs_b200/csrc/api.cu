@@ -123,8 +123,12 @@ struct Stage {
 constexpr int NSTAGE = 3;
 
 // job-kind sets for the host's "which kernels can be needed" hint
-constexpr uint32_t K_R8 = (1u << JK_R8_O0) | (1u << JK_R8_O1) | (1u << JK_R8_O0C) | (1u << JK_R8_O1S) | (1u << JK_R8_O1M);
-constexpr uint32_t K_BIG = (1u << JK_O0_4C) | (1u << JK_R8_O0C) | (1u << JK_O1_4S) | (1u << JK_R8_O1S);   // large batches only
+constexpr uint32_t K_R8_O0 = (1u << JK_R8_O0) | (1u << JK_R8_O0R8) | (1u << JK_R8_O0R16);
+constexpr uint32_t K_R8_O1 = (1u << JK_R8_O1) | (1u << JK_R8_O1M) | (1u << JK_R8_O1R8) | (1u << JK_R8_O1R16);
+constexpr uint32_t K_R8 = K_R8_O0 | K_R8_O1 | (1u << JK_R8_O0C);
+constexpr uint32_t K_BIG = (1u << JK_O0_4C) | (1u << JK_R8_O0C);   // large batches only
+constexpr uint32_t K_O0_4 = (1u << JK_O0_4) | (1u << JK_O0_4R8) | (1u << JK_O0_4R16);
+constexpr uint32_t K_O1_4 = (1u << JK_O1_4) | (1u << JK_O1_4M) | (1u << JK_O1_4R8) | (1u << JK_O1_4R16);
 
 }  // namespace
 
@@ -539,12 +543,12 @@ static int run_host_batch_body(hts_b200_ctx* ctx, bool enc, int nblk, const uint
             for (int i = 0; i < n; i++) {
                 if (!in_len[a + i]) continue;
                 uint8_t f = in_base[in_off[a + i]];
-                if (method && method[a + i] == 1) { kinds |= f ? (1u << JK_R8_O1) | (1u << JK_R8_O1M) : (1u << JK_R8_O0); continue; }
+                if (method && method[a + i] == 1) { kinds |= f ? K_R8_O1 : K_R8_O0; continue; }
                 if (f & F_STRIPE) { kinds |= ~(K_R8 | K_BIG); post |= 7u; continue; }
                 bool x32 = f & F_X32;
                 if (f & F_CAT) kinds |= 1u << JK_COPY;
-                else if (f & F_ORDER1) kinds |= (x32 ? (1u << JK_O1_32) | (1u << JK_O1_32S) : (1u << JK_O1_4) | (1u << JK_O1_4M)) | (1u << JK_TAB);   // TAB: compressed tables
-                else kinds |= 1u << (x32 ? JK_O0_32 : JK_O0_4);
+                else if (f & F_ORDER1) kinds |= (x32 ? (1u << JK_O1_32) | (1u << JK_O1_32S) : K_O1_4) | (1u << JK_TAB);   // TAB: compressed tables
+                else kinds |= x32 ? (1u << JK_O0_32) : K_O0_4;
                 if (f & F_RLE) { post |= 1u; kinds |= 1u << (x32 ? JK_O0_32 : JK_O0_4); }
                 if (f & F_PACK) post |= 2u;
             }

@@ -24,13 +24,15 @@ enum : int32_t {
 enum JobKind : uint32_t {
     JK_O0_4 = 0, JK_O0_32, JK_O1_4, JK_O1_32, JK_R8_O0, JK_R8_O1, JK_COPY,
     JK_O1_32S,             // X_32 order-1 streams with a small alphabet: the high-occupancy kernel variant
-    JK_O1_4S, JK_R8_O1S,   // 4-way / 4x8 order-1 streams with <= 9 symbols in large batches: 120 resident streams per SM
     JK_O0_4C, JK_R8_O0C,   // 4-way / 4x8 order-0 streams on compact tables: 256 resident streams per SM, used
-                           // for batches too large for one wave of the 4 KB-LUT kernels
+                           // for batches too large for one wave of the 4 KB-LUT kernels (17-64 symbols)
     JK_O1_4M, JK_R8_O1M,   // 4-way / 4x8 order-1 streams of 20-47 symbols (q40-style qualities): 12.5 KB of compact
                            // tables per stream in shared memory, 16 resident streams per SM
     JK_TAB,                // order-0 (4-way) jobs that expand an order-1 stream's compressed table: they run before
                            // every other kind, which then run side by side
+    // 4-way / 4x8 streams of up to 8 / 16 symbols: table (order 0) or context row (order 1) in registers, the
+    // renormalisation bytes prefetched as a window (dec_o0r_kernel / dec_o1r_kernel) -- the short-latency variants
+    JK_O0_4R8, JK_O0_4R16, JK_O1_4R8, JK_O1_4R16, JK_R8_O0R8, JK_R8_O0R16, JK_R8_O1R8, JK_R8_O1R16,
     JK_NKINDS
 };
 
@@ -168,7 +170,7 @@ __device__ __forceinline__ void set_status(int32_t* status, uint32_t blk, int32_
 // batch then costs its slowest kind, not the sum over kinds).  Every kind's launch is shaped for the whole batch
 // (c CTAs per SM), so the kinds settle on disjoint groups of SMs, c CTAs each.  Owned by the caller, reused across batches.
 struct SideStreams {
-    static constexpr int N = 16;
+    static constexpr int N = 24;
     cudaStream_t s[N] = {};
     cudaEvent_t fork = nullptr, join[N] = {};
     int init();

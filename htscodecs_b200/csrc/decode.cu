@@ -84,7 +84,6 @@ __device__ int unpack_meta(const uint8_t* d, uint32_t len, uint8_t* map, uint32_
 __host__ __device__ constexpr uint32_t o1_compact_bytes(uint32_t ns) { return ns * 64 + ns * 4 * (ns + 3); }
 constexpr uint32_t O1_SMALL_TAB = 4608;
 constexpr uint32_t O1_TAB4 = 3072, O1_TAB4M = 12544;   // compact-table bytes per 4-way stream: regular / medium variant
-constexpr uint32_t O1_SMALL4_NS = 9;    // alphabet limit of the small 4-way order-1 variant (9 * 64 + 9 * 12 * 4 = 1008 B)
 
 // bounded reader over global-memory bytes
 struct GRd {
@@ -260,21 +259,26 @@ __device__ int32_t plan_chain(DecWork* W, const uint8_t* in, uint32_t in_len, ui
             // a table worth compressing (> 1000 bytes, :767) belongs to an alphabet beyond the regular 4-way variant
             uint32_t kind = x32 ? JK_O1_32 : (j.aux ? JK_O1_4M : JK_O1_4);
             if (!j.aux && in_len > 1) {                              // uncompressed table: count the alphabet to pick
-                GRd ar{in + 1, end};                                 // the kernel variant (small alphabets run at
-                uint32_t ns = 0;                                     // two to three times the occupancy)
+                GRd ar{in + 1, end};                                 // the kernel variant (small alphabets: rows in
+                uint32_t ns = 0;                                     // registers, or two to three times the occupancy)
                 if (count_alphabet(ar, &ns)) {
                     if (x32 && o1_compact_bytes(ns) <= O1_SMALL_TAB) kind = JK_O1_32S;
-                    if (!x32 && W->big_batch && ns <= O1_SMALL4_NS) kind = JK_O1_4S;
+                    if (!x32 && ns <= 8) kind = JK_O1_4R8;
+                    else if (!x32 && ns <= 16) kind = JK_O1_4R16;
                     else if (!x32 && o1_compact_bytes(ns) > O1_TAB4) kind = JK_O1_4M;
                 }
             }
             if (!push_job(W, kind, j)) return ST_ARENA;
         } else {
             uint32_t kind = x32 ? JK_O0_32 : JK_O0_4;
-            if (!x32 && W->big_batch) {                              // large batch: small alphabets decode from compact
-                GRd ar{in, end};                                     // tables at six times the occupancy
+            if (!x32) {                                              // small alphabets: tables in registers; large batch:
+                GRd ar{in, end};                                     // compact tables at six times the occupancy
                 uint32_t ns = 0;
-                if (count_alphabet(ar, &ns) && ns <= O0C_MAX_NS) kind = JK_O0_4C;
+                if (count_alphabet(ar, &ns)) {
+                    if (ns <= 8) kind = JK_O0_4R8;
+                    else if (ns <= 16) kind = JK_O0_4R16;
+                    else if (W->big_batch && ns <= O0C_MAX_NS) kind = JK_O0_4C;
+                }
             }
             if (!push_job(W, kind, j)) return ST_ARENA;
         }
@@ -339,13 +343,18 @@ __device__ void plan_block(const PlanArgs& A, int blk) {
                         else c = ar.get();
                         if (!c) break;
                     }
-                    if (ok && W->big_batch && ns <= O1_SMALL4_NS) kind = JK_R8_O1S;
+                    if (ok && ns <= 8) kind = JK_R8_O1R8;
+                    else if (ok && ns <= 16) kind = JK_R8_O1R16;
                     else if (ok && o1_compact_bytes(ns) > O1_TAB4) kind = JK_R8_O1M;
                 }
-                if (!in[0] && W->big_batch) {
+                if (!in[0]) {
                     GRd ar{in + 9, in + in_len};
                     uint32_t ns = 0, sum = 0;
-                    if (parse_table_4x8(ar, [&](uint32_t, uint32_t) { ns++; }, &sum, false) && ns <= O0C_MAX_NS) kind = JK_R8_O0C;
+                    if (parse_table_4x8(ar, [&](uint32_t, uint32_t) { ns++; }, &sum, false)) {
+                        if (ns <= 8) kind = JK_R8_O0R8;
+                        else if (ns <= 16) kind = JK_R8_O0R16;
+                        else if (W->big_batch && ns <= O0C_MAX_NS) kind = JK_R8_O0C;
+                    }
                 }
                 if (!push_job(W, kind, make_job(in, in_len, out, n, blk))) st = ST_ARENA;
                 A.out_len[blk] = n;
@@ -1055,19 +1064,22 @@ __global__ void __launch_bounds__(32, 32) dec_o0c_kernel(DecWork* W, int32_t* st
 //
 // Shared memory of one group: [0,256) rank -> symbol, [256,512) symbol -> rank, frequency
 // scratch, the word ring, then TAB bytes of compact tables.
-template <int NWAY, int SZ = 0> struct O1Smem {               // SZ: 0 regular, 1 small, 2 medium (4-way only)
-    static constexpr bool SMALL = SZ == 1;
+template <int NWAY, int SZ = 0> struct O1Smem {               // SZ: 0 regular, 1 small, 2 medium (4-way only),
+    static constexpr bool SMALL = SZ == 1;                    //     3 / 4: rows of 8 / 16 entries for the register-table kernels
+    static constexpr bool REG = SZ >= 3;
+    static constexpr int REG_NS = SZ == 3 ? 8 : 16;
     static constexpr int UNRANK = 0, RANK = 256;
-    // the frequency scratch is only live during set-up; X_32 (1 KB ring) and the small 4-way variant
-    // (alphabets of <= 9 symbols, 256-byte ring) let it share the word ring's memory
-    static constexpr bool OVERLAY = (NWAY == 32) || SMALL;
+    // the frequency scratch is only live during set-up; X_32 (1 KB ring) and the small 4-way variants
+    // (alphabets of <= 16 symbols, 256-byte ring) let it share the word ring's memory
+    static constexpr bool OVERLAY = (NWAY == 32) || SMALL || REG;
     static constexpr int FTMP = 512, RINGO = OVERLAY ? 512 : 1536;
-    static constexpr int TABO = RINGO + GroupCfg<NWAY>::RING;
+    static constexpr int TABO = RINGO + GroupCfg<NWAY>::RING + (REG ? 64 : 0);   // REG: + mirror of the ring's first 64 bytes
     // X_32: 12992 B (<= 48 symbols, 15 warps / SM) or, SMALL, 4608 B (<= 25 symbols, 28 warps / SM);
-    // 4-way: 3072 B per group (<= 19 symbols, 40 groups / SM), SMALL 1024 B (<= 9 symbols, 120 groups / SM) or,
-    // medium, 12544 B (<= 47 symbols, 16 groups / SM)
+    // 4-way: 3072 B per group (<= 19 symbols, 40 groups / SM), SMALL 1024 B (<= 9 symbols, 120 groups / SM),
+    // medium 12544 B (<= 47 symbols, 16 groups / SM), REG ns x ns entries (256 B / 1 KB)
     static constexpr int TAB = (NWAY == 32) ? (SMALL ? (int)O1_SMALL_TAB : 12992)
-                                            : (SMALL ? 1024 : SZ == 2 ? (int)O1_TAB4M : (int)O1_TAB4);
+                               : REG ? REG_NS * REG_NS * 4
+                                     : (SMALL ? 1024 : SZ == 2 ? (int)O1_TAB4M : (int)O1_TAB4);
     static constexpr int FTMP_ENTRIES = OVERLAY ? GroupCfg<NWAY>::RING / 4 : 256;
     static constexpr int STRIDE = TABO + TAB;                        // multiple of 16
     static constexpr int TOTAL = STRIDE * GroupCfg<NWAY>::G;
@@ -1078,6 +1090,8 @@ struct O1Tables {
     uint32_t bstride;       // compact: bytes per context block
     uint8_t* g_tabs;        // the same layout in global memory when it does not fit (compact == 0)
     uint32_t ns, shift;
+    uint32_t row_off;       // entries start this far into a context block (64: behind the coarse index; 0: no index)
+    uint32_t cshift;        // position of an entry's last-slot field (20; register-table kernels: 32 - shift)
 };
 
 // Group-cooperative: frequencies of one context (shared u32 array F, indexed by rank, `ns`
@@ -1105,19 +1119,20 @@ __device__ bool build_o1_row_compact(const Grp<NWAY>& G, uint32_t F, const O1Tab
     // 4x8 tables written by the reference sum to M - 1 (rANS_static.c:122-130); slot M - 1 then
     // belongs to no symbol and resolves to the row's sentinel (never reached by a valid stream)
     if (total != M && !(allow_4095 && total == M - 1)) return false;
-    const uint32_t crs = T.tabs + ctx * T.bstride, row = crs + 64;   // shared form
+    const uint32_t crs = T.tabs + ctx * T.bstride, row = crs + T.row_off;   // shared form
     uint8_t* gcrs = T.g_tabs + (size_t)ctx * T.bstride;             // global form
     uint32_t* grow = reinterpret_cast<uint32_t*>(gcrs + 64);
+    const bool coarse = T.row_off != 0;
     for (uint32_t k = 0; k < K; k++) {
         const uint32_t r = r0 + k;
         if (r >= ns) break;
         const uint32_t f = lds_u32(F + 4 * r) << sh;
         if (!f) continue;
         const uint32_t last = c + f - 1;
-        const uint32_t e = (last << 20) | (r << 12) | (f - 1);
+        const uint32_t e = (last << T.cshift) | (r << 12) | (f - 1);
         if (T.compact) {
             sts_u32(row + 4 * idx, e);
-            for (uint32_t q = (c + (1u << bs) - 1) >> bs; q <= (last >> bs); q++) sts_u8(crs + q, idx);
+            if (coarse) for (uint32_t q = (c + (1u << bs) - 1) >> bs; q <= (last >> bs); q++) sts_u8(crs + q, idx);
         } else {
             grow[idx] = e;
             for (uint32_t q = (c + (1u << bs) - 1) >> bs; q <= (last >> bs); q++) gcrs[q] = (uint8_t)idx;
@@ -1203,13 +1218,16 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     O1Tables T;
     T.ns = ns; T.shift = shift;
     T.g_tabs = nullptr;
-    T.bstride = 64 + 4 * (ns + 3);
+    T.bstride = S::REG ? 4u * S::REG_NS : 64 + 4 * (ns + 3);
+    T.row_off = S::REG ? 0u : 64u;
+    T.cshift = S::REG ? 32u - shift : 20u;
     T.tabs = tabs;
-    T.compact = (o1_compact_bytes(ns) <= (uint32_t)S::TAB) ? 1u : 0u;
+    T.compact = S::REG ? 1u : ((o1_compact_bytes(ns) <= (uint32_t)S::TAB) ? 1u : 0u);
+    if (S::REG && ns > (uint32_t)S::REG_NS) return ST_INTERNAL;          // (the planner counts the alphabet before routing here)
     const uint32_t nwords = ns * (T.bstride / 4);
     if (T.compact) {
         for (uint32_t k = G.glane; k < nwords; k += NWAY)                    // coarse: 0, entries: sentinels
-            sts_u32(tabs + 4 * k, (k % (T.bstride / 4)) < 16 ? 0u : O1_SENTINEL);
+            sts_u32(tabs + 4 * k, (!S::REG && (k % (T.bstride / 4)) < 16) ? 0u : O1_SENTINEL);
     } else {
         uint8_t* a = nullptr;
         if (G.glane == 0) a = arena_alloc(W, (uint64_t)nwords * 4);
@@ -1458,7 +1476,7 @@ __global__ void __launch_bounds__(32, (SZ == 1 && NWAY == 32) ? 28 : 1) dec_o1_k
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         O1Tables T;
         T.compact = 1; T.tabs = base + S::TABO; T.bstride = 0;
-        T.g_tabs = nullptr; T.ns = 1; T.shift = 12;
+        T.g_tabs = nullptr; T.ns = 1; T.shift = 12; T.row_off = 64; T.cshift = 20;
         uint32_t R = 0, ctx0 = 0;
         const uint8_t* first_word = nullptr;
         bool ok = false;
@@ -1481,6 +1499,339 @@ __global__ void __launch_bounds__(32, (SZ == 1 && NWAY == 32) ? 28 : 1) dec_o1_k
         if (compact && aligned)      o1_loop<NWAY, BYTE, true, true>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
         else if (compact)            o1_loop<NWAY, BYTE, false, true>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
         else                         o1_loop<NWAY, BYTE, false, false>(R, ring, T, unrank, ctx0, job.out, seg, tail, minit, maxit, G);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 4-way / 4x8 streams with small alphabets: tables in registers, renormalisation bytes as a window
+// ------------------------------------------------------------------------------------------
+// A 4-way stream is four lanes of strictly serial work, so at the batch sizes of BASELINE.json (4096 blocks:
+// 3.5 warps per SM) its speed is the latency of one step, not throughput.  The look-up-table kernels above spend
+// three shared-memory round trips (~30 cycles each) per step: symbol, (F, C), renormalisation word.  Here
+//   * the stream's table (order 0) or the current context's row (order 1) sits in NS registers per lane as packed
+//     entries (C+F-1) << cshift | sym-or-rank << 12 | (F-1), and the symbol is found by a branch-free binary search
+//     (log2 NS compare/select levels, ~9 cycles each); an order-1 lane loads its NEXT row (two or four 128-bit
+//     shared loads) as soon as the symbol is known, behind the renormalisation chain;
+//   * the 8 bytes at the group's read position (a step consumes at most 4 words, or 4 x 2 bytes for 4x8) are fetched
+//     at the START of the step, and after the ballot each lane picks its word with two byte permutes -- the
+//     selector comes from a permute-table indexed by the ballot bits of the lower lanes, so neither a popc nor a
+//     shared-memory load sits between the ballot and the next state.
+// Results are identical to the table kernels by construction (same F, same C); alphabets of up to 16 symbols.
+struct Win { uint32_t lo, hi; };
+
+// prmt.b32 without __byte_perm's selector masking: every selector nibble used here is <= 7 (bit 3 = sign replication)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// The 8 bytes at byte offset `head` of a 4-way group's ring (RING = 256 bytes + mirror of its first 64).
+__device__ __forceinline__ Win win_load(uint32_t ring, uint32_t head) {
+    const uint32_t a = ring + (head & 252u);
+    const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4), w2 = lds_u32(a + 8);
+    const uint32_t sh = (head & 3u) * 8u;
+    Win w;
+    w.lo = __funnelshift_r(w0, w1, sh);
+    w.hi = __funnelshift_r(w1, w2, sh);
+    return w;
+}
+
+// Renormalise every lane of the warp (rANS_word.h:356-410 / rANS_byte.h:435-551) from its group's window.
+// p: this lane's state `x` is below the lower bound (and the lane is active).  Advances `head`.
+template <bool BYTE>
+__device__ __forceinline__ uint32_t win_renorm(uint32_t x, bool p, const Win w, uint32_t& head, uint32_t lt4, uint32_t gshift) {
+    if (BYTE) {
+        const bool p2 = p && x < (1u << 15);
+        const uint32_t b1 = __ballot_sync(0xffffffffu, p) >> gshift, b2 = __ballot_sync(0xffffffffu, p2) >> gshift;
+        const uint32_t o = __popc(b1 & lt4) + __popc(b2 & lt4);                   // 0 .. 6: my first byte
+        const uint32_t ww = prmt(w.lo, w.hi, o * 0x11u + 0x10u);           // bytes o, o + 1
+        if (p2) x = prmt(ww, x, 0x5401);                                   // x << 16 | first << 8 | second
+        else if (p) x = prmt(ww, x, 0x6540);                               // x << 8 | first
+        head += __popc(b1 & 15u) + __popc(b2 & 15u);
+    } else {
+        const uint32_t b = __ballot_sync(0xffffffffu, p) >> gshift;
+        // word index k = popc(b & lt4) -> selector bytes (2k, 2k+1), by table: v = b & lt4 in 0..7
+        const uint32_t selk = prmt(0x54323210u, 0x76545432u, b & lt4);
+        const uint32_t ww = prmt(w.lo, w.hi, selk);
+        if (p) x = prmt(ww, x, 0x5410);                                    // x << 16 | word
+        head += 2u * __popc(b & 15u);
+    }
+    return x;
+}
+
+// First entry whose last slot is >= the probe (entries ascending, padded with sentinels): M > e  <=>  slot beyond e.
+template <int NS> __device__ __forceinline__ uint32_t reg_search(const uint32_t (&e)[NS], uint32_t M);
+template <> __device__ __forceinline__ uint32_t reg_search<8>(const uint32_t (&e)[8], uint32_t M) {
+    const bool p2 = M > e[3];
+    const uint32_t a0 = p2 ? e[4] : e[0], a1 = p2 ? e[5] : e[1], a2 = p2 ? e[6] : e[2], a3 = p2 ? e[7] : e[3];
+    const bool p1 = M > a1;
+    const uint32_t b0 = p1 ? a2 : a0, b1 = p1 ? a3 : a1;
+    return (M > b0) ? b1 : b0;
+}
+template <> __device__ __forceinline__ uint32_t reg_search<16>(const uint32_t (&e)[16], uint32_t M) {
+    const bool p3 = M > e[7];
+    uint32_t h[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) h[k] = p3 ? e[8 + k] : e[k];
+    return reg_search<8>(h, M);
+}
+
+template <int NS> __device__ __forceinline__ void load_row(uint32_t (&e)[NS], uint32_t addr) {
+#pragma unroll
+    for (int k = 0; k < NS; k += 4) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr + 4 * k));
+        e[k] = v.x; e[k + 1] = v.y; e[k + 2] = v.z; e[k + 3] = v.w;
+    }
+}
+
+// One decode step from a register row.  Returns the entry's symbol / rank field; x becomes the new state before
+// renormalisation, *p whether it must be renormalised.  shift / sh32 = 32 - shift are per-lane values.
+template <int NS, bool BYTE>
+__device__ __forceinline__ uint32_t reg_symbol(uint32_t& x, const uint32_t (&E)[NS], uint32_t shift, uint32_t sh32, uint32_t mask, bool* p) {
+    constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
+    const uint32_t e = reg_search<NS>(E, x << sh32);
+    const uint32_t q = x >> shift, m = x & mask;
+    // x' = F q + m - C with F - 1 = e[11:0] and C + F - 1 = e >> sh32:  X = (F-1)(q+1) + q + m = x' + (C+F-1)
+    const uint32_t last = e >> sh32;
+    const uint32_t X = (e & 0xfffu) * (q + 1u) + (q + m);
+    *p = X < last + L;
+    x = X - last;
+    return (e >> 12) & 0xffu;
+}
+
+struct RegSmem0 {            // order 0: per group [entries NS x 4 | ring 256 + 64 mirror]
+    static constexpr int ENT = 0, RINGO = 64, STRIDE = 64 + 256 + 64, TOTAL = 8 * STRIDE;
+};
+
+// Order-0 set-up (one lane parses straight from global memory): entries (C+F-1) << 20 | sym << 12 | (F-1) for the
+// symbols of non-zero frequency, in cumulative order, padded with sentinels.
+template <int NS, bool BYTE>
+__device__ bool o0r_setup(const Grp<4>& G, const DecJob& job, uint32_t gsm, uint32_t* R, uint32_t* first_word) {
+    constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
+    const uint32_t ent = gsm + RegSmem0::ENT, syms = gsm + RegSmem0::RINGO, ftmp = syms + 64;   // ring: free for now
+    const uint8_t* in_end = job.in + job.in_len;
+    const uint32_t hdr0 = BYTE ? 9u : 0u;
+    uint32_t tab = 0;
+    if (G.glane == 0 && job.in_len >= hdr0 + 16) {
+        GRd rd{job.in + hdr0, in_end};
+        uint32_t ns = 0, sum = 0;
+        bool ok;
+        if (BYTE) {
+            ok = parse_table_4x8(rd, [&](uint32_t j, uint32_t f) {
+                if (ns < (uint32_t)NS) { sts_u8(syms + ns, j); sts_u32(ftmp + 4 * ns, f); }
+                ns++; }, &sum, false);
+        } else {
+            uint32_t cnt = 0;
+            ok = list_alphabet(rd, &ns, [&](uint32_t j) { if (cnt < (uint32_t)NS) sts_u8(syms + cnt, j); cnt++; });
+            if (ok && ns <= (uint32_t)NS)
+                for (uint32_t i = 0; i < ns; i++) { const uint32_t f = rd.varint(); sts_u32(ftmp + 4 * i, f); sum += f; }
+        }
+        ok = ok && ns >= 1 && ns <= (uint32_t)NS;
+        uint32_t sh = 0;
+        if (ok && !BYTE && sum != 0 && sum < 4096) while ((sum << sh) < 4096) sh++;      // normalise_freq_shift
+        uint32_t c = 0, idx = 0;
+        for (uint32_t i = 0; ok && i < ns; i++) {
+            const uint32_t f = lds_u32(ftmp + 4 * i) << sh;
+            if (!f) continue;
+            if (f > 4096 - c) { ok = false; break; }
+            sts_u32(ent + 4 * idx, ((c + f - 1) << 20) | (lds_u8(syms + i) << 12) | (f - 1));
+            idx++;
+            c += f;
+        }
+        if (ok && c != 4096 && !(BYTE && c == 4095)) ok = false;                         // :551 / rANS_static.c:305
+        for (uint32_t k = idx; k < (uint32_t)NS; k++) sts_u32(ent + 4 * k, O1_SENTINEL);
+        if (ok) tab = (uint32_t)(rd.p - job.in);
+    }
+    tab = G.bcast(tab);
+    if (tab == 0 || tab + 16 > job.in_len) return false;
+    const uint32_t r0 = ld_u32_le(job.in + tab + 4 * G.glane);
+    if (!G.all(r0 >= L)) return false;
+    *R = r0;
+    *first_word = tab + 16;
+    G.sync();
+    return true;
+}
+
+template <int NS, bool BYTE>
+__global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status, uint32_t kind) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const Grp<4> G;
+    uint32_t base = smem_addr(smem_raw) + G.g * RegSmem0::STRIDE;
+    asm volatile("" : "+r"(base));
+    const uint32_t njobs = W->njobs[kind];
+    const DecJob* jobs = W->jobs[kind];
+    const uint32_t lt4 = (1u << G.glane) - 1u;
+    for (;;) {
+        uint32_t j0 = 0;
+        if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], 8u);
+        j0 = __shfl_sync(0xffffffffu, j0, 0);
+        if (j0 >= njobs) break;
+        const uint32_t ji = j0 + G.g;
+        const bool active = ji < njobs;
+        DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
+        uint32_t R = 0, first_word = 0;
+        bool ok = false;
+        if (active) {
+            job = jobs[ji];
+            ok = o0r_setup<NS, BYTE>(G, job, base, &R, &first_word);
+            if (!ok && G.glane == 0) set_status(status, job.blk, ST_FORMAT);
+        }
+        uint32_t E[NS];
+        load_row<NS>(E, base + RegSmem0::ENT);
+        if (!ok) {
+#pragma unroll
+            for (int k = 0; k < NS; k++) E[k] = O1_SENTINEL;
+        }
+        __syncwarp();
+        WordRing<4> ring;
+        ring.init(job.in + first_word, job.in + job.in_len, base + RegSmem0::RINGO, G, ok, true);
+        __syncwarp();
+        const uint32_t iters = ok ? job.out_len / 4 : 0, rem = ok ? job.out_len % 4 : 0;
+        const uint32_t maxit = __reduce_max_sync(0xffffffffu, iters), minit = __reduce_min_sync(0xffffffffu, iters);
+        uint8_t* op = job.out + G.glane;
+        uint32_t i = 0;
+        const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(job.out) & 3) == 0);
+        for (; i + 4 <= minit; i += 4) {                     // every lane of the warp active: four steps to a ring check
+            uint32_t w = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const Win win = win_load(ring.ring, ring.head);
+                bool p;
+                const uint32_t sy = reg_symbol<NS, BYTE>(R, E, 12u, 20u, 0xfffu, &p);
+                w |= sy << (8 * u);
+                R = win_renorm<BYTE>(R, p, win, ring.head, lt4, G.gshift);
+            }
+            if (al4) *reinterpret_cast<uint32_t*>(op + 3 * G.glane) = transpose4x4(w, G.glane);   // 16 contiguous bytes per group
+            else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) op[4 * u] = (uint8_t)(w >> (8 * u));
+            }
+            op += 16;
+            ring.advance(G.glane, true);
+        }
+        for (; i < maxit; i++) {
+            const bool act = i < iters;
+            const Win win = win_load(ring.ring, ring.head);
+            uint32_t x = R;
+            bool p;
+            const uint32_t sy = reg_symbol<NS, BYTE>(x, E, 12u, 20u, 0xfffu, &p);
+            if (act) { R = x; *op = (uint8_t)sy; op += 4; }
+            R = win_renorm<BYTE>(R, act && p, win, ring.head, lt4, G.gshift);
+            ring.advance(G.glane, act);
+        }
+        if (G.glane < rem) {                                 // the last n % 4 symbols: peek only (rANS_static.c:346-355)
+            const uint32_t e = reg_search<NS>(E, R << 20);
+            *op = (uint8_t)(e >> 12);
+        }
+        __syncwarp();
+    }
+}
+
+// Order 1: the row of the lane's current context in registers; the next row is fetched the moment the symbol is known.
+template <int NS, bool BYTE>
+__global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status, uint32_t kind) {
+    constexpr int SZ = NS == 8 ? 3 : 4;
+    using S = O1Smem<4, SZ>;
+    constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const Grp<4> G;
+    uint8_t* gsm = smem_raw + G.g * S::STRIDE;
+    uint32_t base = smem_addr(gsm);
+    asm volatile("" : "+r"(base));
+    const uint32_t njobs = W->njobs[kind];
+    const DecJob* jobs = W->jobs[kind];
+    const uint32_t lt4 = (1u << G.glane) - 1u;
+    const uint32_t rows = base + S::TABO, unrank = base + S::UNRANK;
+    for (;;) {
+        uint32_t j0 = 0;
+        if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], 8u);
+        j0 = __shfl_sync(0xffffffffu, j0, 0);
+        if (j0 >= njobs) break;
+        const uint32_t ji = j0 + G.g;
+        const bool active = ji < njobs;
+        DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
+        O1Tables T;
+        T.compact = 1; T.tabs = rows; T.bstride = 4 * NS; T.g_tabs = nullptr; T.ns = 1; T.shift = 12; T.row_off = 0; T.cshift = 20;
+        uint32_t R = 0, ctx0 = 0;
+        const uint8_t* first_word = nullptr;
+        bool ok = false;
+        if (active) {
+            job = jobs[ji];
+            int32_t st = job.aux ? ST_INTERNAL : o1_setup<4, BYTE, SZ>(G, W, job, gsm, base, &T, &R, &first_word, &ctx0);
+            ok = st == ST_OK;
+            if (!ok && G.glane == 0) set_status(status, job.blk, st);
+        }
+        if (!ok) for (uint32_t k = G.glane; k < (uint32_t)NS; k += 4) sts_u32(rows + 4 * k, O1_SENTINEL);   // a harmless row 0
+        __syncwarp();
+        WordRing<4> ring;
+        ring.init(first_word, job.in + job.in_len, base + S::RINGO, G, ok, true);
+        __syncwarp();
+        const uint32_t seg = ok ? job.out_len / 4 : 0, tail = ok ? job.out_len - seg * 4 : 0;
+        const uint32_t maxit = __reduce_max_sync(0xffffffffu, seg + tail), minit = __reduce_min_sync(0xffffffffu, seg);
+        const uint32_t shift = ok ? T.shift : 12u, sh32 = 32u - shift, mask = (1u << shift) - 1u;
+        const uint32_t mine = seg + ((G.glane == 3) ? tail : 0u), group_steps = seg + tail;
+        // rank -> symbol in registers (NS = 8: one permute; NS = 16: two and a select)
+        uint32_t U[NS / 4];
+#pragma unroll
+        for (int k = 0; k < NS / 4; k++) U[k] = lds_u32(unrank + 4 * k);
+        auto unrk = [&](uint32_t r) -> uint32_t {
+            if (NS == 8) return prmt(U[0], U[1], r) & 0xffu;
+            const uint32_t lo = prmt(U[0], U[1], r & 7u), hi = prmt(U[NS / 4 - 2], U[NS / 4 - 1], r & 7u);
+            return ((r & 8u) ? hi : lo) & 0xffu;
+        };
+        uint32_t E[NS];
+        load_row<NS>(E, rows + (ok ? ctx0 : 0u) * (4 * NS));
+        ByteSink sink;
+        uint8_t* const op0 = job.out + (size_t)G.glane * seg;
+        sink.init(op0);
+        uint32_t i = 0;
+        const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(op0) & 3) == 0);
+        if (al4) {
+            for (; i + 4 <= minit; i += 4) {
+                uint32_t pack = 0;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const Win win = win_load(ring.ring, ring.head);
+                    bool p;
+                    const uint32_t r = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
+                    load_row<NS>(E, rows + r * (4 * NS));
+                    pack |= unrk(r) << (8 * u);
+                    R = win_renorm<BYTE>(R, p, win, ring.head, lt4, G.gshift);
+                }
+                sink.put4(pack);
+                ring.advance(G.glane, true);
+            }
+        } else {
+            for (; i + 4 <= minit; i += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const Win win = win_load(ring.ring, ring.head);
+                    bool p;
+                    const uint32_t r = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
+                    load_row<NS>(E, rows + r * (4 * NS));
+                    sink.put(unrk(r));
+                    R = win_renorm<BYTE>(R, p, win, ring.head, lt4, G.gshift);
+                }
+                ring.advance(G.glane, true);
+            }
+        }
+        for (; i < maxit; i++) {
+            const bool act = i < mine;
+            const Win win = win_load(ring.ring, ring.head);
+            bool p = false;
+            if (act) {
+                const uint32_t r = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
+                load_row<NS>(E, rows + r * (4 * NS));
+                sink.put(unrk(r));
+            }
+            R = win_renorm<BYTE>(R, act && p, win, ring.head, lt4, G.gshift);
+            ring.advance(G.glane, i < group_steps);
+        }
+        sink.finish();
+        (void)L;
         __syncwarp();
     }
 }
@@ -1804,8 +2155,14 @@ int decode_init(int device) {
     persistent_setup(JK_O1_32,  dec_o1_kernel<32, false, 0>, O1Smem<32>::TOTAL, 32);
     persistent_setup(JK_O1_32S, dec_o1_kernel<32, false, 1>,  O1Smem<32, 1>::TOTAL, 32);
     persistent_setup(JK_O1_4,   dec_o1_kernel<4, false, 0>,  O1Smem<4>::TOTAL, 32);
-    persistent_setup(JK_O1_4S,  dec_o1_kernel<4, false, 1>,   O1Smem<4, 1>::TOTAL, 32);
-    persistent_setup(JK_R8_O1S, dec_o1_kernel<4, true, 1>,    O1Smem<4, 1>::TOTAL, 32);
+    persistent_setup(JK_O0_4R8,   dec_o0r_kernel<8, false>,  RegSmem0::TOTAL, 32);
+    persistent_setup(JK_O0_4R16,  dec_o0r_kernel<16, false>, RegSmem0::TOTAL, 32);
+    persistent_setup(JK_R8_O0R8,  dec_o0r_kernel<8, true>,   RegSmem0::TOTAL, 32);
+    persistent_setup(JK_R8_O0R16, dec_o0r_kernel<16, true>,  RegSmem0::TOTAL, 32);
+    persistent_setup(JK_O1_4R8,   dec_o1r_kernel<8, false>,  O1Smem<4, 3>::TOTAL, 32);
+    persistent_setup(JK_O1_4R16,  dec_o1r_kernel<16, false>, O1Smem<4, 4>::TOTAL, 32);
+    persistent_setup(JK_R8_O1R8,  dec_o1r_kernel<8, true>,   O1Smem<4, 3>::TOTAL, 32);
+    persistent_setup(JK_R8_O1R16, dec_o1r_kernel<16, true>,  O1Smem<4, 4>::TOTAL, 32);
     persistent_setup(JK_R8_O1,  dec_o1_kernel<4, true, 0>,   O1Smem<4>::TOTAL, 32);
     persistent_setup(JK_O1_4M,  dec_o1_kernel<4, false, 2>,  O1Smem<4, 2>::TOTAL, 32);
     persistent_setup(JK_R8_O1M, dec_o1_kernel<4, true, 2>,   O1Smem<4, 2>::TOTAL, 32);
@@ -1866,8 +2223,14 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     LAUNCH_DEC(JK_R8_O1, (dec_o1_kernel<4, true, 0>), 8, false)
     LAUNCH_DEC(JK_O0_4, (dec_o0_kernel<4, false>), 8, false)
     LAUNCH_DEC(JK_R8_O0, (dec_o0_kernel<4, true>), 8, false)
-    LAUNCH_DEC(JK_O1_4S, (dec_o1_kernel<4, false, 1>), 8, false)
-    LAUNCH_DEC(JK_R8_O1S, (dec_o1_kernel<4, true, 1>), 8, false)
+    LAUNCH_DEC(JK_O1_4R16, (dec_o1r_kernel<16, false>), 8, false)
+    LAUNCH_DEC(JK_R8_O1R16, (dec_o1r_kernel<16, true>), 8, false)
+    LAUNCH_DEC(JK_O1_4R8, (dec_o1r_kernel<8, false>), 8, false)
+    LAUNCH_DEC(JK_R8_O1R8, (dec_o1r_kernel<8, true>), 8, false)
+    LAUNCH_DEC(JK_O0_4R16, (dec_o0r_kernel<16, false>), 8, false)
+    LAUNCH_DEC(JK_R8_O0R16, (dec_o0r_kernel<16, true>), 8, false)
+    LAUNCH_DEC(JK_O0_4R8, (dec_o0r_kernel<8, false>), 8, false)
+    LAUNCH_DEC(JK_R8_O0R8, (dec_o0r_kernel<8, true>), 8, false)
     LAUNCH_DEC(JK_O0_4C, (dec_o0c_kernel<false>), 8, false)
     LAUNCH_DEC(JK_R8_O0C, (dec_o0c_kernel<true>), 8, false)
     LAUNCH_DEC(JK_O1_32, (dec_o1_kernel<32, false, 0>), 1, false)

@@ -182,15 +182,19 @@ def test_encode_capacity_below_the_bound_is_refused(oracle):
     ctx.compress_batch_dev(n, torch.from_numpy(rb).cuda(), torch.from_numpy(r_off.view(np.int64)).cuda(),
                            torch.from_numpy(r_len.view(np.int32)).cuda(), d_cb, torch.from_numpy(c_off.view(np.int64)).cuda(),
                            d_len, d_st, torch.tensor(orders, dtype=torch.int32, device="cuda"))
-    for got_b, got_len, got_st in ((cb, c_len, status), (d_cb.cpu().numpy(), d_len.cpu().numpy().view(np.uint32), d_st.cpu().numpy())):
+    for host, got_b, got_len, got_st in ((True, cb, c_len, status),
+                                         (False, d_cb.cpu().numpy(), d_len.cpu().numpy().view(np.uint32), d_st.cpu().numpy())):
         inside = np.zeros(len(cb), bool)
         for i, f in enumerate(orders):
             a = int(c_off[i])
             if i in small:
-                assert got_st[i] == -2, (i, got_st[i])
+                assert got_st[i] == -2, (host, i, got_st[i])
+                # the device writes nothing; the host-buffer call may copy staging bytes, but only into the block's own region
+                if host:
+                    inside[a: a + int(caps[i])] = True
                 continue
             want = oracle.compress_4x8(raw[i], f & 1) if f & hb.ORDER_RANS4x8 else oracle.compress(raw[i], f)
-            assert got_st[i] == 0 and bytes(got_b[a: a + int(got_len[i])]) == want, i
+            assert got_st[i] == 0 and bytes(got_b[a: a + int(got_len[i])]) == want, (host, i)
             inside[a: a + int(bound[i])] = True
-        assert (got_b[~inside] == 0xEE).all(), "a refused block (or a neighbour) wrote outside its region"
+        assert (got_b[~inside] == 0xEE).all(), ("a refused block (or a neighbour) wrote outside its region", host)
     ctx.close()
