@@ -9,7 +9,12 @@ hot path over the whole batch.
 
 * value  : uncompressed GB/s (1e9), inputs and outputs resident in HBM, CUDA-event timed.
 * e2e    : the same batch through the host-buffer C-ABI call (pinned host memory, H2D of the
-           compressed bytes and D2H of the decoded bytes inside the timed region).
+           compressed bytes and D2H of the decoded bytes inside the timed region).  With --gpus N > 1 it is ONE
+           call of hts_b200_uncompress_batch_host_multi over all N devices, made by rank 0 (one host thread +
+           context per device inside the library, copy phases coordinated across devices); the other ranks wait.
+* paths  : the other legs of the path (rank 0): encode / order-1 / 4-way / 4x8, the PACK / RLE / STRIPE transform
+           legs of configs[3], device-resident and end to end; configs[4]'s mixed-flag corpus runs on EVERY rank
+           (65536 / N blocks each: the 64 GiB corpus sharded over the N GPUs).
 * roofline: HBM, algorithmic bytes (compressed read + uncompressed write) over the step time.
 * cpu_baseline / --impl reference: the unmodified reference C (oracle/_ref/libref.so, built from
   /root/reference by oracle/Makefile) decoding the same blocks on all host cores, one block per
@@ -173,7 +178,7 @@ def run_reference(args, rank, world):
     }))
 
 
-def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None):
+def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None, one=None):
     """Device-resident GB/s (uncompressed) of the other hot-path legs on the same 1 MiB quality
     blocks: encode and decode x order-0/1 x X_32/4-way.  Decode inputs come from the encoder under
     test; every leg is checked by a device-side round-trip comparison."""
@@ -191,7 +196,7 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None):
     res = {}
     all_legs = (("o0_x32", 4), ("o1_x32", 5), ("o0_4way", 0), ("o1_4way", 1),
                 ("r4x8_o0", hb.ORDER_RANS4x8), ("r4x8_o1", hb.ORDER_RANS4x8 | 1))
-    for name, f in all_legs:
+    for name, f in ((one,) if one else all_legs):
         if legs is not None and name not in legs:
             continue
         legacy = bool(f & hb.ORDER_RANS4x8)
@@ -238,10 +243,12 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None):
     return res
 
 
-def mixed_leg(ctx, torch, hb, nblk, distinct=128, reps=2):
-    """BASELINE configs[4] scaled to one GPU's share: a mixed-flag corpus (40 % o0, 30 % o1, 10 % X_32 o0,
-    10 % X_32 o1, 5 % PACK/RLE/STRIPE variants, 5 % legacy rANS 4x8; synth.mixed_corpus) of nblk x 1 MiB
-    blocks, encoded and decoded in ONE batched device-resident call per direction."""
+def mixed_leg(ctx, torch, hb, nblk_dec, nblk_enc, distinct=128, reps=2, reduce_max=None):
+    """BASELINE configs[4]: a mixed-flag corpus (40 % o0, 30 % o1, 10 % X_32 o0, 10 % X_32 o1, 5 % PACK/RLE/STRIPE
+    variants, 5 % legacy rANS 4x8; synth.mixed_corpus) of 1 MiB blocks.  Decode: this rank's `nblk_dec` blocks (its
+    share of the 65536-block, 64 GiB corpus) in ONE batched device-resident call, inputs = the GPU encoder's own
+    streams tiled; encode: `nblk_enc` blocks in one call.  reduce_max(t) -> max over ranks (the job is as slow as
+    its slowest GPU).  Returns per-rank figures; the caller aggregates."""
     import numpy as np
     from htscodecs_b200 import synth
     n = BLOCK
@@ -252,57 +259,227 @@ def mixed_leg(ctx, torch, hb, nblk, distinct=128, reps=2):
     lib = hb.load_library()
     cap = max(lib.hts_b200_compress_bound_4x8(n), max(hb.rans_compress_bound_4x16(n, int(f)) for f in set(orders1[meth1 == 0])))
     cap = (cap + 15) // 16 * 16
-    reps_t = (nblk + distinct - 1) // distinct
     stream = torch.cuda.ExternalStream(ctx.stream)
-    d_one = torch.from_numpy(np.concatenate(blocks)).cuda()
-    d_raw = d_one.repeat(reps_t)[: nblk * n].contiguous()
-    del d_one
-    order = torch.from_numpy(np.tile(orders1, reps_t)[:nblk].astype(np.int32)).cuda()
-    method = torch.from_numpy(np.tile(meth1, reps_t)[:nblk].copy()).cuda()
-    raw_off = torch.arange(nblk, dtype=torch.int64, device="cuda") * n
-    raw_len = torch.full((nblk,), n, dtype=torch.int32, device="cuda")
-    status = torch.zeros(nblk, dtype=torch.int32, device="cuda")
-    d_out = torch.empty(nblk * n, dtype=torch.uint8, device="cuda")
-    d_comp = torch.empty(nblk * cap, dtype=torch.uint8, device="cuda")
-    comp_off = torch.arange(nblk, dtype=torch.int64, device="cuda") * cap
-    comp_len = torch.full((nblk,), cap, dtype=torch.int32, device="cuda")
-    out_len = torch.full((nblk,), n, dtype=torch.int32, device="cuda")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reduce_max = reduce_max or (lambda t: t)
+
+    # ---- encode leg (also the source of the decode leg's streams)
+    reps_t = (nblk_enc + distinct - 1) // distinct
+    d_one = torch.from_numpy(np.concatenate(blocks)).cuda()
+    d_raw = d_one.repeat(reps_t)[: nblk_enc * n].contiguous()
+    order = torch.from_numpy(np.tile(orders1, reps_t)[:nblk_enc].astype(np.int32)).cuda()
+    raw_off = torch.arange(nblk_enc, dtype=torch.int64, device="cuda") * n
+    raw_len = torch.full((nblk_enc,), n, dtype=torch.int32, device="cuda")
+    status = torch.zeros(nblk_enc, dtype=torch.int32, device="cuda")
+    d_comp = torch.empty(nblk_enc * cap, dtype=torch.uint8, device="cuda")
+    comp_off = torch.arange(nblk_enc, dtype=torch.int64, device="cuda") * cap
+    comp_len = torch.full((nblk_enc,), cap, dtype=torch.int32, device="cuda")
 
     def enc():
         comp_len.fill_(cap)
         torch.cuda.synchronize()
         e0.record(stream)
-        ctx.compress_batch_dev(nblk, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=False)
+        ctx.compress_batch_dev(nblk_enc, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=False)
         e1.record(stream)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
     enc()
     assert int((status != 0).sum()) == 0, "mixed corpus: encode failed"
-    t_enc = min(enc() for _ in range(reps))
-    in_len = comp_len.clone()
-    csz = int(in_len.to(torch.int64).sum())
+    t_enc = reduce_max(min(enc() for _ in range(reps)))
+    # the distinct streams, packed: the decode leg tiles them
+    clen1 = comp_len[:distinct].cpu().numpy().astype(np.int64)
+    packed = torch.cat([d_comp[i * cap: i * cap + int(clen1[i])] for i in range(distinct)])
+    starts1 = np.concatenate([[0], np.cumsum(clen1)[:-1]])
+    del d_comp, d_raw, comp_off, comp_len, order, raw_off, raw_len, status
+
+    # ---- decode leg
+    reps_d = (nblk_dec + distinct - 1) // distinct
+    d_in = packed.repeat(reps_d)                                          # whole copies of the distinct set
+    per_set = int(clen1.sum())
+    in_off = (np.repeat(np.arange(reps_d, dtype=np.int64) * per_set, distinct) + np.tile(starts1, reps_d))[:nblk_dec]
+    in_len = np.tile(clen1, reps_d)[:nblk_dec]
+    csz = int(in_len.sum())
+    d_in_off = torch.from_numpy(in_off).cuda()
+    d_in_len = torch.from_numpy(in_len.astype(np.int32)).cuda()
+    method = torch.from_numpy(np.tile(meth1, reps_d)[:nblk_dec].copy()).cuda()
+    d_out = torch.empty(nblk_dec * n, dtype=torch.uint8, device="cuda")
+    out_off = torch.arange(nblk_dec, dtype=torch.int64, device="cuda") * n
+    out_len = torch.full((nblk_dec,), n, dtype=torch.int32, device="cuda")
+    status = torch.zeros(nblk_dec, dtype=torch.int32, device="cuda")
 
     def dec():
         out_len.fill_(n)
         torch.cuda.synchronize()
         e0.record(stream)
-        ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, method, sync=False)
+        ctx.uncompress_batch_dev(nblk_dec, d_in, d_in_off, d_in_len, d_out, out_off, out_len, status, method, sync=False)
         e1.record(stream)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
     # first call synchronous: it sizes the context's scratch arena (transform temporaries, large order-1 tables),
     # which an asynchronous call cannot grow (include/htscodecs_b200.h: sync == 0)
-    ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, method, sync=True)
+    ctx.uncompress_batch_dev(nblk_dec, d_in, d_in_off, d_in_len, d_out, out_off, out_len, status, method, sync=True)
     dec()
     assert int((status != 0).sum()) == 0, "mixed corpus: decode failed"
-    assert torch.equal(d_out, d_raw), "mixed corpus: round trip mismatch"
-    t_dec = min(dec() for _ in range(reps))
-    gb = nblk * n / 1e9
-    return {"encode_GBs": round(gb / (t_enc * 1e-3), 1), "decode_GBs": round(gb / (t_dec * 1e-3), 1),
-            "ratio": round(csz / (nblk * n), 4), "blocks": nblk, "distinct_blocks": distinct}
+    for k in (0, nblk_dec // distinct // 2 * distinct, (nblk_dec - distinct) // distinct * distinct):   # three copies of the set
+        assert torch.equal(d_out[k * n:(k + distinct) * n], d_one), "mixed corpus: round trip mismatch"
+    t_dec = reduce_max(min(dec() for _ in range(reps)))
+    del d_in, d_out, d_one, packed
+    torch.cuda.empty_cache()
+    return {"t_enc_ms": t_enc, "t_dec_ms": t_dec, "nblk_enc": nblk_enc, "nblk_dec": nblk_dec,
+            "ratio": round(csz / (nblk_dec * n), 4), "distinct_blocks": distinct}
+
+
+def mixed_e2e(hb, ctx, devs, nblk, distinct=128, reps=2):
+    """configs[4] end to end: `nblk` blocks of the mixed corpus, pinned host buffers, one multi-device decode call."""
+    import numpy as np
+    from htscodecs_b200 import synth
+    n = BLOCK
+    spec = synth.mixed_corpus(distinct, seed=5, size=n, ragged=False)
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        raw = list(ex.map(lambda t: synth.GENERATORS[t[0]](t[1], t[2]), spec))
+    orders = [f | (hb.ORDER_RANS4x8 if meth else 0) for _, _, _, f, meth in spec]
+    comps, st = ctx.compress_many([b.tobytes() for b in raw], orders)
+    assert (st == 0).all(), "mixed e2e: encode failed"
+    in_len = np.array([len(comps[i % distinct]) for i in range(nblk)], np.uint32)
+    in_off = np.zeros(nblk, np.uint64); in_off[1:] = np.cumsum(in_len[:-1].astype(np.uint64))
+    method = np.array([spec[i % distinct][4] for i in range(nblk)], np.uint8)
+    pin_c = hb.PinnedArray(int(in_len.astype(np.uint64).sum()) + 64)
+    for i in range(nblk):
+        pin_c.array[int(in_off[i]): int(in_off[i]) + int(in_len[i])] = np.frombuffer(comps[i % distinct], np.uint8)
+    pin_u = hb.PinnedArray(nblk * n + 64)
+    u_off = np.arange(nblk, dtype=np.uint64) * n
+    status = np.zeros(nblk, np.int32)
+    ts = []
+    for _ in range(reps + 1):
+        out_len = np.full(nblk, n, np.uint32)
+        t0 = time.perf_counter()
+        hb.uncompress_batch_host_multi(devs, nblk, pin_c.array, in_off, in_len, pin_u.array, u_off, out_len, status, method)
+        ts.append(time.perf_counter() - t0)
+    assert (status == 0).all(), "mixed e2e: decode failed"
+    for i in (0, distinct - 1, nblk - 1):
+        assert np.array_equal(pin_u.array[i * n:(i + 1) * n], raw[i % distinct]), "mixed e2e: output differs"
+    return {"e2e_decode_GBs": round(nblk * n / min(ts[1:]) / 1e9, 1), "e2e_blocks": nblk, "e2e_devices": len(devs)}
+
+
+def e2e_leg(hb, devs, comps_by_block, raw_by_block, nblk, flags, reps=2, encode=True, pins=None):
+    """End to end (pinned host buffers -> pinned host buffers) through the multi-device host-buffer C calls for one
+    flag family: decode GB/s and encode GB/s (uncompressed)."""
+    import numpy as np
+    n, distinct = BLOCK, len(raw_by_block)
+    legacy = bool(flags & hb.ORDER_RANS4x8)
+    in_len = np.array([len(comps_by_block[i % distinct]) for i in range(nblk)], np.uint32)
+    in_off = np.zeros(nblk, np.uint64); in_off[1:] = np.cumsum(in_len[:-1].astype(np.uint64))
+    c_bytes = int(in_len.astype(np.uint64).sum())
+    pin_c, pin_u, pin_o = pins                                             # compressed in, raw, compressed out (reused across legs)
+    for i in range(nblk):
+        pin_c.array[int(in_off[i]): int(in_off[i]) + int(in_len[i])] = np.frombuffer(comps_by_block[i % distinct], np.uint8)
+    u_off = np.arange(nblk, dtype=np.uint64) * n
+    status = np.zeros(nblk, np.int32)
+    method = np.full(nblk, 1 if legacy else 0, np.uint8)
+    td = []
+    for _ in range(reps + 1):
+        out_len = np.full(nblk, n, np.uint32)
+        t0 = time.perf_counter()
+        hb.uncompress_batch_host_multi(devs, nblk, pin_c.array, in_off, in_len, pin_u.array, u_off, out_len, status, method)
+        td.append(time.perf_counter() - t0)
+    assert (status == 0).all(), "e2e decode failed"
+    for i in (0, nblk - 1):
+        assert np.array_equal(pin_u.array[i * n:(i + 1) * n], raw_by_block[i % distinct]), "e2e decode differs"
+    res = {"e2e_decode_GBs": round(nblk * n / min(td[1:]) / 1e9, 1)}
+    if encode:
+        lib = hb.load_library()
+        bound = lib.hts_b200_compress_bound_4x8(n) if legacy else hb.rans_compress_bound_4x16(n, flags)
+        cap = (bound + 15) // 16 * 16
+        o_off = np.arange(nblk, dtype=np.uint64) * cap
+        raw_len = np.full(nblk, n, np.uint32)
+        order = np.full(nblk, flags, np.int32)
+        te = []
+        for _ in range(reps + 1):
+            o_len = np.full(nblk, cap, np.uint32)
+            t0 = time.perf_counter()
+            hb.compress_batch_host_multi(devs, nblk, pin_u.array, u_off, raw_len, pin_o.array, o_off, o_len, status, order)
+            te.append(time.perf_counter() - t0)
+        assert (status == 0).all() and bytes(pin_o.array[:int(o_len[0])]) == comps_by_block[0], "e2e encode differs"
+        res["e2e_encode_GBs"] = round(nblk * n / min(te[1:]) / 1e9, 1)
+    return res
+
+
+def extra_legs(ctx, torch, hb, local_rank, nblk):
+    """configs[3] transform legs (device-resident) + every e2e leg + the single-block drop-in latency, on rank 0's GPU."""
+    import ctypes as C
+    import numpy as np
+    from htscodecs_b200 import synth
+    out = {}
+    n = BLOCK
+    # ---- transforms, device-resident: PACK on ACGT, RLE / PACK+RLE on tag data, STRIPE(4) on u32 arrays
+    tl = (("pack_acgt", "acgt", 0x80), ("pack_o1_acgt", "acgt", 0x81), ("rle_tag", "tag", 0x40), ("rle_o1_tag", "tag", 0x41),
+          ("pack_rle_tag", "tag", 0xc0), ("pack_rle_o1_tag", "tag", 0xc1), ("stripe4_u32", "u32", 0x408), ("stripe4_o1_u32", "u32", 0x409),
+          ("pack_x32_acgt", "acgt", 0x84))
+    for name, gen, f in tl:
+        try:
+            blocks = [synth.GENERATORS[gen](i, n) for i in range(16)]
+            out[name] = path_sweep(ctx, torch, hb, blocks, nblk, reps=2, legs=None, one=(name, f))[name]
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": repr(e)[:200]}
+    # ---- end to end, one device, every codec family (qual data)
+    try:
+        distinct = 16
+        raw = [synth.qual_block(i, n) for i in range(distinct)]
+        lib = hb.load_library()
+        capmax = max(lib.hts_b200_compress_bound_4x8(n), hb.rans_compress_bound_4x16(n, 0xc5))
+        pins = (hb.PinnedArray(nblk * n // 2 + 64), hb.PinnedArray(nblk * n + 64), hb.PinnedArray(nblk * ((capmax + 15) // 16 * 16) + 64))
+        for name, f in (("o0_x32", 4), ("o1_x32", 5), ("o0_4way", 0), ("o1_4way", 1), ("r4x8_o0", hb.ORDER_RANS4x8), ("r4x8_o1", hb.ORDER_RANS4x8 | 1)):
+            try:
+                comps, st = ctx.compress_many([b.tobytes() for b in raw], [f] * distinct)
+                assert (st == 0).all()
+                out.setdefault("e2e", {})[name] = e2e_leg(hb, [local_rank], comps, raw, nblk, f, pins=pins)
+            except Exception as e:  # noqa: BLE001
+                out.setdefault("e2e", {})[name] = {"error": repr(e)[:200]}
+        # ---- pointer-array form (what INTEGRATION.md recommends to C callers holding one buffer per block)
+        try:
+            comps, st = ctx.compress_many([b.tobytes() for b in raw], [4] * distinct)
+            m = min(nblk, 1024)
+            ins = [np.frombuffer(comps[i % distinct], np.uint8) for i in range(m)]
+            outs = [np.empty(n, np.uint8) for _ in range(m)]
+            in_ptrs = (C.c_void_p * m)(*[a.ctypes.data for a in ins])
+            out_ptrs = (C.c_void_p * m)(*[a.ctypes.data for a in outs])
+            isz = np.array([a.size for a in ins], np.uint32)
+            stt = np.zeros(m, np.int32)
+            lib.rans4x16_uncompress_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            ts = []
+            for _ in range(3):
+                osz = np.full(m, n, np.uint32)
+                t0 = time.perf_counter()
+                rc = lib.rans4x16_uncompress_batch(ctx.h, m, C.cast(in_ptrs, C.c_void_p), isz.ctypes.data, C.cast(out_ptrs, C.c_void_p), osz.ctypes.data, stt.ctypes.data)
+                ts.append(time.perf_counter() - t0)
+                assert rc == 0 and (stt == 0).all()
+            assert np.array_equal(outs[m - 1], raw[(m - 1) % distinct])
+            out.setdefault("e2e", {})["ptr_array_o0_x32"] = {"e2e_decode_GBs": round(m * n / min(ts[1:]) / 1e9, 1), "blocks": m,
+                                                              "call": "rans4x16_uncompress_batch (pageable per-block buffers)"}
+        except Exception as e:  # noqa: BLE001
+            out.setdefault("e2e", {})["ptr_array_o0_x32"] = {"error": repr(e)[:200]}
+        del pins
+    except Exception as e:  # noqa: BLE001
+        out["e2e"] = {"error": repr(e)[:200]}
+    # ---- single-block drop-in latency (the call tokenise_name3.c:1222,1240 would make), median of 20
+    try:
+        lat = {}
+        for label, size in (("100KB", 100_000), ("1MiB", n)):
+            d = synth.qual_block(7, size).tobytes()
+            for oname, f in (("o0", 0), ("o1", 1)):
+                c = hb.rans_compress_4x16(d, f)
+                assert hb.rans_uncompress_4x16(c) == d
+                te, td = [], []
+                for _ in range(20):
+                    t0 = time.perf_counter(); hb.rans_compress_4x16(d, f); te.append(time.perf_counter() - t0)
+                    t0 = time.perf_counter(); hb.rans_uncompress_4x16(c); td.append(time.perf_counter() - t0)
+                lat[f"{label}_{oname}"] = {"compress_us": round(1e6 * float(np.median(te)), 1), "uncompress_us": round(1e6 * float(np.median(td)), 1)}
+        out["dropin_latency"] = lat
+    except Exception as e:  # noqa: BLE001
+        out["dropin_latency"] = {"error": repr(e)[:200]}
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -310,21 +487,28 @@ def run_ours(args, rank, world, local_rank):
     import htscodecs_b200 as hb
 
     torch.cuda.set_device(local_rank)
-    dist = None
+    dist = cpu_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")          # host-side waits (no spinning kernel on the idle GPUs)
+
+    def cpu_barrier():
+        if dist is not None:
+            dist.barrier(group=cpu_group)
+
+    def reduce_max(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # one nvidia-smi poller per job, not per rank: eight of them at 50 Hz contend on the driver and
     # slow every rank's copies (the GPUs of one box share clocks policy; rank 0's is reported)
     sampler = ClockSampler(local_rank if rank == 0 else None)
     sampler.start()                                          # nvidia-smi needs ~1 s before its first sample
     ctx = hb.Context(local_rank)
-    # host link policy of the e2e leg: full duplex (H2D overlapped with D2H).  On the 8-GPU box the e2e
-    # figure is set by the host link itself (tools/numa_probe.py: 304 GB/s aggregate D2H alone, 134 GB/s
-    # once a quarter as many H2D bytes are in flight); sending inputs first ("half") measured the same.
-    duplex = "full" if args.duplex == "auto" else args.duplex
-    ctx.set_copy_duplex(duplex == "full")
     nblk, distinct = args.blocks, min(args.distinct, args.blocks)
     blocks = make_blocks(distinct, rank)
     # compressed inputs: X_32 order-0 streams made by the encoder under test (the GPU encoder; its
@@ -338,13 +522,11 @@ def run_ours(args, rank, world, local_rank):
     u_bytes = nblk * BLOCK
     out_off = np.arange(nblk, dtype=np.uint64) * BLOCK
 
-    # pinned host copies (e2e) and device-resident copies (value)
-    pin_in = hb.PinnedArray(c_bytes + 64)
+    # device-resident copies (value)
+    h_in = np.empty(c_bytes + 64, np.uint8)
     for i in range(nblk):
-        pin_in.array[int(in_off[i]): int(in_off[i]) + int(in_len[i])] = np.frombuffer(comps[i % distinct], np.uint8)
-    pin_out = hb.PinnedArray(u_bytes + 64)
-    d_in = torch.empty(c_bytes + 64, dtype=torch.uint8, device="cuda")
-    d_in[: c_bytes].copy_(torch.from_numpy(pin_in.array[:c_bytes]))
+        h_in[int(in_off[i]): int(in_off[i]) + int(in_len[i])] = np.frombuffer(comps[i % distinct], np.uint8)
+    d_in = torch.from_numpy(h_in).cuda()
     d_in_off = torch.from_numpy(in_off.view(np.int64)).cuda()
     d_in_len = torch.from_numpy(in_len.view(np.int32)).cuda()
     d_out = torch.empty(u_bytes + 64, dtype=torch.uint8, device="cuda")
@@ -385,63 +567,121 @@ def run_ours(args, rank, world, local_rank):
         step_dev()
     ev1.record(stream)
     barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms = reduce_max(ev0.elapsed_time(ev1))
     launches = ctx.launches - l0
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     ms_per_step = ms / args.steps
     value = world * u_bytes / (ms_per_step * 1e-3) / 1e9
-
-    # ---- timed: end to end through the host-buffer C-ABI call
-    h_out_len = np.full(nblk, BLOCK, np.uint32)
-    h_status = np.zeros(nblk, np.int32)
-
-    def step_host():
-        h_out_len[:] = BLOCK
-        ctx.uncompress_batch_host(nblk, pin_in.array, in_off, in_len, pin_out.array, out_off, h_out_len, h_status)
-
-    e2e_steps = max(1, min(args.steps, 5))
-    if args.skip_e2e:
-        e2e_steps, e2e_s = 0, float("inf")
-    else:
-        for _ in range(2):
-            step_host()
-        assert (h_status == 0).all()
-        for i in (0, distinct - 1, nblk - 1):
-            assert np.array_equal(pin_out.array[i * BLOCK:(i + 1) * BLOCK], blocks[i % distinct]), "e2e output differs"
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_host()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_val = world * u_bytes / e2e_s / 1e9
-    # host-side gather of the per-block results of every rank (the only cross-rank step of the path)
+    # host-side gather of the per-block results of every rank (the only cross-rank step of the device-resident path)
     from htscodecs_b200 import shard
     ranges = shard.partition_blocks([BLOCK] * (world * nblk), world)
     assert ranges[rank] == (rank * nblk, (rank + 1) * nblk)
     all_len, all_status = shard.gather_results(d_out_len.cpu().numpy().view(np.uint32), d_status.cpu().numpy(),
                                                ranges, rank, world, dist, torch.device("cuda", local_rank))
     assert (all_status == 0).all() and (all_len == BLOCK).all(), "a rank reported decode errors"
+
+    # ---- timed: end to end through the host-buffer C-ABI call.  One call for the whole job: N devices, world x nblk
+    # blocks in rank 0's pinned buffers (the other ranks wait on the host); the library partitions the blocks,
+    # runs one thread + context per device and coordinates the copy phases across devices.
+    e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": world * c_bytes, "d2h_bytes_per_step": world * u_bytes,
+           "steps": 0}
+    e2e_stages = None
+    cpu_barrier()
+    if rank == 0 and not args.skip_e2e:
+        ndev = torch.cuda.device_count()
+        devs = list(range(world)) if ndev >= world else [local_rank]
+        tot = nblk * len(devs)
+        g_in_len = np.tile(in_len, len(devs))
+        g_in_off = np.zeros(tot, np.uint64)
+        g_in_off[1:] = np.cumsum(g_in_len[:-1].astype(np.uint64))
+        pin_in = hb.PinnedArray(len(devs) * c_bytes + 64)
+        for d in range(len(devs)):
+            pin_in.array[d * c_bytes:(d + 1) * c_bytes] = h_in[:c_bytes]
+        pin_out = hb.PinnedArray(tot * BLOCK + 64)
+        g_out_off = np.arange(tot, dtype=np.uint64) * BLOCK
+        h_out_len = np.full(tot, BLOCK, np.uint32)
+        h_status = np.zeros(tot, np.int32)
+        if args.phased != "auto":
+            hb.multi_set_phased(args.phased == "on")
+
+        def step_host():
+            h_out_len[:] = BLOCK
+            hb.uncompress_batch_host_multi(devs, tot, pin_in.array, g_in_off, g_in_len, pin_out.array, g_out_off, h_out_len, h_status)
+
+        ml0 = hb.multi_launch_count()
+        for _ in range(2):
+            step_host()
+        assert (h_status == 0).all()
+        for i in (0, distinct - 1, nblk - 1, tot - 1):
+            assert np.array_equal(pin_out.array[i * BLOCK:(i + 1) * BLOCK], blocks[(i % nblk) % distinct]), "e2e output differs"
+        e2e_steps = max(1, min(args.steps, 5 if world == 1 else 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e_stages = hb.multi_last_stats()
+        e2e.update({"value": tot * BLOCK / e2e_s / 1e9, "steps": e2e_steps, "devices": devs,
+                    "h2d_bytes_per_step": len(devs) * c_bytes, "d2h_bytes_per_step": tot * BLOCK,
+                    "api": "hts_b200_uncompress_batch_host_multi (one call, one host thread + context per device, "
+                           + ("copy phases coordinated across devices)" if len(devs) > 1 else "single device: full-duplex chunk pipeline)"),
+                    "gpu_launches_per_step": (hb.multi_launch_count() - ml0) // (2 + e2e_steps),
+                    "timer": "host perf_counter around the synchronous call"})
+        del pin_in, pin_out
+    cpu_barrier()
     clocks = sampler.stop()
-    paths = None
-    if rank == 0 and not args.skip_paths:
-        del d_in, d_out
+    del d_in, d_out
+    torch.cuda.empty_cache()
+
+    # ---- configs[4]: the mixed-flag corpus, sharded: this rank's share of the 65536-block (64 GiB) corpus
+    mixed = None
+    if not args.skip_mixed:
+        free = torch.cuda.mem_get_info()[0]
+        share = max(128, args.mixed_blocks // world)
+        share = max(128, min(share, int(free * 0.75 / (BLOCK * 1.32)) // 128 * 128))   # output + compressed input must fit
+        ncalls = [0]
+
+        def counted_max(v):
+            ncalls[0] += 1
+            return reduce_max(v)
+
+        err = None
+        try:
+            m = mixed_leg(ctx, torch, hb, share, min(share, 8192), reduce_max=counted_max)
+        except Exception as e:  # noqa: BLE001
+            err = repr(e)[:300]
+        for _ in range(2 - ncalls[0]):                                             # keep the ranks' collectives aligned
+            reduce_max(0.0)
+        if reduce_max(1.0 if err else 0.0) > 0:
+            mixed = {"error": err or "another rank failed"}
+        else:
+            gb = BLOCK / 1e9
+            mixed = {"decode_GBs": round(world * m["nblk_dec"] * gb / (m["t_dec_ms"] * 1e-3), 1),
+                     "encode_GBs": round(world * m["nblk_enc"] * gb / (m["t_enc_ms"] * 1e-3), 1),
+                     "decode_blocks_per_gpu": m["nblk_dec"], "encode_blocks_per_gpu": m["nblk_enc"],
+                     "corpus_GiB": round(world * m["nblk_dec"] / 1024, 1), "ratio": m["ratio"], "distinct_blocks": m["distinct_blocks"],
+                     "note": "whole-job GB/s over all ranks (max rank time); device-resident, one batched call per rank"}
         torch.cuda.empty_cache()
+        cpu_barrier()
+        if rank == 0 and "error" not in mixed and not args.skip_e2e:
+            try:
+                ndev = torch.cuda.device_count()
+                mixed.update(mixed_e2e(hb, ctx, list(range(world)) if ndev >= world else [local_rank], 1024 * max(world, 2)))
+            except Exception as e:  # noqa: BLE001
+                mixed["e2e_error"] = repr(e)[:300]
+    paths = None
+    cpu_barrier()
+    if rank == 0 and not args.skip_paths:
         paths = path_sweep(ctx, torch, hb, blocks, min(nblk, 4096))
         # a 4-way stream is 4 lanes of serial work, so its throughput grows with the batch until the SMs
-        # are full: the same legs at 16384 blocks (above ~5000 blocks the planner switches small-alphabet
-        # 4-way streams to the high-occupancy kernel variants)
+        # are full: the same legs at 16384 blocks
         if torch.cuda.get_device_properties(local_rank).total_memory > 100 * 2**30:
             big = path_sweep(ctx, torch, hb, blocks, 16384, reps=2, legs=("o0_4way", "o1_4way"))
             paths.update({k + "_16384blk": v for k, v in big.items()})
-        paths["mixed_corpus"] = mixed_leg(ctx, torch, hb, min(nblk, 4096))
+        paths.update(extra_legs(ctx, torch, hb, local_rank, min(nblk, 4096)))
+    if mixed is not None and paths is not None:
+        paths["mixed_corpus"] = mixed
+    elif mixed is not None:
+        paths = {"mixed_corpus": mixed}
+    cpu_barrier()
 
     if rank != 0:
         if dist is not None:
@@ -473,24 +713,23 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/u32", "data": "synthetic",
         "config": {"workload": f"batched decode of {nblk} x 1 MiB Illumina-binned quality blocks per GPU, "
-                               "rANS Nx16 order-0 X_32 (BASELINE configs[1])",
+                               "rANS Nx16 order-0 X_32 (BASELINE configs[1]); X_32 is parity-unpinned: the v1.1 reference has "
+                               "no 32-way code, the stream is its N = 32 generalisation (DESIGN.md section 6)",
                    "blocks_per_gpu": nblk, "block_bytes": BLOCK, "distinct_blocks": distinct,
                    "compressed_bytes_per_gpu": c_bytes, "ratio": c_bytes / u_bytes,
                    "l2": "inputs+outputs (%.1f GiB) exceed the 126 MB L2; no flush needed" % ((c_bytes + u_bytes) / 2**30),
-                   "parallelism": f"blocks sharded over {world} GPU(s), no collective",
-                   "e2e_copy_duplex": duplex},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": c_bytes, "d2h_bytes_per_step": u_bytes,
-                "steps": e2e_steps, "timer": "host perf_counter around hts_b200_uncompress_batch_host (synchronous)"},
+                   "parallelism": f"blocks sharded over {world} GPU(s), no collective"},
+        "e2e": e2e, "e2e_stages": e2e_stages,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                      "kernel": "dec_o0_kernel<32,false>",
                      "note": "algorithmic bytes = compressed read + uncompressed write per step; duration = "
-                             "CUDA-event step time on the context's stream (dec_o0_kernel<32,false> is 99.0 % of it, "
-                             "profiles/r01_launches_decode.csv), so frac is a slight lower bound",
-                     "limiter": "not HBM: the per-state serial chain (~260 cycles/step) x 28 resident streams/SM; ncu: "
-                                "shared-memory LSU wavefronts 86 % of peak, issue slots 65 %, DRAM 13 % "
+                             "CUDA-event step time on the context's stream (dec_o0_kernel<32,false> is 99 % of it, "
+                             "profiles/), so frac is a slight lower bound",
+                     "limiter": "not HBM: shared-memory LSU wavefronts (86 % of peak at 28 resident warps/SM; an occupancy sweep "
+                                "shows the rate saturating from 24 warps/SM) on top of a ~180-cycle serial chain per step "
                                 "(profiles/README.md)"},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": cpu_kind, "sample": cpu_sample},
         "paths": paths,
@@ -512,7 +751,10 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the CPU baseline leg")
     ap.add_argument("--skip-paths", action="store_true", help="skip the extra encode / order-1 / 4-way legs")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget for the reference leg")
-    ap.add_argument("--duplex", default="auto", choices=["auto", "full", "half"], help="host copy policy of the e2e leg")
+    ap.add_argument("--skip-mixed", action="store_true", help="skip the mixed-flag corpus leg (configs[4])")
+    ap.add_argument("--mixed-blocks", type=int, default=65536, help="blocks of the mixed corpus over ALL GPUs (64 GiB)")
+    ap.add_argument("--phased", default="auto", choices=["auto", "on", "off"],
+                    help="e2e leg with N > 1: coordinate the copy phases across devices (default: the library's choice)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

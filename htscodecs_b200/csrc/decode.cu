@@ -1068,6 +1068,10 @@ template <int NWAY, int SZ = 0> struct O1Smem {               // SZ: 0 regular, 
     static constexpr bool SMALL = SZ == 1;                    //     3 / 4: rows of 8 / 16 entries for the register-table kernels
     static constexpr bool REG = SZ >= 3;
     static constexpr int REG_NS = SZ == 3 ? 8 : 16;
+    // a register-table row: REG_NS entries, then its entry count, padded to REG_NS * 4 + 16 bytes -- rows then start in
+    // all eight 16-byte bank groups (48 / 80-byte stride) instead of two or four, which is what the 128-bit row
+    // loads of lanes sitting in different contexts collide on
+    static constexpr int REG_ROW = REG_NS * 4 + 16;
     static constexpr int UNRANK = 0, RANK = 256;
     // the frequency scratch is only live during set-up; X_32 (1 KB ring) and the small 4-way variants
     // (alphabets of <= 16 symbols, 256-byte ring) let it share the word ring's memory
@@ -1078,7 +1082,7 @@ template <int NWAY, int SZ = 0> struct O1Smem {               // SZ: 0 regular, 
     // 4-way: 3072 B per group (<= 19 symbols, 40 groups / SM), SMALL 1024 B (<= 9 symbols, 120 groups / SM),
     // medium 12544 B (<= 47 symbols, 16 groups / SM), REG ns x ns entries (256 B / 1 KB)
     static constexpr int TAB = (NWAY == 32) ? (SMALL ? (int)O1_SMALL_TAB : 12992)
-                               : REG ? REG_NS * REG_NS * 4
+                               : REG ? REG_NS * REG_ROW
                                      : (SMALL ? 1024 : SZ == 2 ? (int)O1_TAB4M : (int)O1_TAB4);
     static constexpr int FTMP_ENTRIES = OVERLAY ? GroupCfg<NWAY>::RING / 4 : 256;
     static constexpr int STRIDE = TABO + TAB;                        // multiple of 16
@@ -1092,6 +1096,7 @@ struct O1Tables {
     uint32_t ns, shift;
     uint32_t row_off;       // entries start this far into a context block (64: behind the coarse index; 0: no index)
     uint32_t cshift;        // position of an entry's last-slot field (20; register-table kernels: 32 - shift)
+    uint32_t cnt_off;       // register-table rows: the row's entry count is stored at this offset (0: not stored)
 };
 
 // Group-cooperative: frequencies of one context (shared u32 array F, indexed by rank, `ns`
@@ -1123,6 +1128,7 @@ __device__ bool build_o1_row_compact(const Grp<NWAY>& G, uint32_t F, const O1Tab
     uint8_t* gcrs = T.g_tabs + (size_t)ctx * T.bstride;             // global form
     uint32_t* grow = reinterpret_cast<uint32_t*>(gcrs + 64);
     const bool coarse = T.row_off != 0;
+    if (T.cnt_off && G.glane == 0) sts_u32(crs + T.cnt_off, nzt);
     for (uint32_t k = 0; k < K; k++) {
         const uint32_t r = r0 + k;
         if (r >= ns) break;
@@ -1218,16 +1224,17 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     O1Tables T;
     T.ns = ns; T.shift = shift;
     T.g_tabs = nullptr;
-    T.bstride = S::REG ? 4u * S::REG_NS : 64 + 4 * (ns + 3);
+    T.bstride = S::REG ? (uint32_t)S::REG_ROW : 64 + 4 * (ns + 3);
     T.row_off = S::REG ? 0u : 64u;
     T.cshift = S::REG ? 32u - shift : 20u;
+    T.cnt_off = S::REG ? 4u * S::REG_NS : 0u;
     T.tabs = tabs;
     T.compact = S::REG ? 1u : ((o1_compact_bytes(ns) <= (uint32_t)S::TAB) ? 1u : 0u);
     if (S::REG && ns > (uint32_t)S::REG_NS) return ST_INTERNAL;          // (the planner counts the alphabet before routing here)
     const uint32_t nwords = ns * (T.bstride / 4);
     if (T.compact) {
         for (uint32_t k = G.glane; k < nwords; k += NWAY)                    // coarse: 0, entries: sentinels
-            sts_u32(tabs + 4 * k, (!S::REG && (k % (T.bstride / 4)) < 16) ? 0u : O1_SENTINEL);
+            sts_u32(tabs + 4 * k, (S::REG ? (k % (T.bstride / 4)) >= (uint32_t)S::REG_NS : (k % (T.bstride / 4)) < 16) ? 0u : O1_SENTINEL);
     } else {
         uint8_t* a = nullptr;
         if (G.glane == 0) a = arena_alloc(W, (uint64_t)nwords * 4);
@@ -1297,6 +1304,16 @@ __device__ int32_t o1_setup(const Grp<NWAY>& G, DecWork* W, const DecJob& job, u
     }
     __threadfence_block();
     G.sync();
+    if (S::REG && S::REG_NS == 16) {
+        // an entry also tells whether the row of ITS symbol (the next context) holds more than 8 entries: only then
+        // does the decode loop fetch the row's second half (bit 16; ranks are < 16 here)
+        for (uint32_t k = G.glane; k < ns * 16u; k += NWAY) {
+            const uint32_t a = tabs + (k >> 4) * T.bstride + 4 * (k & 15u);
+            const uint32_t e = lds_u32(a);
+            if (lds_u32(tabs + ((e >> 12) & 15u) * T.bstride + T.cnt_off) > 8u) sts_u32(a, e | 0x10000u);
+        }
+        G.sync();
+    }
 
     // ---- states
     const uint8_t* sp = nullptr;
@@ -1476,7 +1493,7 @@ __global__ void __launch_bounds__(32, (SZ == 1 && NWAY == 32) ? 28 : 1) dec_o1_k
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         O1Tables T;
         T.compact = 1; T.tabs = base + S::TABO; T.bstride = 0;
-        T.g_tabs = nullptr; T.ns = 1; T.shift = 12; T.row_off = 64; T.cshift = 20;
+        T.g_tabs = nullptr; T.ns = 1; T.shift = 12; T.row_off = 64; T.cshift = 20; T.cnt_off = 0;
         uint32_t R = 0, ctx0 = 0;
         const uint8_t* first_word = nullptr;
         bool ok = false;
@@ -1538,6 +1555,35 @@ __device__ __forceinline__ Win win_load(uint32_t ring, uint32_t head) {
     return w;
 }
 
+// The same window without a shared-memory round trip between the previous step's ballot and this step's selection
+// (AHEAD): the 20 bytes from the word at or below the PREVIOUS read position are fetched a step early -- the position
+// can only have advanced by 0 .. 8 bytes since -- and the window is cut out of them once the advance is known.
+struct Chunk { uint32_t w0, w1, w2, w3, w4, base; };
+__device__ __forceinline__ Chunk chunk_load(uint32_t ring, uint32_t head) {
+    const uint32_t a = ring + (head & 252u);
+    Chunk c;
+    c.w0 = lds_u32(a); c.w1 = lds_u32(a + 4); c.w2 = lds_u32(a + 8); c.w3 = lds_u32(a + 12); c.w4 = lds_u32(a + 16);
+    c.base = head & ~3u;
+    return c;
+}
+__device__ __forceinline__ Win chunk_window(const Chunk& c, uint32_t head) {
+    const uint32_t s = head - c.base;                        // 0 .. 11
+    const uint32_t sh = (s & 3u) * 8u;
+    const uint32_t f0 = __funnelshift_r(c.w0, c.w1, sh), f1 = __funnelshift_r(c.w1, c.w2, sh);
+    const uint32_t f2 = __funnelshift_r(c.w2, c.w3, sh), f3 = __funnelshift_r(c.w3, c.w4, sh);
+    Win w;
+    w.lo = s < 4u ? f0 : (s < 8u ? f1 : f2);
+    w.hi = s < 4u ? f1 : (s < 8u ? f2 : f3);
+    return w;
+}
+// AHEAD ? (window of this step from the chunk fetched last step; fetch the next chunk) : plain window load
+template <bool AHEAD> __device__ __forceinline__ Win next_window(Chunk& c, uint32_t ring, uint32_t head) {
+    if (!AHEAD) return win_load(ring, head);
+    const Win w = chunk_window(c, head);
+    c = chunk_load(ring, head);
+    return w;
+}
+
 // Renormalise every lane of the warp (rANS_word.h:356-410 / rANS_byte.h:435-551) from its group's window.
 // p: this lane's state `x` is below the lower bound (and the lane is active).  Advances `head`.
 template <bool BYTE>
@@ -1578,17 +1624,24 @@ template <> __device__ __forceinline__ uint32_t reg_search<16>(const uint32_t (&
     return reg_search<8>(h, M);
 }
 
-template <int NS> __device__ __forceinline__ void load_row(uint32_t (&e)[NS], uint32_t addr) {
+// Entries of one row into registers.  NS = 16: the second half only when `lng` (the row holds more than 8 entries),
+// else sentinels -- binned qualities have 9 contexts (symbol 0 is forced into the alphabet) of at most 8 symbols.
+template <int NS> __device__ __forceinline__ void load_row(uint32_t (&e)[NS], uint32_t addr, uint32_t lng = 1u) {
 #pragma unroll
     for (int k = 0; k < NS; k += 4) {
-        uint4 v;
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr + 4 * k));
+        uint4 v = make_uint4(O1_SENTINEL, O1_SENTINEL, O1_SENTINEL, O1_SENTINEL);
+        if (k < 8)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr + 4 * k));
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+                         : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "r"(addr + 4 * k), "r"(lng));
         e[k] = v.x; e[k + 1] = v.y; e[k + 2] = v.z; e[k + 3] = v.w;
     }
 }
 
-// One decode step from a register row.  Returns the entry's symbol / rank field; x becomes the new state before
-// renormalisation, *p whether it must be renormalised.  shift / sh32 = 32 - shift are per-lane values.
+// One decode step from a register row.  Returns the entry (symbol / rank in bits 12.., long-row flag in bit 16 for
+// order 1); x becomes the new state before renormalisation, *p whether it must be renormalised.  shift / sh32 =
+// 32 - shift are per-lane values.
 template <int NS, bool BYTE>
 __device__ __forceinline__ uint32_t reg_symbol(uint32_t& x, const uint32_t (&E)[NS], uint32_t shift, uint32_t sh32, uint32_t mask, bool* p) {
     constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
@@ -1599,7 +1652,7 @@ __device__ __forceinline__ uint32_t reg_symbol(uint32_t& x, const uint32_t (&E)[
     const uint32_t X = (e & 0xfffu) * (q + 1u) + (q + m);
     *p = X < last + L;
     x = X - last;
-    return (e >> 12) & 0xffu;
+    return e;
 }
 
 struct RegSmem0 {            // order 0: per group [entries NS x 4 | ring 256 + 64 mirror]
@@ -1655,7 +1708,7 @@ __device__ bool o0r_setup(const Grp<4>& G, const DecJob& job, uint32_t gsm, uint
     return true;
 }
 
-template <int NS, bool BYTE>
+template <int NS, bool BYTE, bool AHEAD>
 __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status, uint32_t kind) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const Grp<4> G;
@@ -1693,14 +1746,15 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
         const uint32_t maxit = __reduce_max_sync(0xffffffffu, iters), minit = __reduce_min_sync(0xffffffffu, iters);
         uint8_t* op = job.out + G.glane;
         uint32_t i = 0;
+        Chunk ch = chunk_load(ring.ring, ring.head);
         const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(job.out) & 3) == 0);
         for (; i + 4 <= minit; i += 4) {                     // every lane of the warp active: four steps to a ring check
             uint32_t w = 0;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const Win win = win_load(ring.ring, ring.head);
+                const Win win = next_window<AHEAD>(ch, ring.ring, ring.head);
                 bool p;
-                const uint32_t sy = reg_symbol<NS, BYTE>(R, E, 12u, 20u, 0xfffu, &p);
+                const uint32_t sy = (reg_symbol<NS, BYTE>(R, E, 12u, 20u, 0xfffu, &p) >> 12) & 0xffu;
                 w |= sy << (8 * u);
                 R = win_renorm<BYTE>(R, p, win, ring.head, lt4, G.gshift);
             }
@@ -1714,10 +1768,10 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
         }
         for (; i < maxit; i++) {
             const bool act = i < iters;
-            const Win win = win_load(ring.ring, ring.head);
+            const Win win = next_window<AHEAD>(ch, ring.ring, ring.head);
             uint32_t x = R;
             bool p;
-            const uint32_t sy = reg_symbol<NS, BYTE>(x, E, 12u, 20u, 0xfffu, &p);
+            const uint32_t sy = (reg_symbol<NS, BYTE>(x, E, 12u, 20u, 0xfffu, &p) >> 12) & 0xffu;
             if (act) { R = x; *op = (uint8_t)sy; op += 4; }
             R = win_renorm<BYTE>(R, act && p, win, ring.head, lt4, G.gshift);
             ring.advance(G.glane, act);
@@ -1731,11 +1785,11 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
 }
 
 // Order 1: the row of the lane's current context in registers; the next row is fetched the moment the symbol is known.
-template <int NS, bool BYTE>
+template <int NS, bool BYTE, bool AHEAD>
 __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status, uint32_t kind) {
     constexpr int SZ = NS == 8 ? 3 : 4;
     using S = O1Smem<4, SZ>;
-    constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
+    constexpr uint32_t RS = S::REG_ROW;                   // bytes per row
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const Grp<4> G;
     uint8_t* gsm = smem_raw + G.g * S::STRIDE;
@@ -1754,7 +1808,7 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
         const bool active = ji < njobs;
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         O1Tables T;
-        T.compact = 1; T.tabs = rows; T.bstride = 4 * NS; T.g_tabs = nullptr; T.ns = 1; T.shift = 12; T.row_off = 0; T.cshift = 20;
+        T.compact = 1; T.tabs = rows; T.bstride = RS; T.g_tabs = nullptr; T.ns = 1; T.shift = 12; T.row_off = 0; T.cshift = 20; T.cnt_off = 4 * NS;
         uint32_t R = 0, ctx0 = 0;
         const uint8_t* first_word = nullptr;
         bool ok = false;
@@ -1764,7 +1818,7 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
             ok = st == ST_OK;
             if (!ok && G.glane == 0) set_status(status, job.blk, st);
         }
-        if (!ok) for (uint32_t k = G.glane; k < (uint32_t)NS; k += 4) sts_u32(rows + 4 * k, O1_SENTINEL);   // a harmless row 0
+        if (!ok) for (uint32_t k = G.glane; k <= (uint32_t)NS; k += 4) sts_u32(rows + 4 * k, k < (uint32_t)NS ? O1_SENTINEL : 0u);   // a harmless row 0
         __syncwarp();
         WordRing<4> ring;
         ring.init(first_word, job.in + job.in_len, base + S::RINGO, G, ok, true);
@@ -1783,7 +1837,13 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
             return ((r & 8u) ? hi : lo) & 0xffu;
         };
         uint32_t E[NS];
-        load_row<NS>(E, rows + (ok ? ctx0 : 0u) * (4 * NS));
+        {
+            const uint32_t r0a = rows + (ok ? ctx0 : 0u) * RS;
+            load_row<NS>(E, r0a, NS == 16 ? (uint32_t)(lds_u32(r0a + 4 * NS) > 8u) : 1u);
+        }
+        Chunk ch = chunk_load(ring.ring, ring.head);
+        // next row: rank in bits 12-15 of the entry, "more than 8 entries" in bit 16
+        auto fetch_row = [&](uint32_t e) { load_row<NS>(E, rows + ((e >> 12) & 15u) * RS, e & 0x10000u); };
         ByteSink sink;
         uint8_t* const op0 = job.out + (size_t)G.glane * seg;
         sink.init(op0);
@@ -1794,11 +1854,11 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
                 uint32_t pack = 0;
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const Win win = win_load(ring.ring, ring.head);
+                    const Win win = next_window<AHEAD>(ch, ring.ring, ring.head);
                     bool p;
-                    const uint32_t r = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
-                    load_row<NS>(E, rows + r * (4 * NS));
-                    pack |= unrk(r) << (8 * u);
+                    const uint32_t e = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
+                    fetch_row(e);
+                    pack |= unrk((e >> 12) & 15u) << (8 * u);
                     R = win_renorm<BYTE>(R, p, win, ring.head, lt4, G.gshift);
                 }
                 sink.put4(pack);
@@ -1808,11 +1868,11 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
             for (; i + 4 <= minit; i += 4) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const Win win = win_load(ring.ring, ring.head);
+                    const Win win = next_window<AHEAD>(ch, ring.ring, ring.head);
                     bool p;
-                    const uint32_t r = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
-                    load_row<NS>(E, rows + r * (4 * NS));
-                    sink.put(unrk(r));
+                    const uint32_t e = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
+                    fetch_row(e);
+                    sink.put(unrk((e >> 12) & 15u));
                     R = win_renorm<BYTE>(R, p, win, ring.head, lt4, G.gshift);
                 }
                 ring.advance(G.glane, true);
@@ -1820,18 +1880,17 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
         }
         for (; i < maxit; i++) {
             const bool act = i < mine;
-            const Win win = win_load(ring.ring, ring.head);
+            const Win win = next_window<AHEAD>(ch, ring.ring, ring.head);
             bool p = false;
             if (act) {
-                const uint32_t r = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
-                load_row<NS>(E, rows + r * (4 * NS));
-                sink.put(unrk(r));
+                const uint32_t e = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
+                fetch_row(e);
+                sink.put(unrk((e >> 12) & 15u));
             }
             R = win_renorm<BYTE>(R, act && p, win, ring.head, lt4, G.gshift);
             ring.advance(G.glane, i < group_steps);
         }
         sink.finish();
-        (void)L;
         __syncwarp();
     }
 }
@@ -2155,14 +2214,23 @@ int decode_init(int device) {
     persistent_setup(JK_O1_32,  dec_o1_kernel<32, false, 0>, O1Smem<32>::TOTAL, 32);
     persistent_setup(JK_O1_32S, dec_o1_kernel<32, false, 1>,  O1Smem<32, 1>::TOTAL, 32);
     persistent_setup(JK_O1_4,   dec_o1_kernel<4, false, 0>,  O1Smem<4>::TOTAL, 32);
-    persistent_setup(JK_O0_4R8,   dec_o0r_kernel<8, false>,  RegSmem0::TOTAL, 32);
-    persistent_setup(JK_O0_4R16,  dec_o0r_kernel<16, false>, RegSmem0::TOTAL, 32);
-    persistent_setup(JK_R8_O0R8,  dec_o0r_kernel<8, true>,   RegSmem0::TOTAL, 32);
-    persistent_setup(JK_R8_O0R16, dec_o0r_kernel<16, true>,  RegSmem0::TOTAL, 32);
-    persistent_setup(JK_O1_4R8,   dec_o1r_kernel<8, false>,  O1Smem<4, 3>::TOTAL, 32);
-    persistent_setup(JK_O1_4R16,  dec_o1r_kernel<16, false>, O1Smem<4, 4>::TOTAL, 32);
-    persistent_setup(JK_R8_O1R8,  dec_o1r_kernel<8, true>,   O1Smem<4, 3>::TOTAL, 32);
-    persistent_setup(JK_R8_O1R16, dec_o1r_kernel<16, true>,  O1Smem<4, 4>::TOTAL, 32);
+    // (the AHEAD twins share their kind's shared-memory size; the occupancy recorded is the plain variant's)
+    persistent_setup(JK_O0_4R8,   dec_o0r_kernel<8, false, true>,  RegSmem0::TOTAL, 32);
+    persistent_setup(JK_O0_4R16,  dec_o0r_kernel<16, false, true>, RegSmem0::TOTAL, 32);
+    persistent_setup(JK_R8_O0R8,  dec_o0r_kernel<8, true, true>,   RegSmem0::TOTAL, 32);
+    persistent_setup(JK_R8_O0R16, dec_o0r_kernel<16, true, true>,  RegSmem0::TOTAL, 32);
+    persistent_setup(JK_O1_4R8,   dec_o1r_kernel<8, false, true>,  O1Smem<4, 3>::TOTAL, 32);
+    persistent_setup(JK_O1_4R16,  dec_o1r_kernel<16, false, true>, O1Smem<4, 4>::TOTAL, 32);
+    persistent_setup(JK_R8_O1R8,  dec_o1r_kernel<8, true, true>,   O1Smem<4, 3>::TOTAL, 32);
+    persistent_setup(JK_R8_O1R16, dec_o1r_kernel<16, true, true>,  O1Smem<4, 4>::TOTAL, 32);
+    persistent_setup(JK_O0_4R8,   dec_o0r_kernel<8, false, false>,  RegSmem0::TOTAL, 32);
+    persistent_setup(JK_O0_4R16,  dec_o0r_kernel<16, false, false>, RegSmem0::TOTAL, 32);
+    persistent_setup(JK_R8_O0R8,  dec_o0r_kernel<8, true, false>,   RegSmem0::TOTAL, 32);
+    persistent_setup(JK_R8_O0R16, dec_o0r_kernel<16, true, false>,  RegSmem0::TOTAL, 32);
+    persistent_setup(JK_O1_4R8,   dec_o1r_kernel<8, false, false>,  O1Smem<4, 3>::TOTAL, 32);
+    persistent_setup(JK_O1_4R16,  dec_o1r_kernel<16, false, false>, O1Smem<4, 4>::TOTAL, 32);
+    persistent_setup(JK_R8_O1R8,  dec_o1r_kernel<8, true, false>,   O1Smem<4, 3>::TOTAL, 32);
+    persistent_setup(JK_R8_O1R16, dec_o1r_kernel<16, true, false>,  O1Smem<4, 4>::TOTAL, 32);
     persistent_setup(JK_R8_O1,  dec_o1_kernel<4, true, 0>,   O1Smem<4>::TOTAL, 32);
     persistent_setup(JK_O1_4M,  dec_o1_kernel<4, false, 2>,  O1Smem<4, 2>::TOTAL, 32);
     persistent_setup(JK_R8_O1M, dec_o1_kernel<4, true, 2>,   O1Smem<4, 2>::TOTAL, 32);
@@ -2223,14 +2291,22 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     LAUNCH_DEC(JK_R8_O1, (dec_o1_kernel<4, true, 0>), 8, false)
     LAUNCH_DEC(JK_O0_4, (dec_o0_kernel<4, false>), 8, false)
     LAUNCH_DEC(JK_R8_O0, (dec_o0_kernel<4, true>), 8, false)
-    LAUNCH_DEC(JK_O1_4R16, (dec_o1r_kernel<16, false>), 8, false)
-    LAUNCH_DEC(JK_R8_O1R16, (dec_o1r_kernel<16, true>), 8, false)
-    LAUNCH_DEC(JK_O1_4R8, (dec_o1r_kernel<8, false>), 8, false)
-    LAUNCH_DEC(JK_R8_O1R8, (dec_o1r_kernel<8, true>), 8, false)
-    LAUNCH_DEC(JK_O0_4R16, (dec_o0r_kernel<16, false>), 8, false)
-    LAUNCH_DEC(JK_R8_O0R16, (dec_o0r_kernel<16, true>), 8, false)
-    LAUNCH_DEC(JK_O0_4R8, (dec_o0r_kernel<8, false>), 8, false)
-    LAUNCH_DEC(JK_R8_O0R8, (dec_o0r_kernel<8, true>), 8, false)
+    // register-table kernels: with few streams per SM a step's latency is what counts, and the variant that fetches the
+    // renormalisation bytes a step AHEAD is shorter; with many (> ~8 warps per SM) the integer pipe is the limit and the
+    // plain variant executes fewer instructions.  HTSCODECS_B200_AHEAD=0|1 forces one.
+    static const int ahead_env = getenv("HTSCODECS_B200_AHEAD") ? atoi(getenv("HTSCODECS_B200_AHEAD")) : -1;
+    const bool ahead = ahead_env >= 0 ? ahead_env != 0 : b.nblk <= 8 * 8 * g_sms;
+#define LAUNCH_REG(K, KERNEL, ...)                                                             \
+    if (ahead) { LAUNCH_DEC(K, (KERNEL<__VA_ARGS__, true>), 8, false) } else { LAUNCH_DEC(K, (KERNEL<__VA_ARGS__, false>), 8, false) }
+    LAUNCH_REG(JK_O1_4R16, dec_o1r_kernel, 16, false)
+    LAUNCH_REG(JK_R8_O1R16, dec_o1r_kernel, 16, true)
+    LAUNCH_REG(JK_O1_4R8, dec_o1r_kernel, 8, false)
+    LAUNCH_REG(JK_R8_O1R8, dec_o1r_kernel, 8, true)
+    LAUNCH_REG(JK_O0_4R16, dec_o0r_kernel, 16, false)
+    LAUNCH_REG(JK_R8_O0R16, dec_o0r_kernel, 16, true)
+    LAUNCH_REG(JK_O0_4R8, dec_o0r_kernel, 8, false)
+    LAUNCH_REG(JK_R8_O0R8, dec_o0r_kernel, 8, true)
+#undef LAUNCH_REG
     LAUNCH_DEC(JK_O0_4C, (dec_o0c_kernel<false>), 8, false)
     LAUNCH_DEC(JK_R8_O0C, (dec_o0c_kernel<true>), 8, false)
     LAUNCH_DEC(JK_O1_32, (dec_o1_kernel<32, false, 0>), 1, false)
