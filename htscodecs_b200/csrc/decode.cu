@@ -19,6 +19,9 @@
 // rANS_word.h:356-410).  The ring is refilled by coalesced 128-bit loads issued half a ring
 // ahead.  Table set-up runs per group (group-masked warp syncs); the decode loop runs converged.
 #include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
 
 #include "decode.h"
 
@@ -42,6 +45,18 @@ __device__ __forceinline__ bool push_job(DecWork* W, uint32_t kind, const DecJob
     if (at >= W->job_cap) { W->overflow = 1; return false; }
     W->jobs[kind][at] = j;
     return true;
+}
+
+// First thing a persistent entropy kernel does (see DecWork::gate): does this CTA stay on its SM?
+__device__ __forceinline__ bool gate_pass(DecWork* W, uint32_t kind) {
+    const uint32_t c = W->gate_c[kind];
+    if (c == 0) return true;
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    uint32_t slot = 0;
+    if (lane_id() == 0) slot = atomicAdd(&W->gate[kind * GATE_SMS + (smid % GATE_SMS)], 1u);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    return slot < c;
 }
 
 __device__ __forceinline__ DecJob make_job(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len,
@@ -630,6 +645,55 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
 }
 
+// ---- renormalisation bytes of a 4-lane group as a register window (4-way / 4x8 kernels) ----------------------
+// The 8 bytes at the group's read position (a step consumes at most 4 words, or 4 x 2 bytes for 4x8) are fetched at
+// the START of a step, and after the ballot each lane picks its word with two byte permutes -- the selector comes from
+// a permute table indexed by the ballot bits of the lower lanes -- so neither a popc nor a shared-memory load sits
+// between the ballot and the next state.  Needs the ring's mirror (its first 64 bytes repeated behind its end).
+struct Win { uint32_t lo, hi; };
+
+// prmt.b32 without __byte_perm's selector masking: every selector nibble used here is <= 7 (bit 3 = sign replication)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// The 8 bytes at byte offset `head` of a 4-way group's ring (RING = 256 bytes + mirror of its first 64).
+__device__ __forceinline__ Win win_load(uint32_t ring, uint32_t head) {
+    const uint32_t a = ring + (head & 252u);
+    const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4), w2 = lds_u32(a + 8);
+    const uint32_t sh = (head & 3u) * 8u;
+    Win w;
+    w.lo = __funnelshift_r(w0, w1, sh);
+    w.hi = __funnelshift_r(w1, w2, sh);
+    return w;
+}
+
+// Renormalise every lane of the warp (rANS_word.h:356-410 / rANS_byte.h:435-551) from its group's window.
+// p: this lane's state `x` is below the lower bound (and the lane is active).  Advances `head`.
+template <bool BYTE>
+__device__ __forceinline__ uint32_t win_renorm(uint32_t x, bool p, const Win w, uint32_t& head, uint32_t lt4, uint32_t gshift) {
+    if (BYTE) {
+        const bool p2 = p && x < (1u << 15);
+        const uint32_t b1 = __ballot_sync(0xffffffffu, p) >> gshift, b2 = __ballot_sync(0xffffffffu, p2) >> gshift;
+        const uint32_t o = __popc(b1 & lt4) + __popc(b2 & lt4);                   // 0 .. 6: my first byte
+        const uint32_t ww = prmt(w.lo, w.hi, o * 0x11u + 0x10u);           // bytes o, o + 1
+        if (p2) x = prmt(ww, x, 0x5401);                                   // x << 16 | first << 8 | second
+        else if (p) x = prmt(ww, x, 0x6540);                               // x << 8 | first
+        head += __popc(b1 & 15u) + __popc(b2 & 15u);
+    } else {
+        const uint32_t b = __ballot_sync(0xffffffffu, p) >> gshift;
+        // word index k = popc(b & lt4) -> selector bytes (2k, 2k+1), by table: v = b & lt4 in 0..7
+        const uint32_t selk = prmt(0x54323210u, 0x76545432u, b & lt4);
+        const uint32_t ww = prmt(w.lo, w.hi, selk);
+        if (p) x = prmt(ww, x, 0x5410);                                    // x << 16 | word
+        head += 2u * __popc(b & 15u);
+    }
+    return x;
+}
+
+
 // ------------------------------------------------------------------------------------------
 // order-0
 // ------------------------------------------------------------------------------------------
@@ -739,12 +803,15 @@ template <int NWAY, bool BYTE, bool ALIGNED, bool ALLACT>
 __device__ __forceinline__ uint32_t o0_step(uint32_t R, bool act, WordRing<NWAY>& ring, uint32_t lut, uint32_t fc,
                                             uint8_t* op, uint32_t lt, uint32_t gshift, uint32_t* sym_out = nullptr) {
     constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
+    Win win;
+    if (NWAY == 4) win = win_load(ring.ring, ring.head);
     const uint32_t m = R & 0xfffu;
     const uint32_t s = lds_u8(lut + m);
     const uint2 e = lds_v2(fc + s * 8);
     const uint32_t X = e.x * (R >> 12) + m;
     const bool p = (ALLACT || act) && X < e.y;               // x' < L
     if (ALLACT || act) { R = X + L - e.y; if (sym_out) *sym_out = s; else *op = (uint8_t)s; }
+    if (NWAY == 4) return win_renorm<BYTE>(R, p, win, ring.head, lt, gshift);
     return renorm_step<NWAY, BYTE, ALIGNED>(R, p, ring, lt, gshift);
 }
 
@@ -855,6 +922,7 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
     const uint32_t ringa = base + S::RINGO + G.g * S::RINGSZ;
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
+    if (!gate_pass(W, kind)) return;
 
     // Jobs are claimed from an atomic cursor.  The host shapes the launch so that every SM holds the
     // same number of CTAs (shaped_launch below): a batch that fits in one wave is then spread evenly.
@@ -894,7 +962,7 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
 // a 64-bucket coarse index and one packed entry (C+F-1)<<20 | sym<<12 | (F-1) per symbol -- 592
 // bytes per stream with its word ring: 256 resident streams per SM.  Alphabets of up to 64 symbols.
 struct O0CSmem {
-    static constexpr int COARSE = 0, ENT = 64, RINGO = 64 + 4 * (O0C_MAX_NS + 4), STRIDE = RINGO + 256;
+    static constexpr int COARSE = 0, ENT = 64, RINGO = 64 + 4 * (O0C_MAX_NS + 4), STRIDE = RINGO + 256 + 64;   // ring + mirror
     static constexpr int TOTAL = 8 * STRIDE;
 };
 
@@ -952,6 +1020,7 @@ template <bool BYTE, bool ALIGNED, bool ALLACT>
 __device__ __forceinline__ uint32_t o0c_step(uint32_t R, bool act, WordRing<4>& ring, uint32_t coarse, uint32_t ent,
                                              uint8_t* op, uint32_t lt, uint32_t gshift, uint32_t* sym_out = nullptr) {
     constexpr uint32_t L = BYTE ? (1u << 23) : (1u << 15);
+    const Win win = win_load(ring.ring, ring.head);
     const uint32_t m = R & 0xfffu, mk = m << 20, q = R >> 12, qm = q + m;
     uint32_t ea = ent + 4 * lds_u8(coarse + (m >> 6));
     const uint32_t e0 = lds_u32(ea), e1 = lds_u32(ea + 4), e2 = lds_u32(ea + 8);
@@ -963,7 +1032,7 @@ __device__ __forceinline__ uint32_t o0c_step(uint32_t R, bool act, WordRing<4>& 
     const uint32_t Rn = (e & 0xfffu) * (q + 1u) + (qm - (e >> 20));
     const bool p = (ALLACT || act) && Rn < L;
     if (ALLACT || act) { R = Rn; if (sym_out) *sym_out = (e >> 12) & 0xffu; else *op = (uint8_t)(e >> 12); }
-    return renorm_step<4, BYTE, ALIGNED>(R, p, ring, lt, gshift);
+    return win_renorm<BYTE>(R, p, win, ring.head, lt, gshift);
 }
 
 template <bool BYTE, bool ALIGNED>
@@ -1015,6 +1084,7 @@ __global__ void __launch_bounds__(32, 32) dec_o0c_kernel(DecWork* W, int32_t* st
     asm volatile("" : "+r"(base));
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
+    if (!gate_pass(W, kind)) return;
     for (;;) {
         uint32_t j0 = 0;
         if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], 8u);
@@ -1031,7 +1101,7 @@ __global__ void __launch_bounds__(32, 32) dec_o0c_kernel(DecWork* W, int32_t* st
             if (!ok && G.glane == 0) set_status(status, job.blk, ST_FORMAT);
         }
         WordRing<4> ring;
-        ring.init(job.in + first_word, job.in + job.in_len, base + O0CSmem::RINGO, G, ok);
+        ring.init(job.in + first_word, job.in + job.in_len, base + O0CSmem::RINGO, G, ok, true);
         __syncwarp();
         const uint32_t iters = ok ? job.out_len / 4 : 0, rem = ok ? job.out_len % 4 : 0;
         const uint32_t maxit = __reduce_max_sync(0xffffffffu, iters), minit = __reduce_min_sync(0xffffffffu, iters);
@@ -1077,7 +1147,7 @@ template <int NWAY, int SZ = 0> struct O1Smem {               // SZ: 0 regular, 
     // (alphabets of <= 16 symbols, 256-byte ring) let it share the word ring's memory
     static constexpr bool OVERLAY = (NWAY == 32) || SMALL || REG;
     static constexpr int FTMP = 512, RINGO = OVERLAY ? 512 : 1536;
-    static constexpr int TABO = RINGO + GroupCfg<NWAY>::RING + (REG ? 64 : 0);   // REG: + mirror of the ring's first 64 bytes
+    static constexpr int TABO = RINGO + GroupCfg<NWAY>::RING + (NWAY == 4 ? 64 : 0);   // 4-way: + mirror of the ring's first 64 bytes
     // X_32: 12992 B (<= 48 symbols, 15 warps / SM) or, SMALL, 4608 B (<= 25 symbols, 28 warps / SM);
     // 4-way: 3072 B per group (<= 19 symbols, 40 groups / SM), SMALL 1024 B (<= 9 symbols, 120 groups / SM),
     // medium 12544 B (<= 47 symbols, 16 groups / SM), REG ns x ns entries (256 B / 1 KB)
@@ -1439,9 +1509,12 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
             uint32_t pack = 0;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
+                Win win;
+                if (NWAY == 4) win = win_load(ring.ring, ring.head);
                 const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
                 pack |= lds_u8(unrank + r) << (8 * u);
-                R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
+                if (NWAY == 4) R = win_renorm<BYTE>(R, R < LB, win, ring.head, lt, G.gshift);
+                else R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
             }
             sink.put4(pack);
             ring.advance(G.glane, true);
@@ -1450,20 +1523,26 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
         for (; i + 4 <= minit; i += 4) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
+                Win win;
+                if (NWAY == 4) win = win_load(ring.ring, ring.head);
                 const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
                 sink.put(lds_u8(unrank + r));
-                R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
+                if (NWAY == 4) R = win_renorm<BYTE>(R, R < LB, win, ring.head, lt, G.gshift);
+                else R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
             }
             ring.advance(G.glane, true);
         }
     }
     for (; i < maxit; i++) {
         const bool act = i < mine;
+        Win win;
+        if (NWAY == 4) win = win_load(ring.ring, ring.head);
         if (act) {
             const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
             sink.put(lds_u8(unrank + r));
         }
-        R = renorm_step<NWAY, BYTE, ALIGNED>(R, act && R < LB, ring, lt, G.gshift);
+        if (NWAY == 4) R = win_renorm<BYTE>(R, act && R < LB, win, ring.head, lt, G.gshift);
+        else R = renorm_step<NWAY, BYTE, ALIGNED>(R, act && R < LB, ring, lt, G.gshift);
         ring.advance(G.glane, i < group_steps);
     }
     sink.finish();
@@ -1480,6 +1559,7 @@ __global__ void __launch_bounds__(32, (SZ == 1 && NWAY == 32) ? 28 : 1) dec_o1_k
     asm volatile("" : "+r"(base));                      // keep the window base in a register
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
+    if (!gate_pass(W, kind)) return;
 
     // Jobs are claimed from an atomic cursor.  The host shapes the launch so that every SM holds the
     // same number of CTAs (shaped_launch below): a batch that fits in one wave is then spread evenly.
@@ -1506,7 +1586,7 @@ __global__ void __launch_bounds__(32, (SZ == 1 && NWAY == 32) ? 28 : 1) dec_o1_k
             if (!ok && G.glane == 0) set_status(status, job.blk, st);
         }
         WordRing<NWAY> ring;
-        ring.init(first_word, job.in + job.in_len, base + S::RINGO, G, ok);
+        ring.init(first_word, job.in + job.in_len, base + S::RINGO, G, ok, NWAY == 4);
         __syncwarp();
         const uint32_t seg = ok ? job.out_len / NWAY : 0, tail = ok ? job.out_len - seg * NWAY : 0;
         const uint32_t maxit = __reduce_max_sync(0xffffffffu, seg + tail), minit = __reduce_min_sync(0xffffffffu, seg);
@@ -1535,78 +1615,6 @@ __global__ void __launch_bounds__(32, (SZ == 1 && NWAY == 32) ? 28 : 1) dec_o1_k
 //     selector comes from a permute-table indexed by the ballot bits of the lower lanes, so neither a popc nor a
 //     shared-memory load sits between the ballot and the next state.
 // Results are identical to the table kernels by construction (same F, same C); alphabets of up to 16 symbols.
-struct Win { uint32_t lo, hi; };
-
-// prmt.b32 without __byte_perm's selector masking: every selector nibble used here is <= 7 (bit 3 = sign replication)
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-    return d;
-}
-
-// The 8 bytes at byte offset `head` of a 4-way group's ring (RING = 256 bytes + mirror of its first 64).
-__device__ __forceinline__ Win win_load(uint32_t ring, uint32_t head) {
-    const uint32_t a = ring + (head & 252u);
-    const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4), w2 = lds_u32(a + 8);
-    const uint32_t sh = (head & 3u) * 8u;
-    Win w;
-    w.lo = __funnelshift_r(w0, w1, sh);
-    w.hi = __funnelshift_r(w1, w2, sh);
-    return w;
-}
-
-// The same window without a shared-memory round trip between the previous step's ballot and this step's selection
-// (AHEAD): the 20 bytes from the word at or below the PREVIOUS read position are fetched a step early -- the position
-// can only have advanced by 0 .. 8 bytes since -- and the window is cut out of them once the advance is known.
-struct Chunk { uint32_t w0, w1, w2, w3, w4, base; };
-__device__ __forceinline__ Chunk chunk_load(uint32_t ring, uint32_t head) {
-    const uint32_t a = ring + (head & 252u);
-    Chunk c;
-    c.w0 = lds_u32(a); c.w1 = lds_u32(a + 4); c.w2 = lds_u32(a + 8); c.w3 = lds_u32(a + 12); c.w4 = lds_u32(a + 16);
-    c.base = head & ~3u;
-    return c;
-}
-__device__ __forceinline__ Win chunk_window(const Chunk& c, uint32_t head) {
-    const uint32_t s = head - c.base;                        // 0 .. 11
-    const uint32_t sh = (s & 3u) * 8u;
-    const uint32_t f0 = __funnelshift_r(c.w0, c.w1, sh), f1 = __funnelshift_r(c.w1, c.w2, sh);
-    const uint32_t f2 = __funnelshift_r(c.w2, c.w3, sh), f3 = __funnelshift_r(c.w3, c.w4, sh);
-    Win w;
-    w.lo = s < 4u ? f0 : (s < 8u ? f1 : f2);
-    w.hi = s < 4u ? f1 : (s < 8u ? f2 : f3);
-    return w;
-}
-// AHEAD ? (window of this step from the chunk fetched last step; fetch the next chunk) : plain window load
-template <bool AHEAD> __device__ __forceinline__ Win next_window(Chunk& c, uint32_t ring, uint32_t head) {
-    if (!AHEAD) return win_load(ring, head);
-    const Win w = chunk_window(c, head);
-    c = chunk_load(ring, head);
-    return w;
-}
-
-// Renormalise every lane of the warp (rANS_word.h:356-410 / rANS_byte.h:435-551) from its group's window.
-// p: this lane's state `x` is below the lower bound (and the lane is active).  Advances `head`.
-template <bool BYTE>
-__device__ __forceinline__ uint32_t win_renorm(uint32_t x, bool p, const Win w, uint32_t& head, uint32_t lt4, uint32_t gshift) {
-    if (BYTE) {
-        const bool p2 = p && x < (1u << 15);
-        const uint32_t b1 = __ballot_sync(0xffffffffu, p) >> gshift, b2 = __ballot_sync(0xffffffffu, p2) >> gshift;
-        const uint32_t o = __popc(b1 & lt4) + __popc(b2 & lt4);                   // 0 .. 6: my first byte
-        const uint32_t ww = prmt(w.lo, w.hi, o * 0x11u + 0x10u);           // bytes o, o + 1
-        if (p2) x = prmt(ww, x, 0x5401);                                   // x << 16 | first << 8 | second
-        else if (p) x = prmt(ww, x, 0x6540);                               // x << 8 | first
-        head += __popc(b1 & 15u) + __popc(b2 & 15u);
-    } else {
-        const uint32_t b = __ballot_sync(0xffffffffu, p) >> gshift;
-        // word index k = popc(b & lt4) -> selector bytes (2k, 2k+1), by table: v = b & lt4 in 0..7
-        const uint32_t selk = prmt(0x54323210u, 0x76545432u, b & lt4);
-        const uint32_t ww = prmt(w.lo, w.hi, selk);
-        if (p) x = prmt(ww, x, 0x5410);                                    // x << 16 | word
-        head += 2u * __popc(b & 15u);
-    }
-    return x;
-}
-
 // First entry whose last slot is >= the probe (entries ascending, padded with sentinels): M > e  <=>  slot beyond e.
 template <int NS> __device__ __forceinline__ uint32_t reg_search(const uint32_t (&e)[NS], uint32_t M);
 template <> __device__ __forceinline__ uint32_t reg_search<8>(const uint32_t (&e)[8], uint32_t M) {
@@ -1708,7 +1716,7 @@ __device__ bool o0r_setup(const Grp<4>& G, const DecJob& job, uint32_t gsm, uint
     return true;
 }
 
-template <int NS, bool BYTE, bool AHEAD>
+template <int NS, bool BYTE>
 __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status, uint32_t kind) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const Grp<4> G;
@@ -1716,6 +1724,7 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
     asm volatile("" : "+r"(base));
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
+    if (!gate_pass(W, kind)) return;
     const uint32_t lt4 = (1u << G.glane) - 1u;
     for (;;) {
         uint32_t j0 = 0;
@@ -1746,13 +1755,12 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
         const uint32_t maxit = __reduce_max_sync(0xffffffffu, iters), minit = __reduce_min_sync(0xffffffffu, iters);
         uint8_t* op = job.out + G.glane;
         uint32_t i = 0;
-        Chunk ch = chunk_load(ring.ring, ring.head);
         const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(job.out) & 3) == 0);
         for (; i + 4 <= minit; i += 4) {                     // every lane of the warp active: four steps to a ring check
             uint32_t w = 0;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const Win win = next_window<AHEAD>(ch, ring.ring, ring.head);
+                const Win win = win_load(ring.ring, ring.head);
                 bool p;
                 const uint32_t sy = (reg_symbol<NS, BYTE>(R, E, 12u, 20u, 0xfffu, &p) >> 12) & 0xffu;
                 w |= sy << (8 * u);
@@ -1768,7 +1776,7 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
         }
         for (; i < maxit; i++) {
             const bool act = i < iters;
-            const Win win = next_window<AHEAD>(ch, ring.ring, ring.head);
+            const Win win = win_load(ring.ring, ring.head);
             uint32_t x = R;
             bool p;
             const uint32_t sy = (reg_symbol<NS, BYTE>(x, E, 12u, 20u, 0xfffu, &p) >> 12) & 0xffu;
@@ -1785,7 +1793,7 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
 }
 
 // Order 1: the row of the lane's current context in registers; the next row is fetched the moment the symbol is known.
-template <int NS, bool BYTE, bool AHEAD>
+template <int NS, bool BYTE>
 __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status, uint32_t kind) {
     constexpr int SZ = NS == 8 ? 3 : 4;
     using S = O1Smem<4, SZ>;
@@ -1797,6 +1805,7 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
     asm volatile("" : "+r"(base));
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
+    if (!gate_pass(W, kind)) return;
     const uint32_t lt4 = (1u << G.glane) - 1u;
     const uint32_t rows = base + S::TABO, unrank = base + S::UNRANK;
     for (;;) {
@@ -1841,7 +1850,6 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
             const uint32_t r0a = rows + (ok ? ctx0 : 0u) * RS;
             load_row<NS>(E, r0a, NS == 16 ? (uint32_t)(lds_u32(r0a + 4 * NS) > 8u) : 1u);
         }
-        Chunk ch = chunk_load(ring.ring, ring.head);
         // next row: rank in bits 12-15 of the entry, "more than 8 entries" in bit 16
         auto fetch_row = [&](uint32_t e) { load_row<NS>(E, rows + ((e >> 12) & 15u) * RS, e & 0x10000u); };
         ByteSink sink;
@@ -1854,7 +1862,7 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
                 uint32_t pack = 0;
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const Win win = next_window<AHEAD>(ch, ring.ring, ring.head);
+                    const Win win = win_load(ring.ring, ring.head);
                     bool p;
                     const uint32_t e = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
                     fetch_row(e);
@@ -1868,7 +1876,7 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
             for (; i + 4 <= minit; i += 4) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const Win win = next_window<AHEAD>(ch, ring.ring, ring.head);
+                    const Win win = win_load(ring.ring, ring.head);
                     bool p;
                     const uint32_t e = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
                     fetch_row(e);
@@ -1880,7 +1888,7 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
         }
         for (; i < maxit; i++) {
             const bool act = i < mine;
-            const Win win = next_window<AHEAD>(ch, ring.ring, ring.head);
+            const Win win = win_load(ring.ring, ring.head);
             bool p = false;
             if (act) {
                 const uint32_t e = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
@@ -2182,7 +2190,10 @@ static void persistent_setup(uint32_t kind, K kernel, int smem, int threads) {
 
 // The per-batch header travels as a kernel argument (copied at launch), so the host may reuse
 // its copy immediately even when several batches are in flight on the stream.
-__global__ void work_init_kernel(DecWork* dst, DecWork hdr) { *dst = hdr; }
+__global__ void work_init_kernel(DecWork* dst, DecWork hdr) {
+    if (threadIdx.x == 0) *dst = hdr;
+    for (uint32_t k = threadIdx.x; k < JK_NKINDS * GATE_SMS; k += blockDim.x) hdr.gate[k] = 0;
+}
 
 int SideStreams::init() {
     if (fork) return 0;
@@ -2214,23 +2225,14 @@ int decode_init(int device) {
     persistent_setup(JK_O1_32,  dec_o1_kernel<32, false, 0>, O1Smem<32>::TOTAL, 32);
     persistent_setup(JK_O1_32S, dec_o1_kernel<32, false, 1>,  O1Smem<32, 1>::TOTAL, 32);
     persistent_setup(JK_O1_4,   dec_o1_kernel<4, false, 0>,  O1Smem<4>::TOTAL, 32);
-    // (the AHEAD twins share their kind's shared-memory size; the occupancy recorded is the plain variant's)
-    persistent_setup(JK_O0_4R8,   dec_o0r_kernel<8, false, true>,  RegSmem0::TOTAL, 32);
-    persistent_setup(JK_O0_4R16,  dec_o0r_kernel<16, false, true>, RegSmem0::TOTAL, 32);
-    persistent_setup(JK_R8_O0R8,  dec_o0r_kernel<8, true, true>,   RegSmem0::TOTAL, 32);
-    persistent_setup(JK_R8_O0R16, dec_o0r_kernel<16, true, true>,  RegSmem0::TOTAL, 32);
-    persistent_setup(JK_O1_4R8,   dec_o1r_kernel<8, false, true>,  O1Smem<4, 3>::TOTAL, 32);
-    persistent_setup(JK_O1_4R16,  dec_o1r_kernel<16, false, true>, O1Smem<4, 4>::TOTAL, 32);
-    persistent_setup(JK_R8_O1R8,  dec_o1r_kernel<8, true, true>,   O1Smem<4, 3>::TOTAL, 32);
-    persistent_setup(JK_R8_O1R16, dec_o1r_kernel<16, true, true>,  O1Smem<4, 4>::TOTAL, 32);
-    persistent_setup(JK_O0_4R8,   dec_o0r_kernel<8, false, false>,  RegSmem0::TOTAL, 32);
-    persistent_setup(JK_O0_4R16,  dec_o0r_kernel<16, false, false>, RegSmem0::TOTAL, 32);
-    persistent_setup(JK_R8_O0R8,  dec_o0r_kernel<8, true, false>,   RegSmem0::TOTAL, 32);
-    persistent_setup(JK_R8_O0R16, dec_o0r_kernel<16, true, false>,  RegSmem0::TOTAL, 32);
-    persistent_setup(JK_O1_4R8,   dec_o1r_kernel<8, false, false>,  O1Smem<4, 3>::TOTAL, 32);
-    persistent_setup(JK_O1_4R16,  dec_o1r_kernel<16, false, false>, O1Smem<4, 4>::TOTAL, 32);
-    persistent_setup(JK_R8_O1R8,  dec_o1r_kernel<8, true, false>,   O1Smem<4, 3>::TOTAL, 32);
-    persistent_setup(JK_R8_O1R16, dec_o1r_kernel<16, true, false>,  O1Smem<4, 4>::TOTAL, 32);
+    persistent_setup(JK_O0_4R8,   dec_o0r_kernel<8, false>,  RegSmem0::TOTAL, 32);
+    persistent_setup(JK_O0_4R16,  dec_o0r_kernel<16, false>, RegSmem0::TOTAL, 32);
+    persistent_setup(JK_R8_O0R8,  dec_o0r_kernel<8, true>,   RegSmem0::TOTAL, 32);
+    persistent_setup(JK_R8_O0R16, dec_o0r_kernel<16, true>,  RegSmem0::TOTAL, 32);
+    persistent_setup(JK_O1_4R8,   dec_o1r_kernel<8, false>,  O1Smem<4, 3>::TOTAL, 32);
+    persistent_setup(JK_O1_4R16,  dec_o1r_kernel<16, false>, O1Smem<4, 4>::TOTAL, 32);
+    persistent_setup(JK_R8_O1R8,  dec_o1r_kernel<8, true>,   O1Smem<4, 3>::TOTAL, 32);
+    persistent_setup(JK_R8_O1R16, dec_o1r_kernel<16, true>,  O1Smem<4, 4>::TOTAL, 32);
     persistent_setup(JK_R8_O1,  dec_o1_kernel<4, true, 0>,   O1Smem<4>::TOTAL, 32);
     persistent_setup(JK_O1_4M,  dec_o1_kernel<4, false, 2>,  O1Smem<4, 2>::TOTAL, 32);
     persistent_setup(JK_R8_O1M, dec_o1_kernel<4, true, 2>,   O1Smem<4, 2>::TOTAL, 32);
@@ -2243,16 +2245,19 @@ int decode_init(int device) {
 // SMs and leave the rest idle.  So the launch is shaped: with `groups` work items expected, the
 // dynamic shared-memory request is padded until exactly c = ceil(groups / SMs) CTAs fit per SM and
 // the grid is SMs x c -- every SM then holds the same number of streams.
-struct Shape { int grid, smem; };
+struct Shape { int grid, smem; uint32_t gate_c; };
 static Shape shaped_launch(uint32_t kind, uint32_t groups) {
     int c = (int)((groups + g_sms - 1) / g_sms);
     c = std::max(1, std::min(c, g_cap[kind]));
     // experiments: HTSCODECS_B200_CAP_O0_32=<n> limits the X_32 order-0 kernel to n resident warps per SM
     static const int cap32 = getenv("HTSCODECS_B200_CAP_O0_32") ? atoi(getenv("HTSCODECS_B200_CAP_O0_32")) : 0;
     if (kind == JK_O0_32 && cap32 > 0) c = std::min(c, cap32);
-    int smem = g_smem[kind];
-    if (c < g_cap[kind]) smem = std::max(smem, std::min(MAX_DYN, (SM_SMEM / c - CTA_RESERVE) & ~127));
-    return Shape{g_sms * c, smem};
+    // HTSCODECS_B200_SHAPE=pad: the round-1 way -- pad the shared-memory request until exactly c CTAs fit per SM
+    // (which also keeps every OTHER kernel off those SMs); default: gate (DecWork::gate)
+    static const bool pad = getenv("HTSCODECS_B200_SHAPE") && !strcmp(getenv("HTSCODECS_B200_SHAPE"), "pad");
+    if (c >= g_cap[kind]) return Shape{g_sms * g_cap[kind], g_smem[kind], 0u};
+    if (pad) return Shape{g_sms * c, std::max(g_smem[kind], std::min(MAX_DYN, (SM_SMEM / c - CTA_RESERVE) & ~127)), 0u};
+    return Shape{g_sms * g_cap[kind], g_smem[kind], (uint32_t)c};
 }
 
 
@@ -2263,12 +2268,19 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     A.out_base = b.out_base; A.out_off = b.out_off; A.out_len = b.out_len;
     A.status = b.status; A.method = b.method; A.nblk = b.nblk;
     int launches = 0;
-    work_init_kernel<<<1, 1, 0, st>>>(b.work, *b.hdr); launches++;
-    plan_kernel<<<(b.nblk + 127) / 128, 128, 0, st>>>(A); launches++;
     auto want = [&](uint32_t k) { return (b.kinds >> k) & 1u; };
     // expected work items per kind: the host only knows the block count (the planner decides kinds on
     // the device), which is exact for the common single-kind batch and an upper bound otherwise
-    auto shape = [&](uint32_t k, uint32_t per_cta) { return shaped_launch(k, (b.nblk + per_cta - 1) / per_cta); };
+    Shape shapes[JK_NKINDS];
+    DecWork hdr = *b.hdr;
+    for (uint32_t k = 0; k < JK_NKINDS; k++) {
+        const uint32_t per = (k == JK_O0_32 || k == JK_O1_32 || k == JK_O1_32S) ? 1u : 8u;
+        shapes[k] = (k == JK_COPY) ? Shape{0, 0, 0u} : shaped_launch(k, (b.nblk + per - 1) / per);
+        hdr.gate_c[k] = shapes[k].gate_c;
+    }
+    work_init_kernel<<<1, 256, 0, st>>>(b.work, hdr); launches++;
+    plan_kernel<<<(b.nblk + 127) / 128, 128, 0, st>>>(A); launches++;
+    auto shape = [&](uint32_t k, uint32_t) { return shapes[k]; };
     Shape sh;
     // compressed order-1 tables first (tiny jobs), then one stream per kind
     if (want(JK_TAB)) { sh = shape(JK_TAB, 8); dec_o0_kernel<4, false><<<sh.grid, 32, sh.smem, st>>>(b.work, b.status, JK_TAB); launches++; }
@@ -2291,22 +2303,16 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     LAUNCH_DEC(JK_R8_O1, (dec_o1_kernel<4, true, 0>), 8, false)
     LAUNCH_DEC(JK_O0_4, (dec_o0_kernel<4, false>), 8, false)
     LAUNCH_DEC(JK_R8_O0, (dec_o0_kernel<4, true>), 8, false)
-    // register-table kernels: with few streams per SM a step's latency is what counts, and the variant that fetches the
-    // renormalisation bytes a step AHEAD is shorter; with many (> ~8 warps per SM) the integer pipe is the limit and the
-    // plain variant executes fewer instructions.  HTSCODECS_B200_AHEAD=0|1 forces one.
-    static const int ahead_env = getenv("HTSCODECS_B200_AHEAD") ? atoi(getenv("HTSCODECS_B200_AHEAD")) : -1;
-    const bool ahead = ahead_env >= 0 ? ahead_env != 0 : b.nblk <= 8 * 8 * g_sms;
-#define LAUNCH_REG(K, KERNEL, ...)                                                             \
-    if (ahead) { LAUNCH_DEC(K, (KERNEL<__VA_ARGS__, true>), 8, false) } else { LAUNCH_DEC(K, (KERNEL<__VA_ARGS__, false>), 8, false) }
-    LAUNCH_REG(JK_O1_4R16, dec_o1r_kernel, 16, false)
-    LAUNCH_REG(JK_R8_O1R16, dec_o1r_kernel, 16, true)
-    LAUNCH_REG(JK_O1_4R8, dec_o1r_kernel, 8, false)
-    LAUNCH_REG(JK_R8_O1R8, dec_o1r_kernel, 8, true)
-    LAUNCH_REG(JK_O0_4R16, dec_o0r_kernel, 16, false)
-    LAUNCH_REG(JK_R8_O0R16, dec_o0r_kernel, 16, true)
-    LAUNCH_REG(JK_O0_4R8, dec_o0r_kernel, 8, false)
-    LAUNCH_REG(JK_R8_O0R8, dec_o0r_kernel, 8, true)
-#undef LAUNCH_REG
+    // (fetching the renormalisation bytes a step AHEAD of their use was tried and measured no faster at 4096 blocks
+    //  -- 211 vs 215 GB/s order 0, 187 vs 205 order 1 -- and 15 % slower at 16384: the window load is not what bounds a step)
+    LAUNCH_DEC(JK_O1_4R16, (dec_o1r_kernel<16, false>), 8, false)
+    LAUNCH_DEC(JK_R8_O1R16, (dec_o1r_kernel<16, true>), 8, false)
+    LAUNCH_DEC(JK_O1_4R8, (dec_o1r_kernel<8, false>), 8, false)
+    LAUNCH_DEC(JK_R8_O1R8, (dec_o1r_kernel<8, true>), 8, false)
+    LAUNCH_DEC(JK_O0_4R16, (dec_o0r_kernel<16, false>), 8, false)
+    LAUNCH_DEC(JK_R8_O0R16, (dec_o0r_kernel<16, true>), 8, false)
+    LAUNCH_DEC(JK_O0_4R8, (dec_o0r_kernel<8, false>), 8, false)
+    LAUNCH_DEC(JK_R8_O0R8, (dec_o0r_kernel<8, true>), 8, false)
     LAUNCH_DEC(JK_O0_4C, (dec_o0c_kernel<false>), 8, false)
     LAUNCH_DEC(JK_R8_O0C, (dec_o0c_kernel<true>), 8, false)
     LAUNCH_DEC(JK_O1_32, (dec_o1_kernel<32, false, 0>), 1, false)
