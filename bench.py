@@ -392,7 +392,10 @@ def e2e_leg(hb, devs, comps_by_block, raw_by_block, nblk, flags, reps=2, encode=
     assert (status == 0).all(), "e2e decode failed"
     for i in (0, nblk - 1):
         assert np.array_equal(pin_u.array[i * n:(i + 1) * n], raw_by_block[i % distinct]), "e2e decode differs"
-    res = {"e2e_decode_GBs": round(nblk * n / min(td[1:]) / 1e9, 1)}
+    def stages():
+        st = hb.multi_last_stats()
+        return {k: round(sum(x[k] for x in st), 1) for k in ("h2d_ms", "kernel_ms", "d2h_ms", "wall_ms")}
+    res = {"e2e_decode_GBs": round(nblk * n / min(td[1:]) / 1e9, 1), "decode_stages_ms": stages()}
     if encode:
         lib = hb.load_library()
         bound = lib.hts_b200_compress_bound_4x8(n) if legacy else hb.rans_compress_bound_4x16(n, flags)
@@ -408,6 +411,7 @@ def e2e_leg(hb, devs, comps_by_block, raw_by_block, nblk, flags, reps=2, encode=
             te.append(time.perf_counter() - t0)
         assert (status == 0).all() and bytes(pin_o.array[:int(o_len[0])]) == comps_by_block[0], "e2e encode differs"
         res["e2e_encode_GBs"] = round(nblk * n / min(te[1:]) / 1e9, 1)
+        res["encode_stages_ms"] = stages()
     return res
 
 

@@ -232,7 +232,6 @@ static int dec_prepare(hts_b200_ctx* ctx, DecSlot& s, int nblk, size_t arena_byt
     size_t o_rle = off; off += align_up(4 * (size_t)chain_cap, 256);
     size_t o_unp = off; off += align_up(4 * (size_t)chain_cap, 256);
     size_t o_str = off; off += align_up(sizeof(StripeOp) * stripe_cap, 256);
-    size_t o_gate = off; off += align_up(4 * (size_t)JK_NKINDS * GATE_SMS, 256);
     if (s.lists.ensure(off) || s.work.ensure(sizeof(DecWork)) || s.h_work.ensure(2) ||
         s.arena.ensure(std::max<size_t>(arena_bytes, 1 << 20)) || s.cap_save.ensure(nblk)) {
         snprintf(ctx->err, sizeof(ctx->err), "out of device memory (lists %zu B, arena %zu B)", off, arena_bytes);
@@ -249,7 +248,6 @@ static int dec_prepare(hts_b200_ctx* ctx, DecSlot& s, int nblk, size_t arena_byt
     h.rle_list = reinterpret_cast<uint32_t*>(s.lists.p + o_rle);
     h.unpack_list = reinterpret_cast<uint32_t*>(s.lists.p + o_unp);
     h.stripes = reinterpret_cast<StripeOp*>(s.lists.p + o_str);
-    h.gate = reinterpret_cast<uint32_t*>(s.lists.p + o_gate);
     h.arena = s.arena.p;
     return 0;
 }

@@ -36,8 +36,6 @@ enum JobKind : uint32_t {
     JK_NKINDS
 };
 
-constexpr uint32_t GATE_SMS = 256;      // >= SMs of the device (B200: 148)
-
 struct DecJob {
     const uint8_t* in;
     uint8_t* out;
@@ -88,12 +86,6 @@ struct DecWork {
     uint32_t job_cap, chain_cap, stripe_cap;
     uint32_t big_batch;                // host hint: more 4-way streams than the LUT kernels hold in one wave
     uint32_t kinds;                    // job kinds whose kernels this batch launches: a job of any other kind is refused
-    // Spreading a small batch over the SMs by gating: a kind's kernel is launched with every CTA slot of the machine
-    // and a CTA beyond its SM's fair share gate_c[kind] exits at once (gate: JK_NKINDS x GATE_SMS arrival counters,
-    // zeroed with the header) -- the kernels keep their natural shared-memory footprint, so the kinds of a mixed batch
-    // and the chunks of a host-buffer call share the SMs.  gate_c == 0: no gating.
-    uint32_t gate_c[JK_NKINDS];
-    uint32_t* gate;
     unsigned long long arena_cap;
     DecJob* jobs[JK_NKINDS];
     Chain* chains;

@@ -47,18 +47,6 @@ __device__ __forceinline__ bool push_job(DecWork* W, uint32_t kind, const DecJob
     return true;
 }
 
-// First thing a persistent entropy kernel does (see DecWork::gate): does this CTA stay on its SM?
-__device__ __forceinline__ bool gate_pass(DecWork* W, uint32_t kind) {
-    const uint32_t c = W->gate_c[kind];
-    if (c == 0) return true;
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    uint32_t slot = 0;
-    if (lane_id() == 0) slot = atomicAdd(&W->gate[kind * GATE_SMS + (smid % GATE_SMS)], 1u);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    return slot < c;
-}
-
 __device__ __forceinline__ DecJob make_job(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len,
                                            uint32_t blk) {
     DecJob j;
@@ -922,7 +910,6 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
     const uint32_t ringa = base + S::RINGO + G.g * S::RINGSZ;
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
-    if (!gate_pass(W, kind)) return;
 
     // Jobs are claimed from an atomic cursor.  The host shapes the launch so that every SM holds the
     // same number of CTAs (shaped_launch below): a batch that fits in one wave is then spread evenly.
@@ -1084,7 +1071,6 @@ __global__ void __launch_bounds__(32, 32) dec_o0c_kernel(DecWork* W, int32_t* st
     asm volatile("" : "+r"(base));
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
-    if (!gate_pass(W, kind)) return;
     for (;;) {
         uint32_t j0 = 0;
         if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], 8u);
@@ -1559,7 +1545,6 @@ __global__ void __launch_bounds__(32, (SZ == 1 && NWAY == 32) ? 28 : 1) dec_o1_k
     asm volatile("" : "+r"(base));                      // keep the window base in a register
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
-    if (!gate_pass(W, kind)) return;
 
     // Jobs are claimed from an atomic cursor.  The host shapes the launch so that every SM holds the
     // same number of CTAs (shaped_launch below): a batch that fits in one wave is then spread evenly.
@@ -1724,7 +1709,6 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
     asm volatile("" : "+r"(base));
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
-    if (!gate_pass(W, kind)) return;
     const uint32_t lt4 = (1u << G.glane) - 1u;
     for (;;) {
         uint32_t j0 = 0;
@@ -1805,7 +1789,6 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
     asm volatile("" : "+r"(base));
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
-    if (!gate_pass(W, kind)) return;
     const uint32_t lt4 = (1u << G.glane) - 1u;
     const uint32_t rows = base + S::TABO, unrank = base + S::UNRANK;
     for (;;) {
@@ -2190,10 +2173,7 @@ static void persistent_setup(uint32_t kind, K kernel, int smem, int threads) {
 
 // The per-batch header travels as a kernel argument (copied at launch), so the host may reuse
 // its copy immediately even when several batches are in flight on the stream.
-__global__ void work_init_kernel(DecWork* dst, DecWork hdr) {
-    if (threadIdx.x == 0) *dst = hdr;
-    for (uint32_t k = threadIdx.x; k < JK_NKINDS * GATE_SMS; k += blockDim.x) hdr.gate[k] = 0;
-}
+__global__ void work_init_kernel(DecWork* dst, DecWork hdr) { *dst = hdr; }
 
 int SideStreams::init() {
     if (fork) return 0;
@@ -2245,19 +2225,19 @@ int decode_init(int device) {
 // SMs and leave the rest idle.  So the launch is shaped: with `groups` work items expected, the
 // dynamic shared-memory request is padded until exactly c = ceil(groups / SMs) CTAs fit per SM and
 // the grid is SMs x c -- every SM then holds the same number of streams.
-struct Shape { int grid, smem; uint32_t gate_c; };
+// (Spreading by gating instead -- every CTA slot launched, CTAs beyond an SM's fair share exit at once, kernels keep
+// their natural footprint so that chunks and kinds could share SMs -- was built and measured in round 2: 4-way decode
+// at 4096 blocks 177 vs 211 GB/s order 0, 146 vs 204 order 1, and the host-buffer pipeline no faster.  Padding stays.)
+struct Shape { int grid, smem; };
 static Shape shaped_launch(uint32_t kind, uint32_t groups) {
     int c = (int)((groups + g_sms - 1) / g_sms);
     c = std::max(1, std::min(c, g_cap[kind]));
     // experiments: HTSCODECS_B200_CAP_O0_32=<n> limits the X_32 order-0 kernel to n resident warps per SM
     static const int cap32 = getenv("HTSCODECS_B200_CAP_O0_32") ? atoi(getenv("HTSCODECS_B200_CAP_O0_32")) : 0;
     if (kind == JK_O0_32 && cap32 > 0) c = std::min(c, cap32);
-    // HTSCODECS_B200_SHAPE=pad: the round-1 way -- pad the shared-memory request until exactly c CTAs fit per SM
-    // (which also keeps every OTHER kernel off those SMs); default: gate (DecWork::gate)
-    static const bool pad = getenv("HTSCODECS_B200_SHAPE") && !strcmp(getenv("HTSCODECS_B200_SHAPE"), "pad");
-    if (c >= g_cap[kind]) return Shape{g_sms * g_cap[kind], g_smem[kind], 0u};
-    if (pad) return Shape{g_sms * c, std::max(g_smem[kind], std::min(MAX_DYN, (SM_SMEM / c - CTA_RESERVE) & ~127)), 0u};
-    return Shape{g_sms * g_cap[kind], g_smem[kind], (uint32_t)c};
+    int smem = g_smem[kind];
+    if (c < g_cap[kind]) smem = std::max(smem, std::min(MAX_DYN, (SM_SMEM / c - CTA_RESERVE) & ~127));
+    return Shape{g_sms * c, smem};
 }
 
 
@@ -2271,16 +2251,9 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     auto want = [&](uint32_t k) { return (b.kinds >> k) & 1u; };
     // expected work items per kind: the host only knows the block count (the planner decides kinds on
     // the device), which is exact for the common single-kind batch and an upper bound otherwise
-    Shape shapes[JK_NKINDS];
-    DecWork hdr = *b.hdr;
-    for (uint32_t k = 0; k < JK_NKINDS; k++) {
-        const uint32_t per = (k == JK_O0_32 || k == JK_O1_32 || k == JK_O1_32S) ? 1u : 8u;
-        shapes[k] = (k == JK_COPY) ? Shape{0, 0, 0u} : shaped_launch(k, (b.nblk + per - 1) / per);
-        hdr.gate_c[k] = shapes[k].gate_c;
-    }
-    work_init_kernel<<<1, 256, 0, st>>>(b.work, hdr); launches++;
+    auto shape = [&](uint32_t k, uint32_t per_cta) { return shaped_launch(k, (b.nblk + per_cta - 1) / per_cta); };
+    work_init_kernel<<<1, 1, 0, st>>>(b.work, *b.hdr); launches++;
     plan_kernel<<<(b.nblk + 127) / 128, 128, 0, st>>>(A); launches++;
-    auto shape = [&](uint32_t k, uint32_t) { return shapes[k]; };
     Shape sh;
     // compressed order-1 tables first (tiny jobs), then one stream per kind
     if (want(JK_TAB)) { sh = shape(JK_TAB, 8); dec_o0_kernel<4, false><<<sh.grid, 32, sh.smem, st>>>(b.work, b.status, JK_TAB); launches++; }
