@@ -516,7 +516,7 @@ def run_ours(args, rank, world, local_rank):
     def reduce_max(v):
         if dist is None:
             return v
-        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        t = torch.tensor([v], device=torch.device("cuda", local_rank), dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 

@@ -263,7 +263,8 @@ def compress_batch_host_multi(devices, nblk, in_base, in_off, in_len, out_base, 
 
 
 def multi_set_phased(phased):
-    load_library().hts_b200_multi_set_phased(1 if phased else 0)
+    """True: phased copies across devices, False: full duplex per device, None: let the library measure (default)."""
+    load_library().hts_b200_multi_set_phased(-1 if phased is None else (1 if phased else 0))
 
 
 def multi_last_stats():

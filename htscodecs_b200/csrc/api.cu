@@ -157,9 +157,18 @@ struct hts_b200_ctx {
 // ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------
+namespace {
+struct DeviceGuard {            // creating a context on another device must not move the caller's current device
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
+
 extern "C" hts_b200_ctx* hts_b200_create(int device) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return nullptr; }
+    DeviceGuard guard;
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return nullptr;
     if (device >= ndev || cudaSetDevice(device) != cudaSuccess) return nullptr;
     cudaDeviceProp prop;
@@ -189,6 +198,7 @@ extern "C" hts_b200_ctx* hts_b200_create(int device) {
 
 extern "C" void hts_b200_destroy(hts_b200_ctx* ctx) {
     if (!ctx) return;
+    DeviceGuard guard;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ctx->dec.release();
@@ -429,13 +439,31 @@ static std::vector<int> plan_chunks(bool enc, int nblk, const uint8_t* in_base, 
         }
         const uint64_t by_floor = (uint64_t)(steps * 130e-9 * 55e9);
         target = std::max(target, std::min<uint64_t>(std::min<uint64_t>(by_floor, 2048ull << 20), total_bytes / 3));
+        if (enc && total_bytes > (64ull << 20)) {
+            // Encode is bound by the host->device stream, which starts at once, and every chunk costs one round of
+            // latency-bound kernels K (histogram, tables, coder, assembly; rounds of consecutive chunks do not share
+            // SMs).  With n equal chunks the call takes  H/n + max((n-1) H/n, (n-1) K) + K + D/n  (H, D: copy times
+            // at ~55 GB/s; compressed output ~ a third of its capacity): take the n that minimises it.
+            uint64_t in_bytes = 0, cap_bytes = 0;
+            for (int i = 0; i < nblk; i++) { in_bytes += in_len[i]; cap_bytes += out_len[i]; }
+            const double H = in_bytes / 55e9, D = 0.35 * cap_bytes / 55e9, K = steps * 80e-9 + 3e-3;
+            int best_n = 1;
+            double best_t = 1e30;
+            for (int n = 1; n <= 16; n++) {
+                const double t = H / n + std::max((n - 1) * H / n, (n - 1) * K) + K + D / n;
+                if (t < best_t - 1e-9) { best_t = t; best_n = n; }
+            }
+            target = std::max<uint64_t>(32ull << 20, (total_bytes + best_n - 1) / best_n);
+        }
     }
     std::vector<int> cuts{0};
     {
-        // the first chunks are smaller (1/8, 1/4, 1/2 of the target) so that the device->host stream,
-        // the bottleneck of a decode, starts early instead of waiting for a full-size chunk
+        // decode: the first chunks are smaller (1/8, 1/4, 1/2 of the target) so that the device->host stream,
+        // its bottleneck, starts early instead of waiting for a full-size chunk.  Encode is bound by the
+        // host->device stream, which starts at once: equal chunks, as few as the floor above allows (every chunk
+        // costs one latency-bound round of kernels, and those of consecutive chunks do not share SMs).
         uint64_t acc = 0;
-        int ramp = total_bytes > 4 * target ? 3 : 0;
+        int ramp = (!enc && total_bytes > 4 * target) ? 3 : 0;
         for (int i = 0; i < nblk; i++) {
             uint64_t w = (uint64_t)in_len[i] + out_len[i];
             const uint64_t lim = std::max<uint64_t>(32ull << 20, target >> ramp);
@@ -444,6 +472,7 @@ static std::vector<int> plan_chunks(bool enc, int nblk, const uint8_t* in_base, 
         }
         // a small remainder would still cost a whole kernel round (its slowest stream): it joins the previous chunk
         if (cuts.size() > 1 && acc < target / 4) cuts.pop_back();
+        (void)0;
         cuts.push_back(nblk);
     }
     return cuts;
@@ -750,7 +779,13 @@ std::mutex g_multi_mu;
 std::map<int, hts_b200_ctx*> g_multi_ctx;
 std::vector<hts_b200_dev_stats> g_multi_stats;
 char g_multi_err[320] = {0};
-int g_multi_phased = -1;     // -1: from the environment (default: phased when ndev > 1)
+int g_multi_phased = -1;     // -1: from the environment, else measured (see run_multi)
+// Which copy policy a box wants depends on its host: on an 8 x B200 host device->host copies ran at 304 GB/s alone
+// and 134 GB/s with other devices' host->device copies in flight (phased wins), on a 2 x B200 host the two directions
+// simply share ~103 GB/s (full duplex wins: 80 vs 74 GB/s).  So it is measured: per device count the first large
+// call runs full duplex, the second phased, and later calls use the faster of the two (bytes per second).
+struct MultiAuto { int calls = 0; double rate[2] = {0, 0}; };
+std::map<int, MultiAuto> g_multi_auto;
 struct MultiReaper { ~MultiReaper() { for (auto& kv : g_multi_ctx) hts_b200_destroy(kv.second); g_multi_ctx.clear(); } } g_multi_reaper;
 
 int run_multi(bool enc, int ndev, const int* devices, int nblk, const uint8_t* in_base, const uint64_t* in_off,
@@ -770,8 +805,19 @@ int run_multi(bool enc, int ndev, const int* devices, int nblk, const uint8_t* i
         }
     }
     int phased = g_multi_phased;
-    if (phased < 0) { const char* e = getenv("HTSCODECS_B200_MULTI_PHASED"); phased = e ? atoi(e) != 0 : 1; }
+    if (phased < 0) { const char* e = getenv("HTSCODECS_B200_MULTI_PHASED"); if (e) phased = atoi(e) != 0; }
+    uint64_t job_bytes = 0;
+    for (int i = 0; i < nblk; i++) job_bytes += (uint64_t)in_len[i] + out_len[i];
+    MultiAuto* tune = nullptr;
     if (ndev == 1) phased = 0;
+    else if (phased < 0) {
+        if (job_bytes < (256ull << 20) * ndev) phased = 0;            // small jobs: latency, not link policy
+        else {
+            tune = &g_multi_auto[ndev];
+            phased = tune->calls == 0 ? 0 : tune->calls == 1 ? 1 : (tune->rate[1] > tune->rate[0] ? 1 : 0);
+        }
+    }
+    const double t_start = now_ms();
     std::vector<int> cuts(ndev + 1);
     hts_b200_partition(nblk, enc ? in_len : out_len, ndev, cuts.data());      // uncompressed bytes
     PhaseSync ps;
@@ -792,6 +838,11 @@ int run_multi(bool enc, int ndev, const int* devices, int nblk, const uint8_t* i
         });
     }
     for (auto& t : th) t.join();
+    if (tune) {
+        const double r = (double)job_bytes / std::max(1e-3, now_ms() - t_start);
+        if (tune->calls < 2) tune->rate[phased] = r; else tune->rate[phased] = 0.5 * (tune->rate[phased] + r);
+        tune->calls++;
+    }
     for (int d = 0; d < ndev; d++)
         if (rcs[d] != 0) {
             snprintf(g_multi_err, sizeof(g_multi_err), "device %d: %.250s", devices[d], g_multi_ctx[devices[d]]->err);
@@ -813,7 +864,7 @@ extern "C" int hts_b200_compress_batch_host_multi(int ndev, const int* devices, 
                                                   const int32_t* order) {
     return run_multi(true, ndev, devices, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, nullptr, order);
 }
-extern "C" void hts_b200_multi_set_phased(int phased) { std::lock_guard<std::mutex> lk(g_multi_mu); g_multi_phased = phased ? 1 : 0; }
+extern "C" void hts_b200_multi_set_phased(int phased) { std::lock_guard<std::mutex> lk(g_multi_mu); g_multi_phased = phased < 0 ? -1 : (phased ? 1 : 0); }
 extern "C" int hts_b200_multi_last_stats(hts_b200_dev_stats* out, int max) {
     std::lock_guard<std::mutex> lk(g_multi_mu);
     for (int i = 0; i < (int)g_multi_stats.size() && i < max; i++) out[i] = g_multi_stats[i];

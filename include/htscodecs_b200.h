@@ -195,11 +195,12 @@ int hts_b200_plan_chunks(int enc, int nblk, const uint8_t *in_base, const uint64
 
 /* Same contract as hts_b200_{un,}compress_batch_host, spread over devices[0 .. ndev).  The library keeps
  * one context per device (created on first use, reused, destroyed at exit); calls are serialised.
- * Copy phases are coordinated ACROSS devices: every device sends its inputs first, the threads meet at
- * a host-side barrier, then the results travel back (hosts whose device->host rate collapses while
- * other devices' host->device copies are in flight: 304 GB/s vs 134 GB/s aggregate on an 8 x B200 box).
- * hts_b200_multi_set_phased(0) lets every device run its own full-duplex pipeline instead; the
- * default is phased for ndev > 1 (environment: HTSCODECS_B200_MULTI_PHASED=0|1). */
+ * Copy phases can be coordinated ACROSS devices ("phased": every device sends its inputs first, the threads meet
+ * at a host-side barrier, then the results travel back) or every device runs its own full-duplex chunk pipeline.
+ * Which is faster is a property of the host: an 8 x B200 host moved 304 GB/s device->host alone but 134 GB/s with
+ * other devices' host->device copies in flight, a 2 x B200 host shares ~103 GB/s between the directions either way.
+ * So the library measures: per device count the first large call runs full duplex, the second phased, later ones
+ * the faster.  hts_b200_multi_set_phased(0 | 1) or HTSCODECS_B200_MULTI_PHASED=0|1 forces a policy. */
 int hts_b200_uncompress_batch_host_multi(int ndev, const int *devices, int nblk,
                                          const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
                                          uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
@@ -208,7 +209,7 @@ int hts_b200_compress_batch_host_multi(int ndev, const int *devices, int nblk,
                                        const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
                                        uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
                                        int32_t *status, const int32_t *order);
-void hts_b200_multi_set_phased(int phased);
+void hts_b200_multi_set_phased(int phased);   /* 1 phased, 0 full duplex per device, -1 measured (default) */
 
 /* Per-device breakdown of the last multi-device call (busy times from CUDA events on the copy and
  * compute streams, wall times from the host clock). */

@@ -73,7 +73,7 @@ def test_encode_uses_the_order_word():
     x32 = _plan(True, raw, cap, order=[hb.RANS_ORDER_X32] * n)
     way4 = _plan(True, raw, cap, order=[1] * n)
     legacy = _plan(True, raw, cap, order=[hb.ORDER_RANS4x8] * n)
-    assert len(way4) == 4 and len(legacy) == 4 and len(x32) > len(way4)
+    assert 3 <= len(way4) <= 4 and len(legacy) == len(way4) and len(x32) > len(way4)   # 2-3 chunks vs many
     # one 4-way block among X_32 ones sets the pace of its chunk, hence of the call
     mixed = _plan(True, raw, cap, order=[hb.RANS_ORDER_X32] * (n - 1) + [0])
     assert len(mixed) == len(way4)
@@ -86,3 +86,17 @@ def test_ragged_sizes_tile_exactly():
     c = _plan(False, in_len, out_len, first_byte=rng.integers(0, 256, 900).astype(np.uint8))
     b = _chunk_bytes(c, in_len, out_len)
     assert b.sum() == int(in_len.sum() + out_len.sum())
+
+
+def test_encode_chunks_are_equal_and_few():
+    """Encode is bound by the host->device stream, which starts at once: no small leading chunks, and as few chunks
+    as the kernels' latency floor allows (each chunk costs one round of latency-bound kernels)."""
+    n = 4096
+    raw, cap = [MiB] * n, [hb.rans_compress_bound_4x16(MiB, 0)] * n
+    x32 = _chunk_bytes(_plan(True, raw, cap, order=[hb.RANS_ORDER_X32] * n), raw, cap)
+    assert 4 <= len(x32) <= 16
+    assert x32[:-1].max() - x32[:-1].min() <= 3 * MiB                  # equal but for block granularity
+    dec = _chunk_bytes(_plan(False, [300 * 1024] * n, raw, first_byte=4), [300 * 1024] * n, raw)
+    assert len(dec) > len(x32) and dec[0] < dec[3] / 4                 # the decoder still ramps up
+    way4 = _chunk_bytes(_plan(True, raw, cap, order=[0] * n), raw, cap)
+    assert 2 <= len(way4) <= 4 and len(way4) < len(x32)               # a 4-way round of kernels is ~5 x longer

@@ -63,7 +63,7 @@ def test_multi_roundtrip_matches_the_checker(phased, oracle):
     assert all(s["wall_ms"] > 0 and s["kernel_ms"] > 0 and s["d2h_ms"] > 0 for s in st if s["nblk"])
     if phased and len(devs) > 1:
         assert all(s["d2h_phase_ms"] > 0 for s in st)
-    hb.multi_set_phased(True)
+    hb.multi_set_phased(None)
 
 
 def test_multi_bad_block_does_not_strand_the_other_devices(oracle):

@@ -105,8 +105,8 @@ def main():
             pin_u = hb.PinnedArray(nblk * n + 64)
             u_off = np.arange(nblk, dtype=np.uint64) * n
             status = np.zeros(nblk, np.int32)
-            for phased in ((0, 1) if nd > 1 else (0,)):
-                hb.multi_set_phased(phased)
+            for phased in ((0, 1, None) if nd > 1 else (0,)):
+                hb.multi_set_phased(None if phased is None else bool(phased))
                 ts = []
                 for r in range(args.reps + 1):
                     out_len = np.full(nblk, n, np.uint32)
@@ -117,7 +117,7 @@ def main():
                 for i in (0, nblk // 2, nblk - 1):
                     assert np.array_equal(pin_u.array[i * n:(i + 1) * n], blocks[i % distinct])
                 gbs = nblk * n / min(ts[1:]) / 1e9
-                key = f"flags{f:#x}_ndev{nd}_{'phased' if phased else 'duplex'}"
+                key = f"flags{f:#x}_ndev{nd}_{'auto' if phased is None else 'phased' if phased else 'duplex'}"
                 out[key] = {"e2e_decode_GBs": round(gbs, 1), "stats": hb.multi_last_stats()}
                 print(key, round(gbs, 1), "GB/s", json.dumps(out[key]["stats"]), flush=True)
             del pin_c, pin_u
