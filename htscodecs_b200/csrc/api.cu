@@ -120,7 +120,7 @@ struct Stage {
     }
 };
 
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 4;   // chunks in flight: a chunk's copy-in waits for the chunk NSTAGE before it to be collected
 
 // job-kind sets for the host's "which kernels can be needed" hint
 constexpr uint32_t K_R8_O0 = (1u << JK_R8_O0) | (1u << JK_R8_O0R8) | (1u << JK_R8_O0R16);
@@ -898,6 +898,16 @@ extern "C" int hts_b200_compress_batch_dev(hts_b200_ctx* ctx, int nblk, const ui
 // ------------------------------------------------------------------------------------------
 // pointer-array wrappers
 // ------------------------------------------------------------------------------------------
+// Gather / scatter between the caller's per-block buffers and the pinned staging arena.  A single thread copies at
+// ~10 GB/s, which for a large batch costs more than the GPU work: split the blocks over a few host threads.
+template <typename F> static void for_blocks_parallel(int nblk, uint64_t bytes, F f) {
+    const int nt = (int)std::min<uint64_t>(8, std::max<uint64_t>(1, bytes >> 25));     // one thread per 32 MiB, at most 8
+    if (nt <= 1) { f(0, nblk); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([=] { f((int)((long long)nblk * t / nt), (int)((long long)nblk * (t + 1) / nt)); });
+    for (auto& x : th) x.join();
+}
+
 static int run_ptr_batch(hts_b200_ctx* ctx, bool enc, int nblk, const unsigned char* const* in,
                          const unsigned int* in_size, unsigned char* const* out, unsigned int* out_size,
                          const int* order, int* status, const uint8_t* method) {
@@ -910,16 +920,21 @@ static int run_ptr_batch(hts_b200_ctx* ctx, bool enc, int nblk, const unsigned c
         off[nblk + i] = ob; ob += align_up(out_size[i], 16);
     }
     if (ctx->pin_in.ensure(ib + 16) || ctx->pin_out.ensure(ob + 16)) { snprintf(ctx->err, sizeof(ctx->err), "out of pinned memory"); return -1; }
-    for (int i = 0; i < nblk; i++) memcpy(ctx->pin_in.p + off[i], in[i], in_size[i]);
+    uint8_t* const pin_in = ctx->pin_in.p;
+    const uint64_t* const offp = off.data();
+    for_blocks_parallel(nblk, ib, [=](int a, int b) { for (int i = a; i < b; i++) memcpy(pin_in + offp[i], in[i], in_size[i]); });
     std::vector<int32_t> st(nblk), ord;
     if (order) ord.assign(order, order + nblk);
     int rc = run_host_batch(ctx, enc, nblk, ctx->pin_in.p, off.data(), in_size, ctx->pin_out.p, off.data() + nblk,
                             out_size, st.data(), method, order ? ord.data() : nullptr);
     if (rc) return rc;
-    for (int i = 0; i < nblk; i++) {
-        status[i] = st[i];
-        if (st[i] == 0) memcpy(out[i], ctx->pin_out.p + off[nblk + i], out_size[i]);
-    }
+    uint64_t ob_done = 0;
+    for (int i = 0; i < nblk; i++) { status[i] = st[i]; if (st[i] == 0) ob_done += out_size[i]; }
+    const uint8_t* const pin_out = ctx->pin_out.p;
+    const int32_t* const stp = st.data();
+    for_blocks_parallel(nblk, ob_done, [=](int a, int b) {
+        for (int i = a; i < b; i++) if (stp[i] == 0) memcpy(out[i], pin_out + offp[nblk + i], out_size[i]);
+    });
     return 0;
 }
 
