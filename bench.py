@@ -637,8 +637,8 @@ def run_ours(args, rank, world, local_rank):
         e2e_stages = hb.multi_last_stats()
         e2e.update({"value": tot * BLOCK / e2e_s / 1e9, "steps": e2e_steps, "devices": devs,
                     "h2d_bytes_per_step": len(devs) * c_bytes, "d2h_bytes_per_step": tot * BLOCK,
-                    "api": "hts_b200_uncompress_batch_host_multi (one call, one host thread + context per device, "
-                           + ("copy phases coordinated across devices)" if len(devs) > 1 else "single device: full-duplex chunk pipeline)"),
+                    "api": "hts_b200_uncompress_batch_host_multi (one call, one host thread + context per device, full-duplex "
+                           "chunk pipelines" + (" fed from a shared chunk queue)" if len(devs) > 1 else ")"),
                     "gpu_launches_per_step": (hb.multi_launch_count() - ml0) // (2 + e2e_steps),
                     "timer": "host perf_counter around the synchronous call"})
         del pin_in, pin_out
@@ -770,7 +770,8 @@ def main():
     ap.add_argument("--skip-mixed", action="store_true", help="skip the mixed-flag corpus leg (configs[4])")
     ap.add_argument("--mixed-blocks", type=int, default=65536, help="blocks of the mixed corpus over ALL GPUs (64 GiB)")
     ap.add_argument("--phased", default="auto", choices=["auto", "on", "off"],
-                    help="e2e leg with N > 1: coordinate the copy phases across devices (default: the library's choice)")
+                    help="e2e leg with N > 1: 'on' = all devices send, barrier, then fetch (static partition); default: "
+                         "full-duplex pipelines fed from a shared chunk queue")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

@@ -25,8 +25,8 @@ EXPORTS = [
     "rans_uncompress_to_4x16", "rans_uncompress_4x16", "rans_uncompress", "rans_compress",
     "hts_b200_compress_bound_4x8",
     "hts_b200_create", "hts_b200_destroy", "hts_b200_last_error", "hts_b200_launch_count",
-    "hts_b200_stream", "hts_b200_uncompress_batch_dev", "hts_b200_uncompress_batch_host",
-    "hts_b200_compress_batch_dev", "hts_b200_compress_batch_host", "rans4x16_uncompress_batch",
+    "hts_b200_stream", "hts_b200_scratch_bytes", "hts_b200_uncompress_batch_dev", "hts_b200_uncompress_batch_host",
+    "hts_b200_compress_batch_dev", "hts_b200_compress_batch_dev_async", "hts_b200_compress_batch_host", "rans4x16_uncompress_batch",
     "rans4x16_compress_batch", "rans4x16_compress_best_batch", "hts_b200_peek_size", "hts_b200_host_alloc", "hts_b200_host_free",
     "hts_b200_set_copy_duplex", "hts_b200_plan_chunks",
     "hts_b200_uncompress_batch_host_multi", "hts_b200_compress_batch_host_multi", "hts_b200_multi_set_phased",
@@ -75,11 +75,14 @@ def load_library():
     lib.hts_b200_launch_count.argtypes = [vp]
     lib.hts_b200_stream.restype = vp
     lib.hts_b200_stream.argtypes = [vp]
+    lib.hts_b200_scratch_bytes.restype = C.c_size_t
+    lib.hts_b200_scratch_bytes.argtypes = [vp]
     batch = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.hts_b200_uncompress_batch_dev.argtypes = batch + [C.c_int]
     lib.hts_b200_uncompress_batch_host.argtypes = batch
     lib.hts_b200_compress_batch_dev.argtypes = batch + [C.c_int]
     lib.hts_b200_compress_batch_host.argtypes = batch
+    lib.hts_b200_compress_batch_dev_async.argtypes = batch + [vp, vp]
     lib.rans4x16_uncompress_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
     lib.rans4x16_compress_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.rans4x16_compress_best_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp]
@@ -338,6 +341,11 @@ class Context:
     def stream(self):
         return self.lib.hts_b200_stream(self.h)
 
+    @property
+    def scratch_bytes(self):
+        """Device memory held for work lists, scratch arenas and staging."""
+        return int(self.lib.hts_b200_scratch_bytes(self.h))
+
     def set_copy_duplex(self, full):
         """False: send every input of a host-buffer call before fetching any result (half duplex)."""
         self.lib.hts_b200_set_copy_duplex(self.h, 1 if full else 0)
@@ -361,6 +369,13 @@ class Context:
         self._check(self.lib.hts_b200_compress_batch_dev(
             self.h, nblk, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
             _ptr(out_len), _ptr(status), _ptr(order), 1 if sync else 0))
+
+    def compress_batch_dev_async(self, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, order,
+                                 host_in_len, host_order):
+        """Device-resident encode that never synchronises: host_in_len / host_order are numpy copies of in_len / order."""
+        self._check(self.lib.hts_b200_compress_batch_dev_async(
+            self.h, nblk, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
+            _ptr(out_len), _ptr(status), _ptr(order), _ptr(host_in_len), _ptr(host_order)))
 
     # -- host-resident (numpy arrays; pinned or pageable) ------------------------------------------
     def uncompress_batch_host(self, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status,

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <map>
@@ -219,6 +220,13 @@ extern "C" const char* hts_b200_last_error(const hts_b200_ctx* ctx) { return ctx
 extern "C" unsigned long long hts_b200_launch_count(const hts_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* hts_b200_stream(const hts_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" void hts_b200_set_copy_duplex(hts_b200_ctx* ctx, int full) { if (ctx) ctx->full_duplex = full != 0; }
+extern "C" size_t hts_b200_scratch_bytes(const hts_b200_ctx* ctx) {
+    if (!ctx) return 0;
+    auto dec = [](const DecSlot& d) { return d.work.cap + d.lists.cap + d.arena.cap + 4 * d.cap_save.cap; };
+    size_t n = dec(ctx->dec) + encode_device_bytes(ctx->enc);
+    for (const auto& S : ctx->stage) n += dec(S.dec) + encode_device_bytes(S.enc) + S.d_in.cap + S.d_out.cap + 8 * S.d_off.cap + 4 * S.d_u32.cap + S.d_method.cap;
+    return n + ctx->best_in.cap + ctx->best_cand.cap + ctx->best_out.cap + 8 * ctx->best_off.cap + 4 * ctx->best_u32.cap;
+}
 extern "C" void* hts_b200_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }   // pinned for every device
@@ -400,6 +408,12 @@ struct HostRun {                 // optional extras of one host-buffer call
     PhaseSync* phase = nullptr;  // non-null: phased copies with a cross-device rendezvous
     bool arrived = false;
     hts_b200_dev_stats* stats = nullptr;
+    // multi-device calls, full-duplex policy: the chunks of the WHOLE batch and a cursor shared by the device threads --
+    // a device takes the next chunk whenever one of its pipeline stages is free, so devices behind a slower host link
+    // (or sharing one) simply end up with fewer chunks
+    const std::vector<int>* cuts = nullptr;
+    std::atomic<int>* cursor = nullptr;
+    const uint32_t* caps = nullptr;      // the batch's capacities (a copy of out_len taken before any thread writes sizes)
 };
 
 double now_ms() {
@@ -483,10 +497,14 @@ static int run_host_batch_body(hts_b200_ctx* ctx, bool enc, int nblk, const uint
                                const uint32_t* in_len, uint8_t* out_base, const uint64_t* out_off, uint32_t* out_len,
                                int32_t* status, const uint8_t* method, const int32_t* order, HostRun* hr) {
     CK(cudaSetDevice(ctx->device));
-    const std::vector<int> cuts = plan_chunks(enc, nblk, in_base, in_off, in_len, out_len, method, order);
+    const bool shared_queue = hr && hr->cuts && hr->cursor;
+    const std::vector<int> own_cuts = shared_queue ? std::vector<int>() : plan_chunks(enc, nblk, in_base, in_off, in_len, out_len, method, order);
+    const std::vector<int>& cuts = shared_queue ? *hr->cuts : own_cuts;
     const int nchunk = (int)cuts.size() - 1;
     std::vector<int> redo;
-    std::vector<uint32_t> caps(out_len, out_len + nblk);           // capacities, for retries
+    // capacities (out_len is overwritten with sizes as chunks complete); shared by the threads of a multi-device call
+    const std::vector<uint32_t> own_caps = (hr && hr->caps) ? std::vector<uint32_t>() : std::vector<uint32_t>(out_len, out_len + nblk);
+    const uint32_t* const caps = (hr && hr->caps) ? hr->caps : own_caps.data();
     hts_b200_dev_stats* stats = hr ? hr->stats : nullptr;
 
     auto launch_out = [&](Stage& S) -> int {                         // device->host half of a chunk
@@ -519,7 +537,7 @@ static int run_host_batch_body(hts_b200_ctx* ctx, bool enc, int nblk, const uint
     auto launch_chunk = [&](int k, Stage& S, bool defer_out) -> int {
         const int a = cuts[k], b = cuts[k + 1], n = b - a;
         Range ri = span_of(in_off, in_len, a, b);
-        Range ro = span_of(out_off, caps.data(), a, b);
+        Range ro = span_of(out_off, caps, a, b);
         const bool in_mirror = ri.lay != SCATTER;                    // reading a few padding bytes along is harmless
         const bool out_mirror = ro.lay == TILED || ro.lay == STRIDED;
         // staging layout mirrors the host layout where one (pitched) copy moves it, else blocks are packed 256-byte aligned
@@ -617,6 +635,7 @@ static int run_host_batch_body(hts_b200_ctx* ctx, bool enc, int nblk, const uint
             if (dec_needs_retry(S.dec, &ab)) { ctx->arena_hint = std::max(ctx->arena_hint, ab); retry = true; }
             else ctx->arena_hint = std::max(ctx->arena_hint, (size_t)S.dec.h_work.p[1].arena_used);
         }
+        if (enc && encode_needs_retry(S.enc)) retry = true;
         if (retry) { redo.push_back(k); return 0; }
         if (enc) {
             const uint32_t* len = S.h_u32.p + n;
@@ -643,20 +662,28 @@ static int run_host_batch_body(hts_b200_ctx* ctx, bool enc, int nblk, const uint
     };
 
     const bool phased = hr && hr->phase;
-    if (!phased && (ctx->full_duplex || nchunk == 1)) {
-        // ---- software pipeline: chunk k uses stage k % NSTAGE; collect k - NSTAGE before reusing it
-        for (int k = 0; k < nchunk; k++) {
-            Stage& S = ctx->stage[k % NSTAGE];
-            if (k >= NSTAGE) {
+    if (!phased && (ctx->full_duplex || nchunk == 1 || shared_queue)) {
+        // ---- software pipeline: the j-th chunk this context takes uses stage j % NSTAGE; the chunk that used the
+        // stage before is collected first.  Chunks come in order, or -- multi-device call -- from the shared cursor.
+        int inflight[NSTAGE];
+        int taken = 0, local_next = 0;
+        for (;;) {
+            const int k = shared_queue ? hr->cursor->fetch_add(1) : local_next++;
+            if (k >= nchunk) break;
+            Stage& S = ctx->stage[taken % NSTAGE];
+            if (taken >= NSTAGE) {
                 CK(cudaEventSynchronize(S.d2h_done));
-                if (collect_chunk(k - NSTAGE, S)) return -1;
+                if (collect_chunk(inflight[taken % NSTAGE], S)) return -1;
             }
             if (launch_chunk(k, S, false)) return -1;
+            inflight[taken % NSTAGE] = k;
+            taken++;
+            if (stats && shared_queue) stats->nblk += cuts[k + 1] - cuts[k];
         }
-        for (int k = std::max(0, nchunk - NSTAGE); k < nchunk; k++) {
-            Stage& S = ctx->stage[k % NSTAGE];
+        for (int j = std::max(0, taken - NSTAGE); j < taken; j++) {
+            Stage& S = ctx->stage[j % NSTAGE];
             CK(cudaEventSynchronize(S.d2h_done));
-            if (collect_chunk(k, S)) return -1;
+            if (collect_chunk(inflight[j % NSTAGE], S)) return -1;
         }
     } else {
         // ---- half duplex: every chunk has its own stage; all host->device copies (and the kernels behind
@@ -779,13 +806,7 @@ std::mutex g_multi_mu;
 std::map<int, hts_b200_ctx*> g_multi_ctx;
 std::vector<hts_b200_dev_stats> g_multi_stats;
 char g_multi_err[320] = {0};
-int g_multi_phased = -1;     // -1: from the environment, else measured (see run_multi)
-// Which copy policy a box wants depends on its host: on an 8 x B200 host device->host copies ran at 304 GB/s alone
-// and 134 GB/s with other devices' host->device copies in flight (phased wins), on a 2 x B200 host the two directions
-// simply share ~103 GB/s (full duplex wins: 80 vs 74 GB/s).  So it is measured: per device count the first large
-// call runs full duplex, the second phased, and later calls use the faster of the two (bytes per second).
-struct MultiAuto { int calls = 0; double rate[2] = {0, 0}; };
-std::map<int, MultiAuto> g_multi_auto;
+int g_multi_phased = -1;     // -1: from the environment (default 0)
 struct MultiReaper { ~MultiReaper() { for (auto& kv : g_multi_ctx) hts_b200_destroy(kv.second); g_multi_ctx.clear(); } } g_multi_reaper;
 
 int run_multi(bool enc, int ndev, const int* devices, int nblk, const uint8_t* in_base, const uint64_t* in_off,
@@ -804,45 +825,44 @@ int run_multi(bool enc, int ndev, const int* devices, int nblk, const uint8_t* i
             g_multi_ctx[devices[d]] = c;
         }
     }
+    // Copy policy.  Default: every device runs its own full-duplex chunk pipeline and takes chunks of the whole batch
+    // from a shared cursor.  Phased (all devices send, meet at a barrier, then fetch; static partition on uncompressed
+    // bytes) is there for hosts that lose device->host rate while host->device copies are in flight; on the boxes
+    // measured in round 2 it was never faster (2 x B200: 86 vs 98 GB/s; 8 x B200: 82 vs 85 before balancing).
     int phased = g_multi_phased;
-    if (phased < 0) { const char* e = getenv("HTSCODECS_B200_MULTI_PHASED"); if (e) phased = atoi(e) != 0; }
-    uint64_t job_bytes = 0;
-    for (int i = 0; i < nblk; i++) job_bytes += (uint64_t)in_len[i] + out_len[i];
-    MultiAuto* tune = nullptr;
+    if (phased < 0) { const char* e = getenv("HTSCODECS_B200_MULTI_PHASED"); phased = e ? atoi(e) != 0 : 0; }
     if (ndev == 1) phased = 0;
-    else if (phased < 0) {
-        if (job_bytes < (256ull << 20) * ndev) phased = 0;            // small jobs: latency, not link policy
-        else {
-            tune = &g_multi_auto[ndev];
-            phased = tune->calls == 0 ? 0 : tune->calls == 1 ? 1 : (tune->rate[1] > tune->rate[0] ? 1 : 0);
-        }
-    }
-    const double t_start = now_ms();
+    const std::vector<uint32_t> caps(out_len, out_len + nblk);
     std::vector<int> cuts(ndev + 1);
-    hts_b200_partition(nblk, enc ? in_len : out_len, ndev, cuts.data());      // uncompressed bytes
+    std::vector<int> chunks;
+    std::atomic<int> cursor{0};
+    if (phased) hts_b200_partition(nblk, enc ? in_len : out_len, ndev, cuts.data());      // uncompressed bytes
+    else chunks = plan_chunks(enc, nblk, in_base, in_off, in_len, out_len, method, order);
     PhaseSync ps;
     ps.want = ndev;
     std::vector<int> rcs(ndev, 0);
     std::vector<std::thread> th;
     for (int d = 0; d < ndev; d++) {
         th.emplace_back([&, d] {
-            const int a = cuts[d], n = cuts[d + 1] - a;
             hts_b200_ctx* c = g_multi_ctx[devices[d]];
             hts_b200_dev_stats& st = g_multi_stats[d];
-            st.device = devices[d]; st.first_blk = a; st.nblk = n;
+            st.device = devices[d];
             HostRun hr;
-            hr.phase = phased ? &ps : nullptr;
             hr.stats = &st;
-            rcs[d] = run_host_batch(c, enc, n, in_base, in_off + a, in_len + a, out_base, out_off + a, out_len + a,
-                                    status + a, method ? method + a : nullptr, order ? order + a : nullptr, &hr);
+            if (phased) {
+                const int a = cuts[d], n = cuts[d + 1] - a;
+                st.first_blk = a; st.nblk = n;
+                hr.phase = &ps;
+                rcs[d] = run_host_batch(c, enc, n, in_base, in_off + a, in_len + a, out_base, out_off + a, out_len + a,
+                                        status + a, method ? method + a : nullptr, order ? order + a : nullptr, &hr);
+            } else {
+                st.first_blk = -1; st.nblk = 0;                      // counted as chunks are taken
+                hr.cuts = &chunks; hr.cursor = &cursor; hr.caps = caps.data();
+                rcs[d] = run_host_batch(c, enc, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, method, order, &hr);
+            }
         });
     }
     for (auto& t : th) t.join();
-    if (tune) {
-        const double r = (double)job_bytes / std::max(1e-3, now_ms() - t_start);
-        if (tune->calls < 2) tune->rate[phased] = r; else tune->rate[phased] = 0.5 * (tune->rate[phased] + r);
-        tune->calls++;
-    }
     for (int d = 0; d < ndev; d++)
         if (rcs[d] != 0) {
             snprintf(g_multi_err, sizeof(g_multi_err), "device %d: %.250s", devices[d], g_multi_ctx[devices[d]]->err);
@@ -878,21 +898,47 @@ extern "C" unsigned long long hts_b200_multi_launch_count(void) {
 }
 extern "C" const char* hts_b200_multi_last_error(void) { return g_multi_err; }
 
-extern "C" int hts_b200_compress_batch_dev(hts_b200_ctx* ctx, int nblk, const uint8_t* in_base,
-                                           const uint64_t* in_off, const uint32_t* in_len, uint8_t* out_base,
-                                           const uint64_t* out_off, uint32_t* out_len, int32_t* status,
-                                           const int32_t* order, int sync) {
+static int compress_dev(hts_b200_ctx* ctx, int nblk, const uint8_t* in_base, const uint64_t* in_off, const uint32_t* in_len,
+                        uint8_t* out_base, const uint64_t* out_off, uint32_t* out_len, int32_t* status, const int32_t* order,
+                        const uint32_t* h_in_len, const int32_t* h_order, int sync) {
     if (!ctx || nblk < 0 || !order) return -1;
     if (nblk == 0) return 0;
     CK(cudaSetDevice(ctx->device));
     EncodeBatch eb;
     eb.in_base = in_base; eb.in_off = in_off; eb.in_len = in_len; eb.out_base = out_base; eb.out_off = out_off;
     eb.out_len = out_len; eb.status = status; eb.order = order; eb.nblk = nblk;
-    int l = encode_run(ctx->enc, eb, nullptr, nullptr, ctx->stream, ctx->err, sizeof(ctx->err));
-    if (l < 0) return -1;
-    ctx->launches += l;
-    if (sync) CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        // out_len is capacity in, size out: a retry needs the capacities back
+        if (sync) {
+            if (ctx->dec.cap_save.ensure(nblk)) { snprintf(ctx->err, sizeof(ctx->err), "out of device memory"); return -1; }
+            if (attempt == 0) CK(cudaMemcpyAsync(ctx->dec.cap_save.p, out_len, 4 * (size_t)nblk, cudaMemcpyDeviceToDevice, ctx->stream));
+            else CK(cudaMemcpyAsync(out_len, ctx->dec.cap_save.p, 4 * (size_t)nblk, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        int l = encode_run(ctx->enc, eb, h_in_len, h_order, ctx->stream, ctx->err, sizeof(ctx->err));
+        if (l < 0) return -1;
+        ctx->launches += l;
+        if (!sync) return 0;
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!encode_needs_retry(ctx->enc)) return 0;                 // (rare: an order-1 alphabet larger than the arena was sized for)
+    }
+    snprintf(ctx->err, sizeof(ctx->err), "encode arena kept overflowing");
+    return -1;
+}
+
+extern "C" int hts_b200_compress_batch_dev(hts_b200_ctx* ctx, int nblk, const uint8_t* in_base,
+                                           const uint64_t* in_off, const uint32_t* in_len, uint8_t* out_base,
+                                           const uint64_t* out_off, uint32_t* out_len, int32_t* status,
+                                           const int32_t* order, int sync) {
+    return compress_dev(ctx, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, order, nullptr, nullptr, sync);
+}
+
+extern "C" int hts_b200_compress_batch_dev_async(hts_b200_ctx* ctx, int nblk, const uint8_t* in_base,
+                                                 const uint64_t* in_off, const uint32_t* in_len, uint8_t* out_base,
+                                                 const uint64_t* out_off, uint32_t* out_len, int32_t* status,
+                                                 const int32_t* order, const uint32_t* host_in_len,
+                                                 const int32_t* host_order) {
+    if (!host_in_len || !host_order) return -1;
+    return compress_dev(ctx, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, order, host_in_len, host_order, 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1022,11 +1068,20 @@ extern "C" int rans4x16_compress_best_batch(hts_b200_ctx* ctx, int nblk, const u
         eb.out_base = ctx->best_cand.p; eb.out_off = ctx->best_off.p + ncand; eb.out_len = d_c_len;
         eb.status = reinterpret_cast<int32_t*>(d_st); eb.order = reinterpret_cast<const int32_t*>(d_ord);
         eb.nblk = (int)ncand;
-        int l = encode_run(ctx->enc, eb, h_in_len, reinterpret_cast<const int32_t*>(h_ord), st, ctx->err, sizeof(ctx->err));
-        if (l < 0) return -1;
-        ctx->launches += l;
-        CK(cudaMemcpyAsync(h_c_len, d_c_len, 8 * ncand, cudaMemcpyDeviceToHost, st));     // lengths + status
-        CK(cudaStreamSynchronize(st));
+        const std::vector<uint32_t> bounds(h_c_len, h_c_len + ncand);
+        for (int attempt = 0;; attempt++) {
+            if (attempt) {                                               // the arena was too small: capacities back, run again
+                memcpy(h_c_len, bounds.data(), 4 * ncand);
+                memset(h_st, 0, 4 * ncand);
+                CK(cudaMemcpyAsync(ctx->best_u32.p, ctx->best_hu32.p, 16 * ncand, cudaMemcpyHostToDevice, st));
+            }
+            int l = encode_run(ctx->enc, eb, h_in_len, reinterpret_cast<const int32_t*>(h_ord), st, ctx->err, sizeof(ctx->err));
+            if (l < 0) return -1;
+            ctx->launches += l;
+            CK(cudaMemcpyAsync(h_c_len, d_c_len, 8 * ncand, cudaMemcpyDeviceToHost, st));     // lengths + status
+            CK(cudaStreamSynchronize(st));
+            if (!encode_needs_retry(ctx->enc) || attempt >= 5) break;
+        }
         // ---- pick the winners (first strictly smallest, :1280), gather them densely, fetch
         uint64_t* h_src = ctx->best_hoff.p + 2 * ncand; uint64_t* h_dst = h_src + nb;
         std::vector<uint32_t> wlen(nb);

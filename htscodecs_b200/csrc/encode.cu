@@ -56,7 +56,9 @@ struct EncStream {
     EncSym* syms;          // order-0: 256 entries; order-1: ns x ns entries (compact)
     uint8_t* ctab;         // scratch for the order-0 compressed order-1 table
     uint32_t codec;        // 0: rANS Nx16 (CRAM 3.1), 1: legacy rANS 4x8 (CRAM 3.0; byte-wise renormalisation)
-    uint32_t pad1;
+    uint32_t hdr;          // != 0: the stream is built IN the block's own output region, `hdr` bytes in (a plain leaf:
+                           // [flags][varint n] or the 9-byte 4x8 header precede the table); out / cap are patched by
+                           // enc_fix_kernel and enc_finish_kernel only moves the payload down behind the table
 };
 
 struct EncLeaf {
@@ -104,7 +106,20 @@ struct EncWork {
     uint32_t vcount[16];
     uint32_t* vlist;
     uint32_t o0_lo, o1_lo;         // large batches: 4-way alphabets up to these sizes go to the compact-table variants
+    // Order-1 scratch that depends on the alphabet found by the histogram pass: pair counts and encoder symbols of
+    // alphabets beyond 16 symbols (ns x ns x 20 bytes) and the staging area of a table worth compressing come from this
+    // arena (bump allocation; `overflow` makes the host retry with a larger one).  Small alphabets never touch it.
+    uint8_t* arena;
+    unsigned long long arena_cap, arena_used;
+    uint32_t overflow;
 };
+
+__device__ __forceinline__ uint8_t* enc_arena_alloc(EncWork* W, uint64_t bytes) {
+    bytes = (bytes + 255) & ~255ull;
+    unsigned long long at = atomicAdd(&W->arena_used, (unsigned long long)bytes);
+    if (at + bytes > W->arena_cap) { W->overflow = 1; return nullptr; }
+    return W->arena + at;
+}
 
 __constant__ double c_log10[257];   // log(1024 + k)  (host libm, see encode_init)
 __constant__ double c_log12[257];   // log(4096 + k)
@@ -580,6 +595,17 @@ __global__ void __launch_bounds__(HT) enc_hist_kernel(EncWork* W) {
         __syncthreads();
         const uint32_t ns = s_ns;
         const uint32_t seg = n / nway;
+        if (ns > 16) {                                               // beyond the stream's own 256-entry areas: from the arena
+            __shared__ int s_noarena;
+            if (tid == 0) {
+                uint8_t* a = enc_arena_alloc(W, (uint64_t)ns * ns * 20);
+                s_noarena = a == nullptr;
+                if (a) { S.F1 = reinterpret_cast<uint32_t*>(a + (size_t)ns * ns * 16); S.syms = reinterpret_cast<EncSym*>(a); }
+                else S.size = 0xffffffffu;
+            }
+            __syncthreads();
+            if (s_noarena) continue;
+        }
         if (ns <= O1_PRIV_NS) {
             // hist1_4, utils.h:137-202: every adjacent pair of the whole buffer, first context 0
             for (uint32_t k = tid; k < ns * ns; k += HT) ptot[k] = 0;
@@ -894,6 +920,7 @@ __global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
         const uint32_t n = S.n;
         const bool legacy = S.codec != 0;
         if (n == 0) { if (tid == 0) { S.size = legacy ? 0xffffffffu : 0u; S.tab_len = 0; } continue; }   // :405-406
+        if (S.size == 0xffffffffu) continue;                         // no table space (see enc_hist_kernel)
         if (S.order_eff == 0) {
             if (tid == 0) {
                 uint32_t tab = 0;
@@ -1103,6 +1130,15 @@ __global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
         if (tlen) {                                                  // CTA-uniform
             const uint32_t usz = tlen - 1;
             const uint32_t ccap = ((usz + usz / 16 + 1024) & ~15u);
+            if (tid == 0) {
+                S.ctab = enc_arena_alloc(W, (uint64_t)ccap + 1024 + 4096 + 64);
+                if (!S.ctab) S.size = 0xffffffffu;                   // the choice below decides output bytes: fail, never guess
+                s_res[0] = S.ctab != nullptr;
+            }
+            __syncthreads();
+            const bool have = s_res[0] != 0;
+            __syncthreads();
+            if (!have) continue;
             const uint32_t csz = nested_o0_encode(tab + 1, usz, S.ctab, ccap, Fs, nsyms, s_res);
             if (csz && csz + 6 < tlen) {
                 uint32_t hdr = 0;
@@ -1446,6 +1482,21 @@ __device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint3
     for (uint32_t i = head + nv * 16 + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
+// The same for a destination BELOW an overlapping source (the payload of a stream built in place moves down behind its
+// table): tile by tile, every thread reads its 16 bytes before any thread writes the tile.
+__device__ __forceinline__ void cta_move_down(uint8_t* dst, const uint8_t* src, uint32_t n) {
+    if (dst == src || n == 0) return;                       // (CTA-uniform)
+    for (uint32_t t0 = 0; t0 < n; t0 += blockDim.x * 16) {
+        const uint32_t at = t0 + threadIdx.x * 16;
+        uint8_t v[16];
+        const uint32_t cnt = at < n ? min(16u, n - at) : 0u;
+        for (uint32_t k = 0; k < cnt; k++) v[k] = src[at + k];
+        __syncthreads();
+        for (uint32_t k = 0; k < cnt; k++) dst[at + k] = v[k];
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) enc_finish_kernel(EncWork* W) {
     __shared__ uint32_t s_hdr, s_fail, s_cat;
     for (uint32_t li = blockIdx.x; li < W->nleaves; li += gridDim.x) {
@@ -1465,7 +1516,8 @@ __global__ void __launch_bounds__(256) enc_finish_kernel(EncWork* W) {
                 out[0] = (uint8_t)B.order_eff;
                 for (int k = 0; k < 4; k++) { out[1 + k] = (uint8_t)((total - 9) >> (8 * k)); out[5 + k] = (uint8_t)(L.n >> (8 * k)); }
             }
-            if (!bad) {
+            if (!bad && B.hdr) cta_move_down(out + 9 + B.tab_len, B.out + B.pay_off, pay);   // table already in place
+            else if (!bad) {
                 cta_copy(out + 9, B.out, B.tab_len);
                 cta_copy(out + 9 + B.tab_len, B.out + B.pay_off, pay);
             }
@@ -1519,7 +1571,10 @@ __global__ void __launch_bounds__(256) enc_finish_kernel(EncWork* W) {
         const uint32_t cur_n = L.cur_n;
         uint32_t body;
         if (s_cat) { cta_copy(out + hdr, B.src, cur_n); body = cur_n; }
-        else {
+        else if (B.hdr) {                                            // built in place (hdr == B.hdr): the table is where it belongs
+            cta_move_down(out + hdr + B.tab_len, B.out + B.pay_off, B.cap - B.pay_off);
+            body = B.size;
+        } else {
             cta_copy(out + hdr, B.out, B.tab_len);
             cta_copy(out + hdr + B.tab_len, B.out + B.pay_off, B.cap - B.pay_off);
             body = B.size;
@@ -1547,7 +1602,11 @@ __global__ void __launch_bounds__(256) enc_block_kernel(EncWork* W, uint32_t* ou
             continue;
         }
         if (B.mode == 0 || B.mode == 4) {
-            if (threadIdx.x == 0) { const EncLeaf& L = W->leaves[B.leaf0]; out_len[b] = L.out_size; status[b] = L.status; }
+            if (threadIdx.x == 0) {
+                const EncLeaf& L = W->leaves[B.leaf0];
+                out_len[b] = L.out_size;
+                status[b] = (L.status == ST_INTERNAL && W->overflow) ? ST_ARENA : L.status;
+            }
             continue;
         }
         // stripe, :1182-1215
@@ -1572,7 +1631,7 @@ __global__ void __launch_bounds__(256) enc_block_kernel(EncWork* W, uint32_t* ou
             }
             s_hdr = hdr; s_st = st;
             out_len[b] = hdr + pay;
-            status[b] = st;
+            status[b] = (st == ST_INTERNAL && W->overflow) ? ST_ARENA : st;
         }
         __syncthreads();
         for (uint32_t j = 0; j < B.N; j++) {
@@ -1596,7 +1655,16 @@ __global__ void enc_fix_kernel(EncWork* W, const uint8_t* in_base, const uint64_
     if (B.mode == 0 || B.mode == 4) {
         EncLeaf& L = W->leaves[B.leaf0];
         L.src = B.in; L.out = fits ? B.out : nullptr;
-        W->streams[L.body].src = B.in;
+        EncStream& S = W->streams[L.body];
+        S.src = B.in;
+        if (S.hdr) {                                             // the stream is built in the block's own region
+            if (!fits) S.n = 0;                                  // nothing is coded, nothing is written
+            else {
+                S.out = B.out + S.hdr;
+                // the payload grows down from the last even ADDRESS of the region (16-bit stores)
+                S.cap = (uint32_t)(((reinterpret_cast<uintptr_t>(B.out) + B.cap) & ~uintptr_t(1)) - reinterpret_cast<uintptr_t>(S.out));
+            }
+        }
     }
     if (!fits) B.mode = 3;
 }
@@ -1618,6 +1686,10 @@ struct EncImpl {
     // streams per variant of the previous batch (read back asynchronously): a batch that used a single variant
     // predicts another one, which is launched on the caller's stream alone (13 % faster than from a side stream)
     uint32_t* h_vcount = nullptr; cudaEvent_t vc_ready = nullptr; bool vc_pending = false; int mixed = -1;
+    // arena for alphabet-dependent order-1 scratch (EncWork::arena) and the read-back of how much a batch wanted
+    uint8_t* d_arena = nullptr; size_t arena_cap = 0, arena_hint = 0;
+    unsigned long long* h_ret = nullptr;                        // pinned: [arena_used, overflow]
+    cudaEvent_t ret_ready = nullptr; bool ret_pending = false;
 };
 
 int g_sms_enc = 0;
@@ -1671,8 +1743,28 @@ void EncSlot::release() {
     I->side.release();
     if (I->h_vcount) cudaFreeHost(I->h_vcount);
     if (I->vc_ready) cudaEventDestroy(I->vc_ready);
+    if (I->d_arena) cudaFree(I->d_arena);
+    if (I->h_ret) cudaFreeHost(I->h_ret);
+    if (I->ret_ready) cudaEventDestroy(I->ret_ready);
     delete I;
     impl = nullptr;
+}
+
+// After the stream the batch ran on has drained: did it run out of arena?  If so the next encode_run gets a larger one
+// and the caller should run the batch again (blocks that wanted the missing space carry ST_ARENA).
+bool encode_needs_retry(EncSlot& slot) {
+    EncImpl* I = static_cast<EncImpl*>(slot.impl);
+    if (!I || !I->ret_pending) return false;
+    if (cudaEventQuery(I->ret_ready) != cudaSuccess) { cudaGetLastError(); return false; }
+    I->ret_pending = false;
+    if (!(I->h_ret[1] & 0xffffffffull)) return false;
+    I->arena_hint = std::max(I->arena_hint, (size_t)(I->h_ret[0] + I->h_ret[0] / 4 + (16 << 20)));
+    return true;
+}
+
+size_t encode_device_bytes(const EncSlot& slot) {
+    const EncImpl* I = static_cast<const EncImpl*>(slot.impl);
+    return I ? I->scratch_cap + I->desc_cap + I->arena_cap : 0;
 }
 
 int encode_init(int device) {
@@ -1725,23 +1817,22 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     struct Fix { uint32_t kind; uint32_t idx; uint32_t field; uint32_t blk; };
     (void)in_off_needed;
 
-    auto add_stream = [&](uint32_t leaf, uint32_t n_max, uint32_t order, uint32_t nway, bool is_meta, uint32_t codec = 0) {
+    // hdr != 0: the stream is built in the block's own output region (see EncStream::hdr), no output scratch
+    size_t n_o1 = 0;
+    auto add_stream = [&](uint32_t leaf, uint32_t n_max, uint32_t order, uint32_t nway, uint32_t hdr, uint32_t codec = 0) {
         EncStream S;
         memset(&S, 0, sizeof(S));
-        S.n = n_max; S.order = order; S.nway = nway; S.leaf = leaf; S.codec = codec;
-        uint32_t cap = ((codec ? host_bound_4x8(n_max) : host_bound(n_max, order)) + 4 * nway + 64) & ~1u;
-        S.cap = cap;
-        S.out = reinterpret_cast<uint8_t*>(take(cap));
-        S.F0 = reinterpret_cast<uint32_t*>(take(1024));
-        if (order) {
-            S.F1 = reinterpret_cast<uint32_t*>(take(256 * 256 * 4));
-            S.syms = reinterpret_cast<EncSym*>(take(256 * 256 * 16));
-            const size_t tmax = 257 * 257 * 3 + 16;
-            S.ctab = reinterpret_cast<uint8_t*>(take(((tmax + tmax / 16 + 1024) & ~15u) + 1024 + 4096 + 64));
-        } else {
-            S.syms = reinterpret_cast<EncSym*>(take(256 * 16));
+        S.n = n_max; S.order = order; S.nway = nway; S.leaf = leaf; S.codec = codec; S.hdr = hdr;
+        if (!hdr) {
+            uint32_t cap = ((codec ? host_bound_4x8(n_max) : host_bound(n_max, order)) + 4 * nway + 64) & ~1u;
+            S.cap = cap;
+            S.out = reinterpret_cast<uint8_t*>(take(cap));
         }
-        (void)is_meta;
+        S.F0 = reinterpret_cast<uint32_t*>(take(1024));
+        // 256 encoder symbols / pair counts: order 0, and order-1 alphabets of up to 16 symbols (16 x 16 entries);
+        // larger alphabets get theirs from the arena once the histogram pass knows the size (enc_hist_kernel)
+        S.syms = reinterpret_cast<EncSym*>(take(256 * 16));
+        if (order) { S.F1 = reinterpret_cast<uint32_t*>(take(256 * 4)); n_o1++; }
         streams.push_back(S);
         return (uint32_t)streams.size() - 1;
     };
@@ -1761,8 +1852,14 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
         }
         const uint32_t li = (uint32_t)leaves.size();
         const uint32_t nway = (flags & F_X32) ? 32 : 4;
-        L.body = add_stream(li, n, flags & 1, nway, false, codec);
-        L.meta = (flags & F_RLE) ? add_stream(li, n + 272, 0, nway, true) : 0xffffffffu;
+        // a plain leaf written straight to the caller's block: [flags][varint n] (or the 9-byte 4x8 header), then the stream
+        uint32_t hdr = 0;
+        if (!src_scratch && !out_scratch && !(flags & (F_PACK | F_RLE))) {
+            hdr = codec ? 9u : 1u;
+            if (!codec && !(flags & F_NOSZ)) for (uint32_t t = n;; t >>= 7) { hdr++; if (t < 128) break; }
+        }
+        L.body = add_stream(li, n, flags & 1, nway, hdr, codec);
+        L.meta = (flags & F_RLE) ? add_stream(li, n + 272, 0, nway, 0) : 0xffffffffu;
         leaves.push_back(L);
         leaf_src_is_scratch.push_back(src_scratch); leaf_src_off.push_back(src_off);
         leaf_out_is_scratch.push_back(out_scratch); leaf_out_off.push_back(out_off);
@@ -1818,6 +1915,28 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     const size_t desc_bytes = up(sizeof(EncWork)) + up(sizeof(EncBlock) * blocks.size()) + up(sizeof(EncLeaf) * leaves.size()) +
                               up(sizeof(EncStream) * streams.size()) + up(4 * 16 * streams.size()) + 256;
     if (I->pending) { ECK(cudaEventSynchronize(I->uploaded)); I->pending = false; }
+    // ---- arena for alphabet-dependent order-1 scratch.  What a finished batch wanted sizes the next one (an
+    // asynchronous caller cannot be retried; encode_needs_retry does it for the synchronous ones).
+    if (I->ret_pending && cudaEventQuery(I->ret_ready) == cudaSuccess) {
+        I->ret_pending = false;
+        if (I->h_ret[1] & 0xffffffffull) I->arena_hint = std::max(I->arena_hint, (size_t)(I->h_ret[0] + I->h_ret[0] / 4 + (16 << 20)));
+    }
+    cudaGetLastError();
+    {
+        const size_t want = std::max(I->arena_hint, n_o1 * (size_t)(16 << 10) + (4 << 20));
+        if (want > I->arena_cap) {
+            if (I->d_arena) cudaFree(I->d_arena);
+            I->d_arena = nullptr; I->arena_cap = 0;
+            if (cudaMalloc(&I->d_arena, want) != cudaSuccess) { cudaGetLastError(); snprintf(err, errlen, "out of device memory for the encode arena (%zu B)", want); return -1; }
+            I->arena_cap = want;
+        }
+        if (!I->h_ret) {
+            if (cudaHostAlloc(&I->h_ret, 16, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&I->ret_ready, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError(); snprintf(err, errlen, "out of memory for the encode read-back"); return -1;
+            }
+            I->h_ret[0] = I->h_ret[1] = 0;
+        }
+    }
     if (scratch + 256 > I->scratch_cap) {
         if (I->d_scratch) cudaFree(I->d_scratch);
         I->d_scratch = nullptr; I->scratch_cap = 0;
@@ -1839,9 +1958,10 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     // live on the device: a fix-up kernel patches them (enc_fix_kernel below).
     uint8_t* sb = I->d_scratch;
     for (auto& S : streams) {
-        S.out = sb + (size_t)S.out; S.F0 = reinterpret_cast<uint32_t*>(sb + (size_t)S.F0);
+        if (!S.hdr) S.out = sb + (size_t)S.out;
+        S.F0 = reinterpret_cast<uint32_t*>(sb + (size_t)S.F0);
         S.syms = reinterpret_cast<EncSym*>(sb + (size_t)S.syms);
-        if (S.order) { S.F1 = reinterpret_cast<uint32_t*>(sb + (size_t)S.F1); S.ctab = sb + (size_t)S.ctab; }
+        if (S.order) S.F1 = reinterpret_cast<uint32_t*>(sb + (size_t)S.F1);
     }
     for (size_t k = 0; k < leaves.size(); k++) {
         EncLeaf& L = leaves[k];
@@ -1871,6 +1991,7 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     // order 1 with <= 9 symbols (1.5 KB)
     const bool big4 = (streams.size() + 7) / 8 > (size_t)g_grid_enc[0][0];
     hw.o0_lo = big4 ? 48u : 0u; hw.o1_lo = big4 ? 9u : 0u;
+    hw.arena = I->d_arena; hw.arena_cap = I->arena_cap; hw.arena_used = 0; hw.overflow = 0;
     memcpy(I->h_desc + o_work, &hw, sizeof(hw));
     memcpy(I->h_desc + o_blocks, blocks.data(), sizeof(EncBlock) * blocks.size());
     if (!leaves.empty()) memcpy(I->h_desc + o_leaves, leaves.data(), sizeof(EncLeaf) * leaves.size());
@@ -1963,6 +2084,11 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     }
     enc_block_kernel<<<g, 256, 0, st>>>(dW, b.out_len, b.status); launches++;
     ECK(cudaGetLastError());
+    // how much arena the batch wanted, and whether it ran out (read by encode_needs_retry / the next call)
+    ECK(cudaMemcpyAsync(&I->h_ret[0], &dW->arena_used, 8, cudaMemcpyDeviceToHost, st));
+    ECK(cudaMemcpyAsync(&I->h_ret[1], &dW->overflow, 4, cudaMemcpyDeviceToHost, st));
+    ECK(cudaEventRecord(I->ret_ready, st));
+    I->ret_pending = true;
     return launches;
 #undef ECK
 }

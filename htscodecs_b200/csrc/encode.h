@@ -28,5 +28,9 @@ int encode_init(int device);
 // (nullptr: they are fetched with a small synchronous copy).  Returns kernels launched, or -1.
 int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, const int32_t* h_order,
                cudaStream_t st, char* err, size_t errlen);
+// Once the batch's stream has drained: true if it ran out of scratch arena (blocks then carry ST_ARENA); the slot's
+// next encode_run allocates what was missing, so running the batch again succeeds.
+bool encode_needs_retry(EncSlot& slot);
+size_t encode_device_bytes(const EncSlot& slot);   // device memory the slot holds (scratch + descriptors + arena)
 
 }  // namespace hb

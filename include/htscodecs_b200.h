@@ -101,6 +101,8 @@ void hts_b200_destroy(hts_b200_ctx *ctx);
 const char *hts_b200_last_error(const hts_b200_ctx *ctx);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 unsigned long long hts_b200_launch_count(const hts_b200_ctx *ctx);
+/* device memory the context currently holds for work lists, scratch arenas and staging (diagnostics) */
+size_t hts_b200_scratch_bytes(const hts_b200_ctx *ctx);
 /* the context's CUDA stream (a cudaStream_t), so callers can order their own work or events */
 void *hts_b200_stream(const hts_b200_ctx *ctx);
 
@@ -139,6 +141,17 @@ int hts_b200_compress_batch_dev(hts_b200_ctx *ctx, int nblk,
                                 const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
                                 uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
                                 int32_t *status, const int32_t *order, int sync);
+
+/* The same, always asynchronous: host_in_len / host_order are HOST copies of in_len / order (the encoder lays out
+ * its work lists on the host from them), so nothing is read back and the call returns as soon as the kernels are
+ * enqueued on hts_b200_stream(ctx).  hts_b200_compress_batch_dev(..., sync = 0) without them fetches the two arrays
+ * first (one small copy and a stream synchronisation before the kernels are enqueued).  A block that needs more
+ * scratch than the context holds reports HTS_B200_ERR_SCRATCH; the next call starts with enough. */
+int hts_b200_compress_batch_dev_async(hts_b200_ctx *ctx, int nblk,
+                                      const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
+                                      uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
+                                      int32_t *status, const int32_t *order,
+                                      const uint32_t *host_in_len, const int32_t *host_order);
 
 int hts_b200_compress_batch_host(hts_b200_ctx *ctx, int nblk,
                                  const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
@@ -195,12 +208,13 @@ int hts_b200_plan_chunks(int enc, int nblk, const uint8_t *in_base, const uint64
 
 /* Same contract as hts_b200_{un,}compress_batch_host, spread over devices[0 .. ndev).  The library keeps
  * one context per device (created on first use, reused, destroyed at exit); calls are serialised.
- * Copy phases can be coordinated ACROSS devices ("phased": every device sends its inputs first, the threads meet
- * at a host-side barrier, then the results travel back) or every device runs its own full-duplex chunk pipeline.
- * Which is faster is a property of the host: an 8 x B200 host moved 304 GB/s device->host alone but 134 GB/s with
- * other devices' host->device copies in flight, a 2 x B200 host shares ~103 GB/s between the directions either way.
- * So the library measures: per device count the first large call runs full duplex, the second phased, later ones
- * the faster.  hts_b200_multi_set_phased(0 | 1) or HTSCODECS_B200_MULTI_PHASED=0|1 forces a policy. */
+ * Default policy: every device runs its own full-duplex chunk pipeline (host->device, kernels, device->host
+ * overlapped) and takes chunks of the WHOLE batch from a shared cursor whenever one of its pipeline stages is free, so
+ * devices behind a slower host link end up with fewer blocks (on the 8 x B200 host of round 2, GPUs 0-3 moved
+ * 10.7 GB/s each and GPUs 4-7 17 GB/s each).  hts_b200_multi_set_phased(1) / HTSCODECS_B200_MULTI_PHASED=1 selects the
+ * "phased" policy instead -- contiguous ranges balanced on uncompressed bytes (hts_b200_partition), every device sends
+ * its inputs first, the threads meet at a host-side barrier, then the results travel back -- for hosts whose
+ * device->host rate collapses while host->device copies are in flight. */
 int hts_b200_uncompress_batch_host_multi(int ndev, const int *devices, int nblk,
                                          const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
                                          uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
@@ -209,12 +223,12 @@ int hts_b200_compress_batch_host_multi(int ndev, const int *devices, int nblk,
                                        const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,
                                        uint8_t *out_base, const uint64_t *out_off, uint32_t *out_len,
                                        int32_t *status, const int32_t *order);
-void hts_b200_multi_set_phased(int phased);   /* 1 phased, 0 full duplex per device, -1 measured (default) */
+void hts_b200_multi_set_phased(int phased);   /* 1 phased, 0 full duplex + shared chunk queue, -1 environment / default (0) */
 
 /* Per-device breakdown of the last multi-device call (busy times from CUDA events on the copy and
  * compute streams, wall times from the host clock). */
 typedef struct hts_b200_dev_stats {
-    int device, first_blk, nblk, pad;
+    int device, first_blk, nblk, pad;  /* first_blk: phased policy only (-1 when chunks were taken from the shared queue) */
     uint64_t in_bytes, out_bytes;      /* bytes sent to / fetched from the device (payload) */
     double h2d_ms, kernel_ms, d2h_ms;  /* summed busy time of the chunks' copies and kernels */
     double h2d_phase_ms, wait_ms, d2h_phase_ms;   /* phased mode: send phase, barrier wait, fetch phase (host clock) */

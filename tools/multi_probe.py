@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def raw_copies(torch, ndev, mib=2048):
+def raw_copies(torch, ndev, mib=1024):
     n = mib << 20
     hs, ds, h2, d2, st = [], [], [], [], []
     for d in range(ndev):
@@ -105,7 +105,7 @@ def main():
             pin_u = hb.PinnedArray(nblk * n + 64)
             u_off = np.arange(nblk, dtype=np.uint64) * n
             status = np.zeros(nblk, np.int32)
-            for phased in ((0, 1, None) if nd > 1 else (0,)):
+            for phased in ((0, 1) if nd > 1 else (0,)):
                 hb.multi_set_phased(None if phased is None else bool(phased))
                 ts = []
                 for r in range(args.reps + 1):
