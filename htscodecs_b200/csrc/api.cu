@@ -597,7 +597,7 @@ static int run_host_batch_body(hts_b200_ctx* ctx, bool enc, int nblk, const uint
                 else if (f & F_ORDER1) kinds |= (x32 ? (1u << JK_O1_32) | (1u << JK_O1_32S) : K_O1_4) | (1u << JK_TAB);   // TAB: compressed tables
                 else kinds |= x32 ? (1u << JK_O0_32) : K_O0_4;
                 if (f & F_RLE) { post |= 1u; kinds |= 1u << (x32 ? JK_O0_32 : JK_O0_4); }
-                if (f & F_PACK) post |= 2u;
+                if (f & F_PACK) { post |= 2u; kinds |= 1u << (x32 ? JK_O0_32P : JK_O0_4P); }
             }
             db.kinds = kinds; db.post = post;
             if (S.side.init() == 0) db.side = &S.side;

@@ -33,6 +33,7 @@ enum JobKind : uint32_t {
     // 4-way / 4x8 streams of up to 8 / 16 symbols: table (order 0) or context row (order 1) in registers, the
     // renormalisation bytes prefetched as a window (dec_o0r_kernel / dec_o1r_kernel) -- the short-latency variants
     JK_O0_4R8, JK_O0_4R16, JK_O1_4R8, JK_O1_4R16, JK_R8_O0R8, JK_R8_O0R16, JK_R8_O1R8, JK_R8_O1R16,
+    JK_O0_4P, JK_O0_32P,   // order-0 streams of an X_PACK container (no X_RLE): un-PACK is the decoder's sink (pack.c:211-348)
     JK_NKINDS
 };
 
@@ -42,8 +43,12 @@ struct DecJob {
     uint32_t in_len;
     uint32_t out_len;
     uint32_t blk;
-    uint32_t pad;
+    uint32_t fuse;         // != 0: un-PACK fused into the decoder's sink -- every decoded byte expands to `fuse` (2, 4, 8)
+                           // symbols through `map`, written straight to `out` (fin_len bytes in all)
     uint8_t* aux;          // order-1 with an O0-compressed table: scratch for the expanded table
+    uint32_t fin_len;
+    uint32_t pad;
+    uint8_t map[16];
 };
 
 struct Chain {

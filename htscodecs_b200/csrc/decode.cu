@@ -50,7 +50,9 @@ __device__ __forceinline__ bool push_job(DecWork* W, uint32_t kind, const DecJob
 __device__ __forceinline__ DecJob make_job(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len,
                                            uint32_t blk) {
     DecJob j;
-    j.in = in; j.in_len = in_len; j.out = out; j.out_len = out_len; j.blk = blk; j.pad = 0; j.aux = nullptr;
+    j.in = in; j.in_len = in_len; j.out = out; j.out_len = out_len; j.blk = blk; j.fuse = 0; j.aux = nullptr;
+    j.fin_len = 0; j.pad = 0;
+    for (int k = 0; k < 16; k++) j.map[k] = 0;
     return j;
 }
 
@@ -189,14 +191,6 @@ __device__ int32_t plan_chain(DecWork* W, const uint8_t* in, uint32_t in_len, ui
     c.flags = flags & (F_RLE | F_PACK);
     c.osz = osz;
 
-    uint8_t* tmp = nullptr;
-    if (flags & (F_PACK | F_RLE)) {                                  // :1498-1513
-        tmp = arena_alloc(W, (uint64_t)osz + 16);
-        if (!tmp) return ST_ARENA;
-    }
-    if ((flags & F_PACK) && (flags & F_RLE)) { c.t1 = out; c.t2 = tmp; c.t3 = out; }
-    else if (flags & F_PACK)                 { c.t1 = tmp; c.t2 = tmp; c.t3 = out; }
-    else if (flags & F_RLE)                  { c.t1 = tmp; c.t2 = out; c.t3 = out; }
     uint32_t t1_size = osz;
 
     if (flags & F_PACK) {                                            // :1527-1545
@@ -210,6 +204,19 @@ __device__ int32_t plan_chain(DecWork* W, const uint8_t* in, uint32_t in_len, ui
         if (psz > t1_size) return ST_FORMAT;
         t1_size = psz;
     }
+    // X_PACK alone over an order-0 stream: the decoder expands every byte as it produces it (no intermediate buffer,
+    // no un-PACK pass)
+    const bool fused = (flags & F_PACK) && !(flags & (F_RLE | F_CAT | F_ORDER1)) && c.per >= 2 && in_len > 0;
+    if (fused && ((uint64_t)osz + c.per - 1) / c.per > t1_size) return ST_FORMAT;      // pack.c:238,279,314
+    uint8_t* tmp = nullptr;
+    if ((flags & (F_PACK | F_RLE)) && !fused) {                      // :1498-1513
+        tmp = arena_alloc(W, (uint64_t)osz + 16);
+        if (!tmp) return ST_ARENA;
+    }
+    if ((flags & F_PACK) && (flags & F_RLE)) { c.t1 = out; c.t2 = tmp; c.t3 = out; }
+    else if (fused)                          { c.t1 = out; c.t2 = out; c.t3 = out; }
+    else if (flags & F_PACK)                 { c.t1 = tmp; c.t2 = tmp; c.t3 = out; }
+    else if (flags & F_RLE)                  { c.t1 = tmp; c.t2 = out; c.t3 = out; }
 
     const bool x32 = (flags & F_X32) != 0;
     if (flags & F_RLE) {                                             // :1549-1572
@@ -272,6 +279,10 @@ __device__ int32_t plan_chain(DecWork* W, const uint8_t* in, uint32_t in_len, ui
                 }
             }
             if (!push_job(W, kind, j)) return ST_ARENA;
+        } else if (fused) {
+            j.fuse = c.per; j.fin_len = osz;
+            for (int k = 0; k < 16; k++) j.map[k] = c.map[k];
+            if (!push_job(W, x32 ? JK_O0_32P : JK_O0_4P, j)) return ST_ARENA;
         } else {
             uint32_t kind = x32 ? JK_O0_32 : JK_O0_4;
             if (!x32) {                                              // small alphabets: tables in registers; large batch:
@@ -291,19 +302,21 @@ __device__ int32_t plan_chain(DecWork* W, const uint8_t* in, uint32_t in_len, ui
     c.t1_size = t1_size;
     c.t2_size = t1_size;
     if (!(flags & (F_RLE | F_PACK))) c.final_size = t1_size;
+    if (fused) c.final_size = osz;
 
     if (flags & F_RLE) {
         uint32_t at = atomicAdd(&W->nrle, 1u);
         if (at >= W->chain_cap) { W->overflow = 1; return ST_ARENA; }
         W->rle_list[at] = ci;
     }
-    if (flags & F_PACK) {
+    if ((flags & F_PACK) && !fused) {
         uint32_t at = atomicAdd(&W->nunpack, 1u);
         if (at >= W->chain_cap) { W->overflow = 1; return ST_ARENA; }
         W->unpack_list[at] = ci;
     }
     W->chains[ci] = c;
     if (out_len_slot && !(flags & (F_RLE | F_PACK))) *out_len_slot = t1_size;
+    if (out_len_slot && fused) *out_len_slot = osz;
     return ST_OK;
 }
 
@@ -689,11 +702,12 @@ __device__ __forceinline__ uint32_t win_renorm(uint32_t x, bool p, const Win w, 
 // header staging [0,1040), presence bytes [1280,1536) and frequency scratch [2048,3072)),
 // then G fc tables (256 x {F, L + C}, L = the renormalisation bound), then G word rings.  8 KB per
 // X_32 warp with the per-CTA reserve: 28 resident warps per SM.
-template <int NWAY> struct O0Smem {
+template <int NWAY, bool FUSE = false> struct O0Smem {
     static constexpr int G = GroupCfg<NWAY>::G;
     static constexpr int LUT = 0, FC = G * 4096, RINGO = G * 6144;
     static constexpr int RINGSZ = GroupCfg<NWAY>::RING + 64;            // ring + mirror of its first 64 bytes
-    static constexpr int TOTAL = G * (6144 + RINGSZ);
+    static constexpr int EXPO = G * (6144 + RINGSZ);                    // FUSE: 256 x 8-byte un-PACK expansions per group
+    static constexpr int TOTAL = G * (6144 + RINGSZ + (FUSE ? 2048 : 0));
 };
 constexpr int HDR_STAGE = 1040;     // bytes of stream head staged for the table parser
 
@@ -898,10 +912,55 @@ __device__ __forceinline__ void o0_loop(uint32_t R, WordRing<NWAY>& ring, uint32
     if (G.glane < rem) *op = (uint8_t)lds_u8(lut + (R & 0xfffu));
 }
 
-template <int NWAY, bool BYTE>
+// un-PACK as the decoder's sink (pack.c:211-348): decoded byte number idx expands to `per` symbols through the
+// group's expansion table (8-byte entries, built at set-up) and lands at out[idx * per ..); the last byte of a
+// stream may carry fewer symbols than `per`.
+__device__ __forceinline__ void emit_packed(uint8_t* out, uint32_t idx, uint32_t s, uint32_t expt, uint32_t per, uint32_t fin_len, bool aligned) {
+    const uint64_t at = (uint64_t)idx * per;
+    if (at >= fin_len) return;
+    const uint2 e = lds_v2(expt + 8 * s);
+    uint8_t* p = out + at;
+    if (aligned && at + per <= fin_len) {
+        if (per == 4) *reinterpret_cast<uint32_t*>(p) = e.x;
+        else if (per == 8) *reinterpret_cast<uint2*>(p) = e;
+        else *reinterpret_cast<uint16_t*>(p) = (uint16_t)e.x;
+    } else {
+        const uint32_t n = (uint32_t)min((uint64_t)per, fin_len - at);
+        for (uint32_t k = 0; k < n; k++) p[k] = (uint8_t)((k < 4 ? e.x >> (8 * k) : e.y >> (8 * (k - 4))));
+    }
+}
+
+template <int NWAY>
+__device__ __forceinline__ void o0_loop_packed(uint32_t R, WordRing<NWAY>& ring, uint32_t lut, uint32_t fc, uint32_t expt, const DecJob& job,
+                                               uint32_t iters, uint32_t rem, uint32_t minit, uint32_t maxit, const Grp<NWAY>& G) {
+    const uint32_t lt = (NWAY == 32) ? lanemask_lt() : ((1u << G.glane) - 1u);
+    const uint32_t per = job.fuse ? job.fuse : 1u;
+    const bool aligned = (reinterpret_cast<uintptr_t>(job.out) & (per - 1)) == 0;
+    uint32_t idx = G.glane, i = 0;
+    for (; i + 4 <= minit; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint32_t sy;
+            R = o0_step<NWAY, false, false, true>(R, true, ring, lut, fc, nullptr, lt, G.gshift, &sy);
+            emit_packed(job.out, idx, sy, expt, per, job.fin_len, aligned);
+            idx += NWAY;
+        }
+        ring.advance(G.glane, true);
+    }
+    for (; i < maxit; i++) {
+        const bool act = i < iters;
+        uint32_t sy = 0;
+        R = o0_step<NWAY, false, false, false>(R, act, ring, lut, fc, nullptr, lt, G.gshift, &sy);
+        if (act) { emit_packed(job.out, idx, sy, expt, per, job.fin_len, aligned); idx += NWAY; }
+        ring.advance(G.glane, act);
+    }
+    if (G.glane < rem) emit_packed(job.out, idx, lds_u8(lut + (R & 0xfffu)), expt, per, job.fin_len, aligned);
+}
+
+template <int NWAY, bool BYTE, bool FUSE = false>
 __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status, uint32_t kind) {
     using C = GroupCfg<NWAY>;
-    using S = O0Smem<NWAY>;
+    using S = O0Smem<NWAY, FUSE>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const Grp<NWAY> G;
     uint32_t base = smem_addr(smem_raw);
@@ -933,9 +992,27 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
         __syncwarp();
         const uint32_t iters = ok ? job.out_len / NWAY : 0, rem = ok ? job.out_len % NWAY : 0;
         const uint32_t maxit = __reduce_max_sync(0xffffffffu, iters), minit = __reduce_min_sync(0xffffffffu, iters);
-        const bool aligned = !BYTE && __all_sync(0xffffffffu, (ring.head & 1u) == 0);
-        if (aligned) o0_loop<NWAY, BYTE, true >(R, ring, lut, fc, job.out, iters, rem, minit, maxit, G);
-        else         o0_loop<NWAY, BYTE, false>(R, ring, lut, fc, job.out, iters, rem, minit, maxit, G);
+        if (FUSE) {
+            // the group's un-PACK expansions: byte value -> its `per` symbols (pack.c:211-348, LSB-first), 8 bytes each
+            const uint32_t expt = base + S::EXPO + G.g * 2048;
+            if (ok) {
+                const uint32_t per = job.fuse, bits = 8 / (per ? per : 1u), cmask = (1u << bits) - 1u;
+                for (uint32_t v = G.glane; v < 256; v += NWAY) {
+                    uint32_t lo = 0, hi = 0;
+                    for (uint32_t k = 0; k < per; k++) {
+                        const uint32_t b = job.map[(v >> (k * bits)) & cmask & 15u];
+                        if (k < 4) lo |= b << (8 * k); else hi |= b << (8 * (k - 4));
+                    }
+                    sts_v2(expt + 8 * v, make_uint2(lo, hi));
+                }
+            }
+            __syncwarp();
+            o0_loop_packed<NWAY>(R, ring, lut, fc, expt, job, iters, rem, minit, maxit, G);
+        } else {
+            const bool aligned = !BYTE && __all_sync(0xffffffffu, (ring.head & 1u) == 0);
+            if (aligned) o0_loop<NWAY, BYTE, true >(R, ring, lut, fc, job.out, iters, rem, minit, maxit, G);
+            else         o0_loop<NWAY, BYTE, false>(R, ring, lut, fc, job.out, iters, rem, minit, maxit, G);
+        }
         __syncwarp();
     }
 }
@@ -2217,6 +2294,8 @@ int decode_init(int device) {
     persistent_setup(JK_O1_4M,  dec_o1_kernel<4, false, 2>,  O1Smem<4, 2>::TOTAL, 32);
     persistent_setup(JK_R8_O1M, dec_o1_kernel<4, true, 2>,   O1Smem<4, 2>::TOTAL, 32);
     persistent_setup(JK_TAB,    dec_o0_kernel<4, false>,  O0Smem<4>::TOTAL, 32);
+    persistent_setup(JK_O0_4P,  dec_o0_kernel<4, false, true>,  O0Smem<4, true>::TOTAL, 32);
+    persistent_setup(JK_O0_32P, dec_o0_kernel<32, false, true>, O0Smem<32, true>::TOTAL, 32);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -2286,6 +2365,8 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     LAUNCH_DEC(JK_R8_O0R16, (dec_o0r_kernel<16, true>), 8, false)
     LAUNCH_DEC(JK_O0_4R8, (dec_o0r_kernel<8, false>), 8, false)
     LAUNCH_DEC(JK_R8_O0R8, (dec_o0r_kernel<8, true>), 8, false)
+    LAUNCH_DEC(JK_O0_4P, (dec_o0_kernel<4, false, true>), 8, false)
+    LAUNCH_DEC(JK_O0_32P, (dec_o0_kernel<32, false, true>), 1, false)
     LAUNCH_DEC(JK_O0_4C, (dec_o0c_kernel<false>), 8, false)
     LAUNCH_DEC(JK_R8_O0C, (dec_o0c_kernel<true>), 8, false)
     LAUNCH_DEC(JK_O1_32, (dec_o1_kernel<32, false, 0>), 1, false)
