@@ -678,7 +678,8 @@ __device__ __forceinline__ uint32_t win_renorm(uint32_t x, bool p, const Win w, 
     if (BYTE) {
         const bool p2 = p && x < (1u << 15);
         const uint32_t b1 = __ballot_sync(0xffffffffu, p) >> gshift, b2 = __ballot_sync(0xffffffffu, p2) >> gshift;
-        const uint32_t o = __popc(b1 & lt4) + __popc(b2 & lt4);                   // 0 .. 6: my first byte
+        // bytes taken by the lower lanes = popc(b1 & lt4) + popc(b2 & lt4), each from a permute table (v in 0..7)
+        const uint32_t o = prmt(0x02010100u, 0x03020201u, b1 & lt4) + prmt(0x02010100u, 0x03020201u, b2 & lt4);   // 0 .. 6
         const uint32_t ww = prmt(w.lo, w.hi, o * 0x11u + 0x10u);           // bytes o, o + 1
         if (p2) x = prmt(ww, x, 0x5401);                                   // x << 16 | first << 8 | second
         else if (p) x = prmt(ww, x, 0x6540);                               // x << 8 | first

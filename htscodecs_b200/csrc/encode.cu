@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "encode.h"
@@ -1687,12 +1688,19 @@ struct EncImpl {
     // predicts another one, which is launched on the caller's stream alone (13 % faster than from a side stream)
     uint32_t* h_vcount = nullptr; cudaEvent_t vc_ready = nullptr; bool vc_pending = false; int mixed = -1;
     // arena for alphabet-dependent order-1 scratch (EncWork::arena) and the read-back of how much a batch wanted
-    uint8_t* d_arena = nullptr; size_t arena_cap = 0, arena_hint = 0;
+    uint8_t* d_arena = nullptr; size_t arena_cap = 0, batch_o1 = 1;
     unsigned long long* h_ret = nullptr;                        // pinned: [arena_used, overflow]
     cudaEvent_t ret_ready = nullptr; bool ret_pending = false;
 };
 
 int g_sms_enc = 0;
+// what any slot of the process learnt about arena needs, in bytes per order-1 stream (the chunk stages of a host-buffer
+// call are separate slots; batches differ in size)
+std::atomic<size_t> g_arena_hint{0};
+void raise_arena_hint(size_t v) {
+    size_t cur = g_arena_hint.load();
+    while (cur < v && !g_arena_hint.compare_exchange_weak(cur, v)) {}
+}
 int g_grid_enc[2][2];
 
 unsigned int host_bound(unsigned int size, int order) {        // rans_compress_bound_4x16, :360-372
@@ -1758,7 +1766,7 @@ bool encode_needs_retry(EncSlot& slot) {
     if (cudaEventQuery(I->ret_ready) != cudaSuccess) { cudaGetLastError(); return false; }
     I->ret_pending = false;
     if (!(I->h_ret[1] & 0xffffffffull)) return false;
-    I->arena_hint = std::max(I->arena_hint, (size_t)(I->h_ret[0] + I->h_ret[0] / 4 + (16 << 20)));
+    raise_arena_hint((size_t)((I->h_ret[0] + I->h_ret[0] / 4) / I->batch_o1 + 4096));
     return true;
 }
 
@@ -1919,11 +1927,12 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     // asynchronous caller cannot be retried; encode_needs_retry does it for the synchronous ones).
     if (I->ret_pending && cudaEventQuery(I->ret_ready) == cudaSuccess) {
         I->ret_pending = false;
-        if (I->h_ret[1] & 0xffffffffull) I->arena_hint = std::max(I->arena_hint, (size_t)(I->h_ret[0] + I->h_ret[0] / 4 + (16 << 20)));
+        if (I->h_ret[1] & 0xffffffffull) raise_arena_hint((size_t)((I->h_ret[0] + I->h_ret[0] / 4) / I->batch_o1 + 4096));
     }
     cudaGetLastError();
     {
-        const size_t want = std::max(I->arena_hint, n_o1 * (size_t)(16 << 10) + (4 << 20));
+        const size_t want = n_o1 * std::max<size_t>(g_arena_hint.load(), 16 << 10) + (4 << 20);
+        I->batch_o1 = std::max<size_t>(1, n_o1);
         if (want > I->arena_cap) {
             if (I->d_arena) cudaFree(I->d_arena);
             I->d_arena = nullptr; I->arena_cap = 0;
