@@ -1580,19 +1580,24 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
     uint32_t i = 0;
     const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(op0) & 3) == 0);
     if (al4) {
-        for (; i + 4 <= minit; i += 4) {
-            uint32_t pack = 0;
+        // after three rounds (12 bytes) every lane's first, possibly partial, 16-byte line is out: the sink's flush
+        // is then one predicated store (put4_fast) instead of a branch that diverges on every call
+        for (int fast = 0; fast < 2; fast++) {
+            const uint32_t lim = fast ? minit : min(minit, 12u);
+            for (; i + 4 <= lim; i += 4) {
+                uint32_t pack = 0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                Win win;
-                if (NWAY == 4) win = win_load(ring.ring, ring.head);
-                const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
-                pack |= lds_u8(unrank + r) << (8 * u);
-                if (NWAY == 4) R = win_renorm<BYTE>(R, R < LB, win, ring.head, lt, G.gshift);
-                else R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
+                for (int u = 0; u < 4; u++) {
+                    Win win;
+                    if (NWAY == 4) win = win_load(ring.ring, ring.head);
+                    const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
+                    pack |= lds_u8(unrank + r) << (8 * u);
+                    if (NWAY == 4) R = win_renorm<BYTE>(R, R < LB, win, ring.head, lt, G.gshift);
+                    else R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
+                }
+                if (fast) sink.put4_fast(pack); else sink.put4(pack);
+                ring.advance(G.glane, true);
             }
-            sink.put4(pack);
-            ring.advance(G.glane, true);
         }
     } else {
         for (; i + 4 <= minit; i += 4) {
