@@ -219,6 +219,9 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None, one=None):
             torch.cuda.synchronize()
             return e0.elapsed_time(e1)
 
+        # first call synchronous: it sizes the encoder's scratch arena (large order-1 alphabets), which an asynchronous
+        # call cannot grow
+        ctx.compress_batch_dev(nblk, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=True)
         enc()
         assert int((status != 0).sum()) == 0, "encode failed"
         t_enc = min(enc() for _ in range(reps))
@@ -289,6 +292,7 @@ def mixed_leg(ctx, torch, hb, nblk_dec, nblk_enc, distinct=128, reps=2, reduce_m
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
+    ctx.compress_batch_dev(nblk_enc, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=True)   # sizes the arena
     enc()
     assert int((status != 0).sum()) == 0, "mixed corpus: encode failed"
     t_enc = reduce_max(min(enc() for _ in range(reps)))

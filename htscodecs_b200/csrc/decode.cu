@@ -707,8 +707,8 @@ template <int NWAY, bool FUSE = false> struct O0Smem {
     static constexpr int G = GroupCfg<NWAY>::G;
     static constexpr int LUT = 0, FC = G * 4096, RINGO = G * 6144;
     static constexpr int RINGSZ = GroupCfg<NWAY>::RING + 64;            // ring + mirror of its first 64 bytes
-    static constexpr int EXPO = G * (6144 + RINGSZ);                    // FUSE: 256 x 8-byte un-PACK expansions per group
-    static constexpr int TOTAL = G * (6144 + RINGSZ + (FUSE ? 2048 : 0));
+    static constexpr int EXPO = G * (6144 + RINGSZ);                    // FUSE: 16 x 4-byte un-PACK nibble expansions per group
+    static constexpr int TOTAL = G * (6144 + RINGSZ + (FUSE ? 64 : 0));
 };
 constexpr int HDR_STAGE = 1040;     // bytes of stream head staged for the table parser
 
@@ -913,13 +913,17 @@ __device__ __forceinline__ void o0_loop(uint32_t R, WordRing<NWAY>& ring, uint32
     if (G.glane < rem) *op = (uint8_t)lds_u8(lut + (R & 0xfffu));
 }
 
-// un-PACK as the decoder's sink (pack.c:211-348): decoded byte number idx expands to `per` symbols through the
-// group's expansion table (8-byte entries, built at set-up) and lands at out[idx * per ..); the last byte of a
-// stream may carry fewer symbols than `per`.
+// un-PACK as the decoder's sink (pack.c:211-348): decoded byte number idx expands to `per` symbols and lands at
+// out[idx * per ..); the last byte of a stream may carry fewer symbols than `per`.  The expansion goes through the
+// group's 16-entry nibble table (built at set-up from the container's symbol map): a nibble holds per / 2 codes, so
+// T[lo] and T[hi] are the byte's first and second half (4 + 4, 2 + 2 or 1 + 1 symbols, LSB-first).
 __device__ __forceinline__ void emit_packed(uint8_t* out, uint32_t idx, uint32_t s, uint32_t expt, uint32_t per, uint32_t fin_len, bool aligned) {
     const uint64_t at = (uint64_t)idx * per;
     if (at >= fin_len) return;
-    const uint2 e = lds_v2(expt + 8 * s);
+    const uint32_t lo = lds_u32(expt + 4 * (s & 15u)), hi = lds_u32(expt + 4 * (s >> 4));
+    uint2 e;
+    if (per == 8) e = make_uint2(lo, hi);
+    else e = make_uint2(lo | (hi << (4 * per)), 0u);         // per 4: 16-bit halves; per 2: 8-bit halves
     uint8_t* p = out + at;
     if (aligned && at + per <= fin_len) {
         if (per == 4) *reinterpret_cast<uint32_t*>(p) = e.x;
@@ -994,17 +998,14 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
         const uint32_t iters = ok ? job.out_len / NWAY : 0, rem = ok ? job.out_len % NWAY : 0;
         const uint32_t maxit = __reduce_max_sync(0xffffffffu, iters), minit = __reduce_min_sync(0xffffffffu, iters);
         if (FUSE) {
-            // the group's un-PACK expansions: byte value -> its `per` symbols (pack.c:211-348, LSB-first), 8 bytes each
-            const uint32_t expt = base + S::EXPO + G.g * 2048;
+            // the group's un-PACK nibble expansions: 4 bits -> per / 2 symbols (pack.c:211-348, LSB-first)
+            const uint32_t expt = base + S::EXPO + G.g * 64;
             if (ok) {
-                const uint32_t per = job.fuse, bits = 8 / (per ? per : 1u), cmask = (1u << bits) - 1u;
-                for (uint32_t v = G.glane; v < 256; v += NWAY) {
-                    uint32_t lo = 0, hi = 0;
-                    for (uint32_t k = 0; k < per; k++) {
-                        const uint32_t b = job.map[(v >> (k * bits)) & cmask & 15u];
-                        if (k < 4) lo |= b << (8 * k); else hi |= b << (8 * (k - 4));
-                    }
-                    sts_v2(expt + 8 * v, make_uint2(lo, hi));
+                const uint32_t per = job.fuse, bits = 8 / (per ? per : 1u), cmask = (1u << bits) - 1u, half = per / 2;
+                for (uint32_t v = G.glane; v < 16; v += NWAY) {
+                    uint32_t t = 0;
+                    for (uint32_t k = 0; k < half; k++) t |= (uint32_t)job.map[(v >> (k * bits)) & cmask & 15u] << (8 * k);
+                    sts_u32(expt + 4 * v, t);
                 }
             }
             __syncwarp();

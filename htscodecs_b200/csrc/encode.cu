@@ -1492,16 +1492,45 @@ __device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint3
 }
 
 // The same for a destination BELOW an overlapping source (the payload of a stream built in place moves down behind its
-// table): tile by tile, every thread reads its 16 bytes before any thread writes the tile.
+// table): tile by tile, every thread reads its 16 bytes (aligned 32-bit source words, realigned with funnel shifts)
+// before any thread writes the tile's 16-byte aligned stores.
 __device__ __forceinline__ void cta_move_down(uint8_t* dst, const uint8_t* src, uint32_t n) {
     if (dst == src || n == 0) return;                       // (CTA-uniform)
-    for (uint32_t t0 = 0; t0 < n; t0 += blockDim.x * 16) {
-        const uint32_t at = t0 + threadIdx.x * 16;
-        uint8_t v[16];
-        const uint32_t cnt = at < n ? min(16u, n - at) : 0u;
-        for (uint32_t k = 0; k < cnt; k++) v[k] = src[at + k];
+    const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+    {                                                       // the bytes up to dst's first 16-byte boundary
+        uint8_t v = 0;
+        if (threadIdx.x < head) v = src[threadIdx.x];
         __syncthreads();
-        for (uint32_t k = 0; k < cnt; k++) dst[at + k] = v[k];
+        if (threadIdx.x < head) dst[threadIdx.x] = v;
+        __syncthreads();
+    }
+    const uint32_t nv = (n - head) / 16;
+    const uint8_t* s0 = src + head;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s0) & 3) * 8;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - (sh >> 3));
+    uint4* dv = reinterpret_cast<uint4*>(dst + head);
+    for (uint32_t i0 = 0; i0 < nv; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        if (i < nv) {
+            const uint32_t* w = sw + 4 * (size_t)i;
+            a0 = w[0]; a1 = w[1]; a2 = w[2]; a3 = w[3];
+            if (sh) {                                       // block-uniform; w[4] is inside the source (the chunk ends sh/8 bytes into it)
+                const uint32_t a4 = w[4];
+                a0 = __funnelshift_r(a0, a1, sh); a1 = __funnelshift_r(a1, a2, sh);
+                a2 = __funnelshift_r(a2, a3, sh); a3 = __funnelshift_r(a3, a4, sh);
+            }
+        }
+        __syncthreads();
+        if (i < nv) dv[i] = make_uint4(a0, a1, a2, a3);
+        __syncthreads();
+    }
+    {                                                       // tail
+        const uint32_t t0 = head + nv * 16;
+        uint8_t v = 0;
+        if (t0 + threadIdx.x < n) v = src[t0 + threadIdx.x];
+        __syncthreads();
+        if (t0 + threadIdx.x < n) dst[t0 + threadIdx.x] = v;
         __syncthreads();
     }
 }
@@ -1696,14 +1725,14 @@ struct EncImpl {
     // predicts another one, which is launched on the caller's stream alone (13 % faster than from a side stream)
     uint32_t* h_vcount = nullptr; cudaEvent_t vc_ready = nullptr; bool vc_pending = false; int mixed = -1;
     // arena for alphabet-dependent order-1 scratch (EncWork::arena) and the read-back of how much a batch wanted
-    uint8_t* d_arena = nullptr; size_t arena_cap = 0, batch_o1 = 1;
+    uint8_t* d_arena = nullptr; size_t arena_cap = 0;
     unsigned long long* h_ret = nullptr;                        // pinned: [arena_used, overflow]
     cudaEvent_t ret_ready = nullptr; bool ret_pending = false;
 };
 
 int g_sms_enc = 0;
-// what any slot of the process learnt about arena needs, in bytes per order-1 stream (the chunk stages of a host-buffer
-// call are separate slots; batches differ in size)
+// the largest arena any batch of the process asked for, in bytes (the chunk stages of a host-buffer call are separate
+// slots); a batch never gets more than it could need (1.6 MB per order-1 stream)
 std::atomic<size_t> g_arena_hint{0};
 void raise_arena_hint(size_t v) {
     size_t cur = g_arena_hint.load();
@@ -1774,7 +1803,7 @@ bool encode_needs_retry(EncSlot& slot) {
     if (cudaEventQuery(I->ret_ready) != cudaSuccess) { cudaGetLastError(); return false; }
     I->ret_pending = false;
     if (!(I->h_ret[1] & 0xffffffffull)) return false;
-    raise_arena_hint((size_t)((I->h_ret[0] + I->h_ret[0] / 4) / I->batch_o1 + 4096));
+    raise_arena_hint((size_t)(I->h_ret[0] + I->h_ret[0] / 4 + (16 << 20)));
     return true;
 }
 
@@ -1935,12 +1964,13 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     // asynchronous caller cannot be retried; encode_needs_retry does it for the synchronous ones).
     if (I->ret_pending && cudaEventQuery(I->ret_ready) == cudaSuccess) {
         I->ret_pending = false;
-        if (I->h_ret[1] & 0xffffffffull) raise_arena_hint((size_t)((I->h_ret[0] + I->h_ret[0] / 4) / I->batch_o1 + 4096));
+        if (I->h_ret[1] & 0xffffffffull) raise_arena_hint((size_t)(I->h_ret[0] + I->h_ret[0] / 4 + (16 << 20)));
     }
     cudaGetLastError();
     {
-        const size_t want = n_o1 * std::max<size_t>(g_arena_hint.load(), 16 << 10) + (4 << 20);
-        I->batch_o1 = std::max<size_t>(1, n_o1);
+        // default: 64 KB per order-1 stream (an alphabet of up to 56 symbols) + 64 MB (forty 256-symbol streams)
+        const size_t want = std::max(n_o1 * (size_t)(64 << 10) + (64 << 20),
+                                     std::min(g_arena_hint.load(), n_o1 * (size_t)(1600 << 10) + (64 << 20)));
         if (want > I->arena_cap) {
             if (I->d_arena) cudaFree(I->d_arena);
             I->d_arena = nullptr; I->arena_cap = 0;

@@ -50,6 +50,7 @@ def main():
             comp_len.fill_(cap)
             torch.cuda.synchronize()
             ctx.compress_batch_dev(nblk, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=False)
+        ctx.compress_batch_dev(nblk, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=True)   # sizes the arena
         enc(); torch.cuda.synchronize()
         assert int((status != 0).sum()) == 0, "encode failed"
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
