@@ -1428,17 +1428,17 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                     gather(sy);
                     run4(sy);
                 }
-            } else if (k + 5 <= maxsteps) {                          // global tables: one batch of look-ups in flight
-                EncSym cur[4], nxt[4];
-                gather(cur);
-                for (; k + 9 <= maxsteps; k += 4) {
-                    gather(nxt);
-                    run4(cur);
+            } else if (k + 9 <= maxsteps) {                          // global tables: eight look-ups in flight (an L2 round trip
+                EncSym ca[4], cb[4], na[4], nb[4];                   // is ~250 cycles, a state update ~40)
+                gather(ca); gather(cb);
+                for (; k + 17 <= maxsteps; k += 8) {
+                    gather(na); gather(nb);
+                    run4(ca); run4(cb);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) cur[u] = nxt[u];
+                    for (int u = 0; u < 4; u++) { ca[u] = na[u]; cb[u] = nb[u]; }
                 }
-                run4(cur);
-                k += 4;
+                run4(ca); run4(cb);
+                k += 8;
             }
             for (; k + 1 < maxsteps; k++) {
                 const uint32_t rc = srank[src.get()];

@@ -133,9 +133,14 @@ int hts_b200_uncompress_batch_host(hts_b200_ctx *ctx, int nblk,
                                    int32_t *status, const uint8_t *method);
 
 /*
- * Device-resident batched encode (rANS 4x16 only).  order[i] is the reference's `order` argument
- * for block i.  out_len[i]: capacity on entry (>= rans_compress_bound_4x16(in_len[i], order[i])),
- * stream length on return.
+ * Device-resident batched encode.  order[i] is the reference's `order` argument for block i (OR in
+ * HTS_B200_ORDER_RANS4x8 for the legacy codec).  out_len[i]: capacity on entry -- a block whose capacity is below
+ * rans_compress_bound_4x16(in_len[i], order[i]) (hts_b200_compress_bound_4x8 for the legacy codec) is refused
+ * with HTS_B200_ERR_SIZE and nothing is written to it, like the reference's coders (rANS_static4x16pr.c:396-397,
+ * :706-707) -- stream length on return.  A plain block (no X_PACK / X_RLE / X_STRIPE) is coded inside its own
+ * output region, so in and out must not overlap.  sync != 0: the call returns when the results are there (and has
+ * retried by itself if order-1 alphabets beyond 16 symbols needed more scratch than the context held); sync == 0:
+ * such blocks report HTS_B200_ERR_SCRATCH and the next call starts with enough.
  */
 int hts_b200_compress_batch_dev(hts_b200_ctx *ctx, int nblk,
                                 const uint8_t *in_base, const uint64_t *in_off, const uint32_t *in_len,

@@ -30,9 +30,10 @@ def test_large_alphabet_order1_grows_the_arena_and_retries(oracle):
     arena.  Synchronous calls retry by themselves; results equal the checker's."""
     import torch
     ctx = hb.Context(0)
-    raw = [synth.random_block(i, 50000).tobytes() for i in range(24)] + [synth.wide_block(i, 60000).tobytes() for i in range(40)] + \
+    # 72 x 1.5 MB of tables for the 256-symbol blocks alone: more than the 64 MB + 64 KB per stream a context starts with
+    raw = [synth.random_block(i, 50000).tobytes() for i in range(72)] + [synth.wide_block(i, 60000).tobytes() for i in range(40)] + \
           [synth.qual_block(i, 30000).tobytes() for i in range(8)]
-    orders = [1] * 24 + [1, 5] * 20 + [1] * 8
+    orders = [1] * 72 + [1, 5] * 20 + [1] * 8
     want = [oracle.compress(d, f) for d, f in zip(raw, orders)]
     # host-buffer path
     got, st = ctx.compress_many(raw, orders)
