@@ -82,3 +82,22 @@ def test_reference_test_programs_link_against_the_library():
                              check=True).stdout
         have = {ln.split()[-1] for ln in lib.splitlines()}
         assert wanted <= have, wanted - have
+
+
+def test_multi_device_call_fails_loudly_without_a_gpu():
+    """No CPU fallback behind the multi-device entry either: without an sm_100 device it returns an error."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        return
+    n = 2
+    buf = np.zeros(64, np.uint8)
+    off = np.zeros(n, np.uint64)
+    ln = np.full(n, 8, np.uint32)
+    st = np.zeros(n, np.int32)
+    with pytest.raises(RuntimeError) as e:
+        hb.uncompress_batch_host_multi([0], n, buf, off, ln, buf, off, ln.copy(), st)
+    assert "no CPU fallback" in str(e.value)
+    assert hb.multi_last_stats() is not None and hb.multi_launch_count() == 0
+    lib = hb.load_library()
+    assert lib.hts_b200_scratch_bytes(None) == 0
