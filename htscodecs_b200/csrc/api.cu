@@ -75,7 +75,7 @@ struct DecSlot {
     // Did the previous batch use more than one entropy kernel kind?  (Read from its header once that has arrived.)
     // A single-kind batch predicts another one, which is launched on the caller's stream alone -- measured 13 %
     // faster than from a side stream; -1 = not known yet.
-    cudaEvent_t hdr_ready = nullptr; bool hdr_pending = false; int mixed = -1;
+    cudaEvent_t hdr_ready = nullptr; bool hdr_pending = false; int mixed = -1; uint32_t hot = ~0u;
     void release() { work.release(); lists.release(); arena.release(); cap_save.release(); h_work.release(); if (hdr_ready) cudaEventDestroy(hdr_ready); hdr_ready = nullptr; }
 };
 
@@ -278,9 +278,12 @@ static int dec_enqueue(hts_b200_ctx* ctx, DecSlot& s, const DecodeBatch& b, cuda
         int used = 0;
         for (int k = 0; k < JK_NKINDS; k++) used += (k != JK_COPY && k != JK_TAB && r.njobs[k] != 0);
         s.mixed = used > 1;
+        uint32_t hot = 0;
+        for (int k = 0; k < JK_NKINDS; k++) if (r.njobs[k] != 0) hot |= 1u << k;
+        s.hot = hot;
         s.hdr_pending = false;
     }
-    if (s.mixed == 0) bb.side = nullptr;
+    bb.hot = s.hot;
     bb.work = reinterpret_cast<DecWork*>(s.work.p);
     s.h_work.p[0].big_batch = b.big_batch ? 1u : 0u;
     s.h_work.p[0].kinds = b.kinds;

@@ -2363,12 +2363,25 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     int nside = 0;
     if (side) cudaEventRecord(side->fork, st);
     cudaStream_t ks = st;
+    // b.hot: the kinds the context's previous batch had jobs for (all bits set: not known).  Kinds outside it are
+    // launched all the same -- the planner decides on the device -- but on ONE shared "cold" stream beside the caller's,
+    // so that a single-kind batch does not pay two dozen empty launches one after the other; a single hot kind runs on
+    // the caller's stream (measured 13 % faster there than from a side stream), several get a side stream each.
+    const uint32_t hot = b.hot & b.kinds;
+    const uint32_t hot_e = hot & ~((1u << JK_COPY) | (1u << JK_TAB));          // entropy kinds among them
+    const bool one_hot = hot_e != 0 && (hot_e & (hot_e - 1)) == 0 && b.hot != ~0u;
+    bool cold_used = false;
+    cudaStream_t cold = side ? side->s[SideStreams::N - 1] : st;
 #define LAUNCH_DEC(K, KERNEL, PER, ON_MAIN)                                                    \
     if (want(K)) {                                                                             \
-        const bool on_main = !side || ON_MAIN;                                                 \
-        if (!on_main) { ks = side->s[nside]; cudaStreamWaitEvent(ks, side->fork, 0); } else ks = st; \
+        const bool is_hot = (hot >> K) & 1u;                                                   \
+        const bool on_main = !side || (is_hot && (ON_MAIN || one_hot));                        \
+        const bool on_cold = !on_main && !is_hot;                                              \
+        if (on_main) ks = st;                                                                  \
+        else if (on_cold) { ks = cold; if (!cold_used) { cudaStreamWaitEvent(cold, side->fork, 0); cold_used = true; } } \
+        else { ks = side->s[nside]; cudaStreamWaitEvent(ks, side->fork, 0); }                  \
         sh = shape(K, PER); KERNEL<<<sh.grid, 32, sh.smem, ks>>>(b.work, b.status, K); launches++; \
-        if (!on_main) { cudaEventRecord(side->join[nside], ks); nside++; }                     \
+        if (!on_main && !on_cold) { cudaEventRecord(side->join[nside], ks); nside++; }         \
     }
     // the long-latency kinds go first so that they start on an empty machine
     LAUNCH_DEC(JK_O1_4M, (dec_o1_kernel<4, false, 2>), 8, false)
@@ -2397,6 +2410,7 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     // share 8 hardware queues; bench.py's headline batch is all of this kind)
     LAUNCH_DEC(JK_O0_32, (dec_o0_kernel<32, false>), 1, true)
 #undef LAUNCH_DEC
+    if (cold_used) { cudaEventRecord(side->join[SideStreams::N - 1], cold); cudaStreamWaitEvent(st, side->join[SideStreams::N - 1], 0); }
     for (int i = 0; i < nside; i++) cudaStreamWaitEvent(st, side->join[i], 0);
     if (want(JK_COPY))  { copy_kernel<<<g_sms * 4, 256, 0, st>>>(b.work); launches++; }
     if (b.post & 1u) { rle_kernel<<<g_sms * 4, RLE_T, 0, st>>>(b.work, b.status, b.out_len); launches++; }

@@ -20,6 +20,7 @@ struct DecodeBatch {
     uint32_t post;              // bit0 RLE, bit1 PACK, bit2 STRIPE may occur
     bool big_batch = false;     // route small-alphabet 4-way order-0 streams to the compact-table kernels
     SideStreams* side = nullptr;   // nullptr: every kernel on the caller's stream, one after the other
+    uint32_t hot = ~0u;            // kinds the previous batch on this context had jobs for (~0u: not known)
 };
 
 int decode_init(int device);
