@@ -222,8 +222,9 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None, one=None):
         # first call synchronous: it sizes the encoder's scratch arena (large order-1 alphabets), which an asynchronous
         # call cannot grow
         ctx.compress_batch_dev(nblk, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=True)
+        assert int((status != 0).sum()) == 0, ("encode failed (sync)", torch.unique(status).tolist())
         enc()
-        assert int((status != 0).sum()) == 0, "encode failed"
+        assert int((status != 0).sum()) == 0, ("encode failed", torch.unique(status).tolist(), int((status != 0).sum()))
         t_enc = min(enc() for _ in range(reps))
         in_len = comp_len.clone()
         csz = int(in_len.to(torch.int64).sum())

@@ -1506,17 +1506,6 @@ struct ByteSink {
             line += 16; k = 0;
         }
     }
-    // put4 once the first (possibly partial) line is out: skip == 0, so the flush is one predicated 128-bit store and
-    // no branch (lanes reach their line ends at different steps: a branch here would diverge every time)
-    __device__ __forceinline__ void put4_fast(uint32_t v) {
-        w0 = w1; w1 = w2; w2 = w3; w3 = v;
-        k += 4;
-        const uint32_t full = (k == 16) ? 1u : 0u;
-        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.global.v4.u32 [%0], {%1,%2,%3,%4};\n\t}"
-                     :: "l"(line), "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(full) : "memory");
-        line = full ? line + 16 : line;
-        k = full ? 0u : k;
-    }
     __device__ __forceinline__ void finish() { if (k > skip) sink_drain(line, k, skip, w0, w1, w2, w3); }
 };
 
@@ -1581,24 +1570,21 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
     uint32_t i = 0;
     const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(op0) & 3) == 0);
     if (al4) {
-        // after three rounds (12 bytes) every lane's first, possibly partial, 16-byte line is out: the sink's flush
-        // is then one predicated store (put4_fast) instead of a branch that diverges on every call
-        for (int fast = 0; fast < 2; fast++) {
-            const uint32_t lim = fast ? minit : min(minit, 12u);
-            for (; i + 4 <= lim; i += 4) {
-                uint32_t pack = 0;
+        // (flushing the sink with a predicated store instead of a branch, once every lane's first partial line is out,
+        //  was measured 1-2 % slower)
+        for (; i + 4 <= minit; i += 4) {
+            uint32_t pack = 0;
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    Win win;
-                    if (NWAY == 4) win = win_load(ring.ring, ring.head);
-                    const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
-                    pack |= lds_u8(unrank + r) << (8 * u);
-                    if (NWAY == 4) R = win_renorm<BYTE>(R, R < LB, win, ring.head, lt, G.gshift);
-                    else R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
-                }
-                if (fast) sink.put4_fast(pack); else sink.put4(pack);
-                ring.advance(G.glane, true);
+            for (int u = 0; u < 4; u++) {
+                Win win;
+                if (NWAY == 4) win = win_load(ring.ring, ring.head);
+                const uint32_t r = o1_symbol<COMPACT>(R, cs, T, mask);
+                pack |= lds_u8(unrank + r) << (8 * u);
+                if (NWAY == 4) R = win_renorm<BYTE>(R, R < LB, win, ring.head, lt, G.gshift);
+                else R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
             }
+            sink.put4(pack);
+            ring.advance(G.glane, true);
         }
     } else {
         for (; i + 4 <= minit; i += 4) {
@@ -1936,23 +1922,19 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
         uint32_t i = 0;
         const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(op0) & 3) == 0);
         if (al4) {
-            // after three rounds (12 bytes) every lane's first, possibly partial, 16-byte line is out: skip == 0
-            for (int fast = 0; fast < 2; fast++) {
-                const uint32_t lim = fast ? minit : min(minit, 12u);
-                for (; i + 4 <= lim; i += 4) {
-                    uint32_t pack = 0;
+            for (; i + 4 <= minit; i += 4) {
+                uint32_t pack = 0;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const Win win = win_load(ring.ring, ring.head);
-                        bool p;
-                        const uint32_t e = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
-                        fetch_row(e);
-                        pack |= unrk((e >> 12) & 15u) << (8 * u);
-                        R = win_renorm<BYTE>(R, p, win, ring.head, lt4, G.gshift);
-                    }
-                    if (fast) sink.put4_fast(pack); else sink.put4(pack);
-                    ring.advance(G.glane, true);
+                for (int u = 0; u < 4; u++) {
+                    const Win win = win_load(ring.ring, ring.head);
+                    bool p;
+                    const uint32_t e = reg_symbol<NS, BYTE>(R, E, shift, sh32, mask, &p);
+                    fetch_row(e);
+                    pack |= unrk((e >> 12) & 15u) << (8 * u);
+                    R = win_renorm<BYTE>(R, p, win, ring.head, lt4, G.gshift);
                 }
+                sink.put4(pack);
+                ring.advance(G.glane, true);
             }
         } else {
             for (; i + 4 <= minit; i += 4) {

@@ -1194,20 +1194,14 @@ struct ByteSrc {
         }
         k = lo;
     }
-    // Branch-free: lanes run out of bytes at different steps (their segments start at different alignments), so a
-    // branch here diverges on almost every call; the refill is selects and one predicated load instead.
+    // (A branch-free refill -- selects and one predicated load -- was measured SLOWER: order-1 encode 110 -> 95 GB/s
+    // 4-way, 300 -> 263 X_32; the rare divergent refill costs less than eight extra instructions per byte.)
     __device__ __forceinline__ uint32_t get() {
-        const bool refill = k == 0;
-        w0 = refill ? pre.x : w0; w1 = refill ? pre.y : w1; w2 = refill ? pre.z : w2; w3 = refill ? pre.w : w3;
-        line = refill ? line - 16 : line;
-        k = refill ? 16u : k;
-        {
-            const uint8_t* nl = line - 16;
-            const uint32_t doit = (refill && nl >= lo_line) ? 1u : 0u;
-            uint4 v = refill ? make_uint4(0, 0, 0, 0) : pre;
-            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
-                         : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "l"(nl), "r"(doit));
-            pre = v;
+        if (k == 0) {
+            w0 = pre.x; w1 = pre.y; w2 = pre.z; w3 = pre.w;
+            line -= 16;
+            pre = fetch(line - 16);
+            k = 16;
         }
         const uint32_t b = w3 >> 24;
         w3 = __funnelshift_l(w2, w3, 8); w2 = __funnelshift_l(w1, w2, 8); w1 = __funnelshift_l(w0, w1, 8); w0 <<= 8;
