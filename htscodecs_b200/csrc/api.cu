@@ -429,7 +429,7 @@ double now_ms() {
 // (exported as hts_b200_plan_chunks for the CPU tests).
 static std::vector<int> plan_chunks(bool enc, int nblk, const uint8_t* in_base, const uint64_t* in_off,
                                     const uint32_t* in_len, const uint32_t* out_len, const uint8_t* method,
-                                    const int32_t* order) {
+                                    const int32_t* order, bool* latency_bound = nullptr) {
     // ---- chunking.  The entropy kernels give one warp (or 4 lanes) to a block, so a chunk's kernel time is
     // its slowest block's time however few blocks it holds: chunks must be big enough to fill the SMs
     // (hundreds of blocks) yet numerous enough (>= ~6) for the copies of one to hide behind the next.
@@ -455,6 +455,7 @@ static std::vector<int> plan_chunks(bool enc, int nblk, const uint8_t* in_base, 
             steps = std::max<uint64_t>(steps, u / lanes / parts);
         }
         const uint64_t by_floor = (uint64_t)(steps * 130e-9 * 55e9);
+        if (latency_bound) *latency_bound = by_floor > target;       // chunks sized by the kernels' latency, not by the copies
         target = std::max(target, std::min<uint64_t>(std::min<uint64_t>(by_floor, 2048ull << 20), total_bytes / 3));
         if (enc && total_bytes > (64ull << 20)) {
             // Encode is bound by the host->device stream, which starts at once, and every chunk costs one round of
@@ -840,7 +841,23 @@ int run_multi(bool enc, int ndev, const int* devices, int nblk, const uint8_t* i
     std::vector<int> chunks;
     std::atomic<int> cursor{0};
     if (phased) hts_b200_partition(nblk, enc ? in_len : out_len, ndev, cuts.data());      // uncompressed bytes
-    else chunks = plan_chunks(enc, nblk, in_base, in_off, in_len, out_len, method, order);
+    else {
+        bool latency_bound = false;
+        chunks = plan_chunks(enc, nblk, in_base, in_off, in_len, out_len, method, order, &latency_bound);
+        // finer chunks towards the end (halves, then quarters): the devices then finish within a fraction of a chunk of
+        // each other instead of a whole one (a slow device's chunk takes ~35 ms on the 8 x B200 host).  Not when the
+        // chunks are as small as the kernels' latency allows (4-way streams): every extra chunk costs a kernel round.
+        for (int pass = 0; pass < 2 && ndev > 1 && !latency_bound; pass++) {
+            const int nch = (int)chunks.size() - 1, first = std::max(0, nch - 2 * ndev);
+            std::vector<int> fine(chunks.begin(), chunks.begin() + first + 1);
+            for (int k = first; k < nch; k++) {
+                const int a = chunks[k], b = chunks[k + 1];
+                if (b - a >= 2) fine.push_back(a + (b - a) / 2);
+                fine.push_back(b);
+            }
+            if (nch > ndev) chunks.swap(fine);
+        }
+    }
     PhaseSync ps;
     ps.want = ndev;
     std::vector<int> rcs(ndev, 0);
