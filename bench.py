@@ -221,6 +221,7 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None, one=None):
 
         # first call synchronous: it sizes the encoder's scratch arena (large order-1 alphabets), which an asynchronous
         # call cannot grow
+        torch.cuda.synchronize()                 # (the tensors above were filled on torch's stream, the library runs on its own)
         ctx.compress_batch_dev(nblk, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=True)
         assert int((status != 0).sum()) == 0, ("encode failed (sync)", torch.unique(status).tolist())
         enc()
@@ -240,6 +241,7 @@ def path_sweep(ctx, torch, hb, blocks, nblk, reps=3, legs=None, one=None):
 
         # first call synchronous: it sizes the context's scratch arena (transform temporaries), which an
         # asynchronous call cannot grow
+        torch.cuda.synchronize()
         ctx.uncompress_batch_dev(nblk, d_comp, comp_off, in_len, d_out, raw_off, out_len, status, method, sync=True)
         dec()
         assert int((status != 0).sum()) == 0, "decode failed"
@@ -293,6 +295,7 @@ def mixed_leg(ctx, torch, hb, nblk_dec, nblk_enc, distinct=128, reps=2, reduce_m
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
+    torch.cuda.synchronize()                     # (tensors filled on torch's stream; the library runs on its own)
     ctx.compress_batch_dev(nblk_enc, d_raw, raw_off, raw_len, d_comp, comp_off, comp_len, status, order, sync=True)   # sizes the arena
     enc()
     assert int((status != 0).sum()) == 0, "mixed corpus: encode failed"
@@ -329,6 +332,7 @@ def mixed_leg(ctx, torch, hb, nblk_dec, nblk_enc, distinct=128, reps=2, reduce_m
 
     # first call synchronous: it sizes the context's scratch arena (transform temporaries, large order-1 tables),
     # which an asynchronous call cannot grow (include/htscodecs_b200.h: sync == 0)
+    torch.cuda.synchronize()
     ctx.uncompress_batch_dev(nblk_dec, d_in, d_in_off, d_in_len, d_out, out_off, out_len, status, method, sync=True)
     dec()
     assert int((status != 0).sum()) == 0, "mixed corpus: decode failed"

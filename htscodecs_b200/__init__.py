@@ -358,21 +358,35 @@ class Context:
             raise RuntimeError("htscodecs_b200 batch call failed: " + self.last_error())
 
     # -- device-resident (all arguments are device pointers / CUDA tensors) ----------------------
+    @staticmethod
+    def _wait_producers():
+        """The context's stream is non-blocking, so it does not wait for work torch queued on ITS current
+        stream (torch.full / .cuda() / fill_ of the arguments).  Drain that stream before the library reads them;
+        on an idle stream this is a few microseconds."""
+        import sys
+        torch = sys.modules.get("torch")
+        if torch is not None and torch.cuda.is_initialized():
+            torch.cuda.current_stream().synchronize()
+
     def uncompress_batch_dev(self, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status,
                              method=None, sync=True):
+        self._wait_producers()
         self._check(self.lib.hts_b200_uncompress_batch_dev(
             self.h, nblk, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
             _ptr(out_len), _ptr(status), _ptr(method), 1 if sync else 0))
 
     def compress_batch_dev(self, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, order,
                            sync=True):
+        self._wait_producers()
         self._check(self.lib.hts_b200_compress_batch_dev(
             self.h, nblk, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
             _ptr(out_len), _ptr(status), _ptr(order), 1 if sync else 0))
 
     def compress_batch_dev_async(self, nblk, in_base, in_off, in_len, out_base, out_off, out_len, status, order,
                                  host_in_len, host_order):
-        """Device-resident encode that never synchronises: host_in_len / host_order are numpy copies of in_len / order."""
+        """Device-resident encode that never synchronises the context's stream: host_in_len / host_order are numpy
+        copies of in_len / order."""
+        self._wait_producers()
         self._check(self.lib.hts_b200_compress_batch_dev_async(
             self.h, nblk, _ptr(in_base), _ptr(in_off), _ptr(in_len), _ptr(out_base), _ptr(out_off),
             _ptr(out_len), _ptr(status), _ptr(order), _ptr(host_in_len), _ptr(host_order)))

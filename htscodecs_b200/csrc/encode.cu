@@ -704,7 +704,9 @@ __device__ __forceinline__ uint32_t enc_put(uint32_t x, bool act, const EncSym s
     const bool emit = act && x >= s.x_max;
     const uint32_t m = (__ballot_sync(0xffffffffu, emit) >> G.gshift) & EGrp<NWAY>::GM;
     const uint32_t above = __popc((m >> G.glane) >> 1);              // emitting lanes with a higher index write first
-    st_u16_if(wp - 2 * (above + 1), x, emit);
+    // the stored half-word gets a register of its own: with the state register as the store's source, the state's
+    // shift had to wait for the store to issue -- i.e. for the whole ballot / popc address chain (ncu: 11 of 129 cycles)
+    st_u16_if(wp - 2 * (above + 1), __byte_perm(x, 0, 0x4410), emit);
     x = emit ? (x >> 16) : x;
     wp -= 2 * __popc(m);
     const uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift & 31u);
@@ -755,8 +757,8 @@ __device__ __forceinline__ uint32_t enc_put8(uint32_t x, bool act, const EncSym 
     const uint32_t m2 = (__ballot_sync(0xffffffffu, e2) >> G.gshift) & EGrp<NWAY>::GM;
     const uint32_t above = __popc((m1 >> G.glane) >> 1) + __popc((m2 >> G.glane) >> 1);
     uint8_t* p = wp - 1 - above;
-    st_u8_if(p, x, e1);
-    st_u8_if(p - 1, x >> 8, e2);
+    st_u8_if(p, __byte_perm(x, 0, 0x4440), e1);                        // (registers of their own, as in enc_put)
+    st_u8_if(p - 1, __byte_perm(x, 0, 0x4441), e2);
     x = e2 ? (x1 >> 8) : x1;
     wp -= __popc(m1) + __popc(m2);
     const uint32_t q = __umulhi(x, s.rcp_freq) >> (s.cmpl_shift & 31u);
@@ -1320,7 +1322,7 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                 x = enc_step<NWAY, BYTE>(x, act, s, wp, G);
             }
             // from here on every lane of the warp codes rows full-1 .. 0 of its stream
-            constexpr int B = 8;
+            constexpr int B = (NWAY == 32) ? 8 : 16;                // 4-way: a lone warp per scheduler, so the fetch runs ~2000 cycles ahead
             const uint8_t* ip = in + G.glane;
             uint8_t* const obase = act_s ? S->out : nullptr;         // (kept in registers: the asm steps clobber memory)
             uint32_t r = full;                                       // rows left
@@ -1417,6 +1419,49 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                 }
             };
             if (__all_sync(0xffffffffu, sm_syms)) {                  // shared-memory tables: nothing to hide
+                // Rounds of 16 steps with the context bytes taken from aligned 32-bit words that every lane fetches
+                // at the same step, a round ahead (ByteSrc's per-lane refill is a divergent branch per byte, and the
+                // compiler's copies of its in-flight line stalled every step: ncu, 275 K of 2.2 M samples).
+                if (k + 17 <= maxsteps) {
+                    const uint8_t* lane_begin = in + (size_t)G.glane * seg;
+                    const uint8_t* e = src.line + src.k;             // one past the next byte to hand out
+                    const uint32_t s8 = ((uint32_t)reinterpret_cast<uintptr_t>(e) & 3u) * 8u;
+                    const uint8_t* wa = e - (s8 >> 3);
+                    const uint8_t* lo_word = lane_begin - (reinterpret_cast<uintptr_t>(lane_begin) & 3);
+                    auto word = [&](const uint8_t* p) -> uint32_t {  // nothing below the word of the lane's first byte is touched
+                        return (p >= lo_word) ? __ldg(reinterpret_cast<const uint32_t*>(p)) : 0u;
+                    };
+                    uint32_t hi = s8 ? word(wa) : 0u;                // the word holding e[-1] when e is not word aligned
+                    uint32_t nq[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) nq[j] = word(wa - 4 * (j + 1));
+                    wa -= 16;
+                    const uint32_t ssym_a = smem_addr(ssym), srank_a = smem_addr(srank);
+                    for (; k + 17 <= maxsteps; k += 16) {
+                        uint32_t c[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) c[j] = nq[j];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) nq[j] = word(wa - 4 * (j + 1));
+                        wa -= 16;
+                        e -= 16;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t cur = __funnelshift_r(c[j], hi, s8);   // bytes e-4j-4 .. e-4j-1, the last one on top
+                            hi = c[j];
+                            EncSym sy[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const uint32_t rc = lds_u8(srank_a + __byte_perm(cur, 0, 0x4443 - u));
+                                const uint4 v = lds_v4(ssym_a + ((rc * ns + rs) << 4));
+                                sy[u].x_max = v.x; sy[u].rcp_freq = v.y; sy[u].bias = v.z; sy[u].cmpl_shift = v.w;
+                                rs = rc;
+                            }
+                            run4(sy);
+                        }
+                    }
+                    src.init(lane_begin, e);                         // the remaining (< 16 + 4) steps go through the byte source
+                }
                 for (; k + 5 <= maxsteps; k += 4) {
                     EncSym sy[4];
                     gather(sy);

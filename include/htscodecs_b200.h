@@ -103,7 +103,10 @@ const char *hts_b200_last_error(const hts_b200_ctx *ctx);
 unsigned long long hts_b200_launch_count(const hts_b200_ctx *ctx);
 /* device memory the context currently holds for work lists, scratch arenas and staging (diagnostics) */
 size_t hts_b200_scratch_bytes(const hts_b200_ctx *ctx);
-/* the context's CUDA stream (a cudaStream_t), so callers can order their own work or events */
+/* the context's CUDA stream (a cudaStream_t), so callers can order their own work or events.
+ * It is a NON-BLOCKING stream: it does not wait for the legacy default stream, so device inputs
+ * (data, offsets, lengths, capacities) produced on another stream must be complete -- or ordered
+ * before this stream with an event -- when a *_dev call is made. */
 void *hts_b200_stream(const hts_b200_ctx *ctx);
 
 /*
