@@ -882,7 +882,7 @@ __device__ __forceinline__ void o0_loop(uint32_t R, WordRing<NWAY>& ring, uint32
             ring.advance(G.glane, true);
         }
     } else if (NWAY == 4 && __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(out) & 3) == 0)) {
-        for (; i + 4 <= minit; i += 4) {                     // word stores after a 4 x 4 transpose
+        auto four = [&]() -> uint32_t {
             uint32_t w = 0;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -890,7 +890,24 @@ __device__ __forceinline__ void o0_loop(uint32_t R, WordRing<NWAY>& ring, uint32
                 R = o0_step<NWAY, BYTE, ALIGNED, true>(R, true, ring, lut, fc, nullptr, lt, G.gshift, &sy);
                 w |= sy << (8 * u);
             }
-            *reinterpret_cast<uint32_t*>(op - G.glane + 4 * G.glane) = transpose4x4(w, G.glane);
+            return w;
+        };
+        if (minit >= 12) {                                   // rounds of eight steps, as in dec_o0r_kernel
+            uint32_t pend = four();
+            ring.advance(G.glane, true);
+            for (i = 4; i + 8 <= minit; i += 8) {
+                *reinterpret_cast<uint32_t*>(op + 3 * G.glane) = transpose4x4(pend, G.glane);
+                const uint32_t w0 = four();
+                *reinterpret_cast<uint32_t*>(op + 16 + 3 * G.glane) = transpose4x4(w0, G.glane);
+                pend = four();
+                op += 32;
+                ring.advance(G.glane, true);
+            }
+            *reinterpret_cast<uint32_t*>(op + 3 * G.glane) = transpose4x4(pend, G.glane);
+            op += 16;
+        }
+        for (; i + 4 <= minit; i += 4) {                     // word stores after a 4 x 4 transpose
+            *reinterpret_cast<uint32_t*>(op + 3 * G.glane) = transpose4x4(four(), G.glane);
             op += 4 * NWAY;
             ring.advance(G.glane, true);
         }
@@ -1108,7 +1125,7 @@ __device__ __forceinline__ void o0c_loop(uint32_t R, WordRing<4>& ring, uint32_t
     uint8_t* op = out + G.glane;
     uint32_t i = 0;
     if (__all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(out) & 3) == 0)) {
-        for (; i + 4 <= minit; i += 4) {                     // word stores after a 4 x 4 transpose
+        auto four = [&]() -> uint32_t {
             uint32_t w = 0;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -1116,7 +1133,24 @@ __device__ __forceinline__ void o0c_loop(uint32_t R, WordRing<4>& ring, uint32_t
                 R = o0c_step<BYTE, ALIGNED, true>(R, true, ring, coarse, ent, nullptr, lt, G.gshift, &sy);
                 w |= sy << (8 * u);
             }
-            *reinterpret_cast<uint32_t*>(op + 3 * G.glane) = transpose4x4(w, G.glane);
+            return w;
+        };
+        if (minit >= 12) {                                   // rounds of eight steps, as in dec_o0r_kernel
+            uint32_t pend = four();
+            ring.advance(G.glane, true);
+            for (i = 4; i + 8 <= minit; i += 8) {
+                *reinterpret_cast<uint32_t*>(op + 3 * G.glane) = transpose4x4(pend, G.glane);
+                const uint32_t w0 = four();
+                *reinterpret_cast<uint32_t*>(op + 16 + 3 * G.glane) = transpose4x4(w0, G.glane);
+                pend = four();
+                op += 32;
+                ring.advance(G.glane, true);
+            }
+            *reinterpret_cast<uint32_t*>(op + 3 * G.glane) = transpose4x4(pend, G.glane);
+            op += 16;
+        }
+        for (; i + 4 <= minit; i += 4) {                     // word stores after a 4 x 4 transpose
+            *reinterpret_cast<uint32_t*>(op + 3 * G.glane) = transpose4x4(four(), G.glane);
             op += 16;
             ring.advance(G.glane, true);
         }
@@ -1572,7 +1606,7 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
     if (al4) {
         // (flushing the sink with a predicated store instead of a branch, once every lane's first partial line is out,
         //  was measured 1-2 % slower)
-        for (; i + 4 <= minit; i += 4) {
+        auto four = [&]() {
             uint32_t pack = 0;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -1584,6 +1618,14 @@ __device__ __forceinline__ void o1_loop(uint32_t R, WordRing<NWAY>& ring, const 
                 else R = renorm_step<NWAY, BYTE, ALIGNED>(R, R < LB, ring, lt, G.gshift);
             }
             sink.put4(pack);
+        };
+        if (NWAY == 4)                                       // 4-way: eight steps use <= 64 of the 128 bytes kept ahead
+            for (; i + 8 <= minit; i += 8) {
+                four(); four();
+                ring.advance(G.glane, true);
+            }
+        for (; i + 4 <= minit; i += 4) {
+            four();
             ring.advance(G.glane, true);
         }
     } else {
@@ -1788,8 +1830,6 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
     const Grp<4> G;
     uint32_t base = smem_addr(smem_raw) + G.g * RegSmem0::STRIDE;
     asm volatile("" : "+r"(base));
-    const bool rounds8 = (kind >> 31) != 0;                  // (experiment switch, see decode_launch)
-    kind &= 0x7fffffffu;
     const uint32_t njobs = W->njobs[kind];
     const DecJob* jobs = W->jobs[kind];
     const uint32_t lt4 = (1u << G.glane) - 1u;
@@ -1823,10 +1863,11 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
         uint8_t* op = job.out + G.glane;
         uint32_t i = 0;
         const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(job.out) & 3) == 0);
-        if (al4 && rounds8 && minit >= 12) {
+        if (al4 && minit >= 12) {
             // Eight steps to a ring check (a step consumes at most 8 bytes, the ring keeps 128 ahead), and the
             // lane-transposed output word of steps 4..7 is exchanged and stored during the NEXT round's steps:
-            // the two shuffles' latency sat exposed at the end of every four steps (ncu: 7 % of the samples).
+            // the two shuffles' latency sat exposed at the end of every four steps (ncu: 7 % of the samples, and
+            // as much again for the ring check).  Measured 216 -> 271 GB/s at 4096 blocks (4x8: 142 -> 160).
             auto four = [&]() -> uint32_t {
                 uint32_t w = 0;
 #pragma unroll
@@ -1953,7 +1994,7 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
         uint32_t i = 0;
         const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(op0) & 3) == 0);
         if (al4) {
-            for (; i + 4 <= minit; i += 4) {
+            auto four = [&]() {
                 uint32_t pack = 0;
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -1965,6 +2006,13 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
                     R = win_renorm<BYTE>(R, p, win, ring.head, lt4, G.gshift);
                 }
                 sink.put4(pack);
+            };
+            for (; i + 8 <= minit; i += 8) {                 // eight steps to a ring check (<= 64 of the 128 bytes kept ahead)
+                four(); four();
+                ring.advance(G.glane, true);
+            }
+            for (; i + 4 <= minit; i += 4) {
+                four();
                 ring.advance(G.glane, true);
             }
         } else {
@@ -2384,7 +2432,6 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     const uint32_t hot_e = hot & ~((1u << JK_COPY) | (1u << JK_TAB));          // entropy kinds among them
     const bool one_hot = hot_e != 0 && (hot_e & (hot_e - 1)) == 0 && b.hot != ~0u;
     bool cold_used = false;
-    uint32_t kx = 0;                                                           // flag bits for the kernel's `kind` argument
     cudaStream_t cold = side ? side->s[SideStreams::N - 1] : st;
 #define LAUNCH_DEC(K, KERNEL, PER, ON_MAIN)                                                    \
     if (want(K)) {                                                                             \
@@ -2394,7 +2441,7 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
         if (on_main) ks = st;                                                                  \
         else if (on_cold) { ks = cold; if (!cold_used) { cudaStreamWaitEvent(cold, side->fork, 0); cold_used = true; } } \
         else { ks = side->s[nside]; cudaStreamWaitEvent(ks, side->fork, 0); }                  \
-        sh = shape(K, PER); KERNEL<<<sh.grid, 32, sh.smem, ks>>>(b.work, b.status, (K) | kx); launches++; \
+        sh = shape(K, PER); KERNEL<<<sh.grid, 32, sh.smem, ks>>>(b.work, b.status, K); launches++; \
         if (!on_main && !on_cold) { cudaEventRecord(side->join[nside], ks); nside++; }         \
     }
     // the long-latency kinds go first so that they start on an empty machine
@@ -2410,13 +2457,10 @@ int decode_launch(const DecodeBatch& b, cudaStream_t st) {
     LAUNCH_DEC(JK_R8_O1R16, (dec_o1r_kernel<16, true>), 8, false)
     LAUNCH_DEC(JK_O1_4R8, (dec_o1r_kernel<8, false>), 8, false)
     LAUNCH_DEC(JK_R8_O1R8, (dec_o1r_kernel<8, true>), 8, false)
-    static const bool o0r_rounds8 = getenv("HTSCODECS_B200_O0R8") && atoi(getenv("HTSCODECS_B200_O0R8")) != 0;
-    kx = o0r_rounds8 ? 0x80000000u : 0u;
     LAUNCH_DEC(JK_O0_4R16, (dec_o0r_kernel<16, false>), 8, false)
     LAUNCH_DEC(JK_R8_O0R16, (dec_o0r_kernel<16, true>), 8, false)
     LAUNCH_DEC(JK_O0_4R8, (dec_o0r_kernel<8, false>), 8, false)
     LAUNCH_DEC(JK_R8_O0R8, (dec_o0r_kernel<8, true>), 8, false)
-    kx = 0;
     LAUNCH_DEC(JK_O0_4P, (dec_o0_kernel<4, false, true>), 8, false)
     LAUNCH_DEC(JK_O0_32P, (dec_o0_kernel<32, false, true>), 1, false)
     LAUNCH_DEC(JK_O0_4C, (dec_o0c_kernel<false>), 8, false)
