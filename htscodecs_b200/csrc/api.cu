@@ -454,7 +454,8 @@ static std::vector<int> plan_chunks(bool enc, int nblk, const uint8_t* in_base, 
             }
             steps = std::max<uint64_t>(steps, u / lanes / parts);
         }
-        const uint64_t by_floor = (uint64_t)(steps * 130e-9 * 55e9);
+        static const double step_ns = getenv("HTSCODECS_B200_STEP_NS") ? atof(getenv("HTSCODECS_B200_STEP_NS")) : 130.0;   // (experiment knob)
+        const uint64_t by_floor = (uint64_t)(steps * step_ns * 1e-9 * 55e9);
         if (latency_bound) *latency_bound = by_floor > target;       // chunks sized by the kernels' latency, not by the copies
         target = std::max(target, std::min<uint64_t>(std::min<uint64_t>(by_floor, 2048ull << 20), total_bytes / 3));
         if (enc && total_bytes > (64ull << 20)) {
@@ -624,8 +625,20 @@ static int run_host_batch_body(hts_b200_ctx* ctx, bool enc, int nblk, const uint
         if (stats) { for (int i = a; i < b; i++) { stats->in_bytes += in_len[i]; } }
         return defer_out ? 0 : launch_out(S);
     };
+    // HTSCODECS_B200_TRACE=1: one stderr line per chunk with its H2D / kernel / D2H intervals (ms since the call began)
+    static const bool trace = getenv("HTSCODECS_B200_TRACE") && atoi(getenv("HTSCODECS_B200_TRACE")) != 0;
+    cudaEvent_t t_base = nullptr;
+    if (trace) { cudaEventCreate(&t_base); cudaEventRecord(t_base, ctx->s_in); }
     auto collect_chunk = [&](int k, Stage& S) -> int {               // after S.d2h_done
         const int a = cuts[k], n = cuts[k + 1] - a;
+        if (trace && t_base) {
+            float t[6] = {0, 0, 0, 0, 0, 0};
+            cudaEvent_t ev[6] = {S.t_h2d0, S.t_h2d1, S.t_k0, S.t_k1, S.t_d2h0, S.t_d2h1};
+            for (int q = 0; q < 6; q++) cudaEventElapsedTime(&t[q], t_base, ev[q]);
+            fprintf(stderr, "[hts_b200 trace] dev %d chunk %d blocks %d: h2d %.2f-%.2f  kernels %.2f-%.2f  d2h %.2f-%.2f  host %.2f\n",
+                    ctx->device, k, n, t[0], t[1], t[2], t[3], t[4], t[5], now_ms());
+            cudaGetLastError();
+        }
         if (stats) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, S.t_h2d0, S.t_h2d1) == cudaSuccess) stats->h2d_ms += ms;

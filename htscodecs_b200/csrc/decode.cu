@@ -999,8 +999,11 @@ __global__ void __launch_bounds__(32) dec_o0_kernel(DecWork* W, int32_t* status,
         if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], (uint32_t)C::G);
         j0 = __shfl_sync(0xffffffffu, j0, 0);
         if (j0 >= njobs) break;
-        const uint32_t ji = j0 + G.g;
-        const bool active = ji < njobs;
+        // (the groups of a last, partly filled warp repeat the list's last job -- identical bytes to identical
+        //  addresses -- instead of idling: an idle group would keep the whole warp out of the all-lanes-active loops,
+        //  i.e. at half speed, and the kernel ends with its slowest warp)
+        const uint32_t ji = min(j0 + G.g, njobs - 1u);
+        const bool active = true;
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         uint32_t R = 0, first_word = 0;
         bool ok = false;
@@ -1189,8 +1192,11 @@ __global__ void __launch_bounds__(32, 32) dec_o0c_kernel(DecWork* W, int32_t* st
         if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], 8u);
         j0 = __shfl_sync(0xffffffffu, j0, 0);
         if (j0 >= njobs) break;
-        const uint32_t ji = j0 + G.g;
-        const bool active = ji < njobs;
+        // (the groups of a last, partly filled warp repeat the list's last job -- identical bytes to identical
+        //  addresses -- instead of idling: an idle group would keep the whole warp out of the all-lanes-active loops,
+        //  i.e. at half speed, and the kernel ends with its slowest warp)
+        const uint32_t ji = min(j0 + G.g, njobs - 1u);
+        const bool active = true;
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         uint32_t R = 0, first_word = 0;
         bool ok = false;
@@ -1676,8 +1682,11 @@ __global__ void __launch_bounds__(32, (SZ == 1 && NWAY == 32) ? 28 : 1) dec_o1_k
         if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], (uint32_t)C::G);
         j0 = __shfl_sync(0xffffffffu, j0, 0);
         if (j0 >= njobs) break;
-        const uint32_t ji = j0 + G.g;
-        const bool active = ji < njobs;
+        // (the groups of a last, partly filled warp repeat the list's last job -- identical bytes to identical
+        //  addresses -- instead of idling: an idle group would keep the whole warp out of the all-lanes-active loops,
+        //  i.e. at half speed, and the kernel ends with its slowest warp)
+        const uint32_t ji = min(j0 + G.g, njobs - 1u);
+        const bool active = true;
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         O1Tables T;
         T.compact = 1; T.tabs = base + S::TABO; T.bstride = 0;
@@ -1838,8 +1847,11 @@ __global__ void __launch_bounds__(32) dec_o0r_kernel(DecWork* W, int32_t* status
         if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], 8u);
         j0 = __shfl_sync(0xffffffffu, j0, 0);
         if (j0 >= njobs) break;
-        const uint32_t ji = j0 + G.g;
-        const bool active = ji < njobs;
+        // (the groups of a last, partly filled warp repeat the list's last job -- identical bytes to identical
+        //  addresses -- instead of idling: an idle group would keep the whole warp out of the all-lanes-active loops,
+        //  i.e. at half speed, and the kernel ends with its slowest warp)
+        const uint32_t ji = min(j0 + G.g, njobs - 1u);
+        const bool active = true;
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         uint32_t R = 0, first_word = 0;
         bool ok = false;
@@ -1949,8 +1961,11 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
         if (lane_id() == 0) j0 = atomicAdd(&W->next[kind], 8u);
         j0 = __shfl_sync(0xffffffffu, j0, 0);
         if (j0 >= njobs) break;
-        const uint32_t ji = j0 + G.g;
-        const bool active = ji < njobs;
+        // (the groups of a last, partly filled warp repeat the list's last job -- identical bytes to identical
+        //  addresses -- instead of idling: an idle group would keep the whole warp out of the all-lanes-active loops,
+        //  i.e. at half speed, and the kernel ends with its slowest warp)
+        const uint32_t ji = min(j0 + G.g, njobs - 1u);
+        const bool active = true;
         DecJob job = make_job(nullptr, 0, nullptr, 0, 0);
         O1Tables T;
         T.compact = 1; T.tabs = rows; T.bstride = RS; T.g_tabs = nullptr; T.ns = 1; T.shift = 12; T.row_off = 0; T.cshift = 20; T.cnt_off = 4 * NS;
@@ -2397,9 +2412,15 @@ static Shape shaped_launch(uint32_t kind, uint32_t groups) {
     // experiments: HTSCODECS_B200_CAP_O0_32=<n> limits the X_32 order-0 kernel to n resident warps per SM
     static const int cap32 = getenv("HTSCODECS_B200_CAP_O0_32") ? atoi(getenv("HTSCODECS_B200_CAP_O0_32")) : 0;
     if (kind == JK_O0_32 && cap32 > 0) c = std::min(c, cap32);
+    // Never pad below 4 CTAs per SM (HTSCODECS_B200_MIN_C overrides): four one-warp CTAs still have a scheduler each, and a
+    // small launch then leaves whole SMs to the kernels of the host pipeline's other chunks (measured: end-to-end encode
+    // +2-3 GB/s on every stream type, decode unchanged)
+    static const int min_c = getenv("HTSCODECS_B200_MIN_C") ? atoi(getenv("HTSCODECS_B200_MIN_C")) : 4;
+    int grid = g_sms * c;
+    if (c < min_c) { c = std::min(min_c, g_cap[kind]); grid = std::min(g_sms * c, (int)std::max(groups, 1u)); }
     int smem = g_smem[kind];
     if (c < g_cap[kind]) smem = std::max(smem, std::min(MAX_DYN, (SM_SMEM / c - CTA_RESERVE) & ~127));
-    return Shape{g_sms * c, smem};
+    return Shape{grid, smem};
 }
 
 

@@ -1330,8 +1330,10 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
         if (lane_id() == 0) s0 = atomicAdd(cursor, (uint32_t)EG::G);
         s0 = __shfl_sync(0xffffffffu, s0, 0);
         if (s0 >= nstreams) break;
-        const bool act_s = s0 + G.g < nstreams;
-        EncStream* S = act_s ? &W->streams[vlist[s0 + G.g]] : nullptr;
+        // (the groups of a last, partly filled warp code the list's last stream again -- identical bytes to identical
+        //  addresses -- instead of idling: an idle group would keep the whole warp in the ragged loops at half speed)
+        const bool act_s = true;
+        EncStream* S = &W->streams[vlist[min(s0 + G.g, nstreams - 1u)]];
 
         const uint8_t* in = act_s ? S->src : nullptr;
         const uint32_t n = act_s ? S->n : 0;
@@ -2168,6 +2170,8 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
             int c = (int)((groups + g_sms_enc - 1) / g_sms_enc);
             c = std::max(1, std::min(c, cap));
             *grid = g_sms_enc * c;
+            static const int min_c = getenv("HTSCODECS_B200_MIN_C") ? atoi(getenv("HTSCODECS_B200_MIN_C")) : 4;   // (see shaped_launch)
+            if (c < min_c) { c = std::min(min_c, cap); *grid = std::min(g_sms_enc * c, (int)std::max(groups, 1u)); }
             return c < cap ? std::max(smem, std::min(232448, (233472 / c - 1024) & ~127)) : smem;
         };
         int grid = 0, sm = 0;
