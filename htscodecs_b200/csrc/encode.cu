@@ -1378,8 +1378,9 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
             }
             // from here on every lane of the warp codes rows full-1 .. 0 of its stream
             // 4-way: a lone warp per scheduler, so the fetch runs ~1300 cycles ahead.  (32 rows, and two rounds in flight
-            // in the order-1 word source, were measured SLOWER -- 307 -> 294 and 213 -> 192 GB/s: the unrolled bodies
-            // outgrow the instruction cache -- although ncu still shows a quarter of the samples on a batch's first byte.)
+            // in the order-1 word source, were measured SLOWER -- 307 -> 294 and 213 -> 192 GB/s, presumably the twice
+            // as long unrolled bodies missing the instruction cache (not profiled) -- although ncu still shows a quarter of
+            // the samples on a batch's first byte.)
             constexpr int B = (NWAY == 32) ? 8 : 16;
             const uint8_t* ip = in + G.glane;
             uint8_t* const obase = act_s ? S->out : nullptr;         // (kept in registers: the asm steps clobber memory)
