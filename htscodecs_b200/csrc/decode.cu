@@ -2008,6 +2008,38 @@ __global__ void __launch_bounds__(32) dec_o1r_kernel(DecWork* W, int32_t* status
         sink.init(op0);
         uint32_t i = 0;
         const bool al4 = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(op0) & 3) == 0);
+        if constexpr (NS == 16) if (al4 && minit >= 8) {
+            // No row of any of the warp's streams holds more than 8 entries (binned qualities: 9 contexts of at most 8
+            // symbols): search 8 registers instead of 16 -- the first compare / select level, its register moves and the
+            // predicated second-half loads were 18 of the 78 instructions of a step, and the kernel is bound by its
+            // instruction count (ncu: the lone warp issues on 49 % of the cycles).
+            bool lng = false;
+            if (ok) for (uint32_t k = G.glane; k < T.ns; k += 4) lng |= lds_u32(rows + k * RS + 4 * NS) > 8u;
+            if (!__any_sync(0xffffffffu, lng)) {
+                uint32_t E8[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) E8[k] = E[k];
+                auto four8 = [&]() {
+                    uint32_t pack = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const Win win = win_load(ring.ring, ring.head);
+                        bool p;
+                        const uint32_t e = reg_symbol<8, BYTE>(R, E8, shift, sh32, mask, &p);
+                        load_row<8>(E8, rows + ((e >> 12) & 15u) * RS);
+                        pack |= unrk((e >> 12) & 15u) << (8 * u);
+                        R = win_renorm<BYTE>(R, p, win, ring.head, lt4, G.gshift);
+                    }
+                    sink.put4(pack);
+                };
+                for (; i + 8 <= minit; i += 8) {
+                    four8(); four8();
+                    ring.advance(G.glane, true);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) { E[k] = E8[k]; E[8 + k] = O1_SENTINEL; }
+            }
+        }
         if (al4) {
             auto four = [&]() {
                 uint32_t pack = 0;
