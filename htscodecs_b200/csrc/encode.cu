@@ -1859,6 +1859,10 @@ constexpr int ORDER_LEGACY_4x8 = 0x40000000;                    // HTS_B200_ORDE
 
 size_t up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
+__global__ void __launch_bounds__(256) enc_upload_kernel(uint4* dst, const uint4* src, uint32_t n16) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 template <typename K> int occ_grid(K kernel, int smem, int sms) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);   // launches may pad (shaping)
     int per = 0;
@@ -2141,12 +2145,16 @@ int encode_run(EncSlot& slot, const EncodeBatch& b, const uint32_t* h_in_len, co
     memcpy(I->h_desc + o_blocks, blocks.data(), sizeof(EncBlock) * blocks.size());
     if (!leaves.empty()) memcpy(I->h_desc + o_leaves, leaves.data(), sizeof(EncLeaf) * leaves.size());
     if (!streams.empty()) memcpy(I->h_desc + o_streams, streams.data(), sizeof(EncStream) * streams.size());
-    ECK(cudaMemcpyAsync(I->d_desc, I->h_desc, o, cudaMemcpyHostToDevice, st));
+    // The descriptors go up by a KERNEL reading the pinned host copy (unified addressing), not through the copy engine:
+    // in the host-buffer pipeline that engine is busy with the following chunks' input for as long as the host keeps it
+    // fed, and a small copy on the compute stream queued behind all of them -- the chunk trace showed every chunk's
+    // kernels starting only once the fourth chunk's input had landed (38 -> see DESIGN.md 4.1).
+    enc_upload_kernel<<<64, 256, 0, st>>>(reinterpret_cast<uint4*>(I->d_desc), reinterpret_cast<const uint4*>(I->h_desc), (uint32_t)((o + 15) / 16));
     ECK(cudaEventRecord(I->uploaded, st));
     I->pending = true;
 
     EncWork* dW = reinterpret_cast<EncWork*>(I->d_desc + o_work);
-    int launches = 0;
+    int launches = 1;                                            // enc_upload_kernel
     const int g = g_sms_enc * 4;
     enc_fix_kernel<<<(nblk + 127) / 128, 128, 0, st>>>(dW, b.in_base, b.in_off, b.out_base, b.out_off, b.out_len); launches++;
     bool any_stripe = false, any_tr = false, any32[2] = {false, false}, any4[2] = {false, false}, any8[2] = {false, false};
