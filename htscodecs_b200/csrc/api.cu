@@ -11,6 +11,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -417,6 +418,7 @@ struct HostRun {                 // optional extras of one host-buffer call
     const std::vector<int>* cuts = nullptr;
     std::atomic<int>* cursor = nullptr;
     const uint32_t* caps = nullptr;      // the batch's capacities (a copy of out_len taken before any thread writes sizes)
+    std::function<void(int, int)> on_chunk;   // called with (first block, count) once a chunk's sizes, status and bytes have landed
 };
 
 double now_ms() {
@@ -675,6 +677,7 @@ static int run_host_batch_body(hts_b200_ctx* ctx, bool enc, int nblk, const uint
         memcpy(out_len + a, S.h_u32.p + n, 4 * (size_t)n);
         memcpy(status + a, S.h_u32.p + 2 * (size_t)n, 4 * (size_t)n);
         if (stats) for (int i = 0; i < n; i++) if (status[a + i] == 0) stats->out_bytes += out_len[a + i];
+        if (hr && hr->on_chunk) hr->on_chunk(a, n);
         return 0;
     };
 
@@ -979,8 +982,8 @@ extern "C" int hts_b200_compress_batch_dev_async(hts_b200_ctx* ctx, int nblk, co
 // ------------------------------------------------------------------------------------------
 // Gather / scatter between the caller's per-block buffers and the pinned staging arena.  A single thread copies at
 // ~10 GB/s, which for a large batch costs more than the GPU work: split the blocks over a few host threads.
-template <typename F> static void for_blocks_parallel(int nblk, uint64_t bytes, F f) {
-    const int nt = (int)std::min<uint64_t>(8, std::max<uint64_t>(1, bytes >> 25));     // one thread per 32 MiB, at most 8
+template <typename F> static void for_blocks_parallel(int nblk, uint64_t bytes, F f, int max_threads = 8) {
+    const int nt = (int)std::min<uint64_t>(max_threads, std::max<uint64_t>(1, bytes >> 25));   // one thread per 32 MiB, at most 8
     if (nt <= 1) { f(0, nblk); return; }
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++) th.emplace_back([=] { f((int)((long long)nblk * t / nt), (int)((long long)nblk * (t + 1) / nt)); });
@@ -1004,16 +1007,26 @@ static int run_ptr_batch(hts_b200_ctx* ctx, bool enc, int nblk, const unsigned c
     for_blocks_parallel(nblk, ib, [=](int a, int b) { for (int i = a; i < b; i++) memcpy(pin_in + offp[i], in[i], in_size[i]); });
     std::vector<int32_t> st(nblk), ord;
     if (order) ord.assign(order, order + nblk);
-    int rc = run_host_batch(ctx, enc, nblk, ctx->pin_in.p, off.data(), in_size, ctx->pin_out.p, off.data() + nblk,
-                            out_size, st.data(), method, order ? ord.data() : nullptr);
-    if (rc) return rc;
-    uint64_t ob_done = 0;
-    for (int i = 0; i < nblk; i++) { status[i] = st[i]; if (st[i] == 0) ob_done += out_size[i]; }
+    // The results of a chunk are scattered to the caller's buffers as soon as the chunk has landed, by threads of their
+    // own, while the pipeline moves the following chunks (scattering after the call cost as much as the call itself).
     const uint8_t* const pin_out = ctx->pin_out.p;
     const int32_t* const stp = st.data();
-    for_blocks_parallel(nblk, ob_done, [=](int a, int b) {
-        for (int i = a; i < b; i++) if (stp[i] == 0) memcpy(out[i], pin_out + offp[nblk + i], out_size[i]);
-    });
+    std::vector<std::thread> scatter;
+    HostRun hr;
+    hr.on_chunk = [&](int a, int n) {
+        uint64_t bytes = 0;
+        for (int i = a; i < a + n; i++) if (stp[i] == 0) bytes += out_size[i];
+        scatter.emplace_back([=] {
+            for_blocks_parallel(n, bytes, [=](int x, int y) {
+                for (int i = a + x; i < a + y; i++) if (stp[i] == 0) memcpy(out[i], pin_out + offp[nblk + i], out_size[i]);
+            }, 4);
+        });
+    };
+    int rc = run_host_batch(ctx, enc, nblk, ctx->pin_in.p, off.data(), in_size, ctx->pin_out.p, off.data() + nblk,
+                            out_size, st.data(), method, order ? ord.data() : nullptr, &hr);
+    for (auto& t : scatter) t.join();
+    if (rc) return rc;
+    for (int i = 0; i < nblk; i++) status[i] = st[i];
     return 0;
 }
 
