@@ -1219,6 +1219,15 @@ __global__ void __launch_bounds__(KT) enc_table_kernel(EncWork* W) {
 // enc_rans_kernel: persistent, one warp per CTA, a group of NWAY lanes per stream
 // ------------------------------------------------------------------------------------------
 constexpr int ENC_O0_SMEM_PER_GROUP = 256 * 16;                      // EncSym[256]
+// Order 1, per group: [NSCAP x NSCAP 16-byte encoder symbols][256 B byte -> rank] and, for the small-alphabet variants,
+// the same symbols once more as 8-byte packed entries {rcp_freq, bias | freq << 13 | rcp_shift << 26} for the hot loop:
+// a 128-bit look-up per lane is four shared-memory wavefronts per warp (plus replays), and ncu shows the X_32 order-1
+// coder bound by exactly those (LSU data pipe 93 % busy at 33 % issue); x_max and cmpl_freq are one shift and one
+// subtraction away from freq (rANS_word.h:190-266).
+__host__ __device__ constexpr bool enc_o1_packed(int nscap) { return nscap <= 16; }
+__host__ __device__ constexpr int enc_o1_smem(int nscap) {
+    return nscap * nscap * 16 + 256 + (enc_o1_packed(nscap) ? ((nscap * nscap * 8 + 15) & ~15) : 0);
+}
 
 // Per-lane backward byte reader of the order-1 loop.  A lane walks its own segment from the end,
 // so a plain byte load per symbol would cost one memory transaction per lane per step; instead
@@ -1313,7 +1322,8 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
     // order 0, NSCAP 48: symbol table compacted over the alphabet ([256 B byte -> rank][NSCAP x 16 B]), 1 KB per
     // stream instead of 4 KB -- the 4-way variant for batches too large for one wave of the 4 KB kernel
     constexpr bool O0C = ORDER == 0 && NSCAP == 48;
-    constexpr uint32_t PER_GROUP = ORDER ? (NSCAP * NSCAP * 16 + 256) : (O0C ? (256 + NSCAP * 16) : ENC_O0_SMEM_PER_GROUP);
+    constexpr uint32_t PER_GROUP = ORDER ? (uint32_t)enc_o1_smem(NSCAP) : (O0C ? (256 + NSCAP * 16) : ENC_O0_SMEM_PER_GROUP);
+    constexpr bool PK = ORDER == 1 && enc_o1_packed(NSCAP);
     uint8_t* gsm = esm + G.g * PER_GROUP;
     EncSym* ssym = reinterpret_cast<EncSym*>(O0C ? gsm + 256 : gsm);
     uint8_t* srank = O0C ? gsm : gsm + NSCAP * NSCAP * 16;          // byte -> rank (order 1, compact order 0)
@@ -1350,8 +1360,18 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
             // symbol -> rank
             uint32_t r = 0;
             if (G.glane == 0) for (int s = 0; s < 256; s++) { srank[s] = (uint8_t)r; if (S->F0[s] != 0 || s == 0) r++; }
-            if (ns <= NSCAP) for (uint32_t k = G.glane; k < ns * ns; k += NWAY) ssym[k] = S->syms[k];
-            else syms = S->syms;
+            if (ns <= NSCAP) {
+                const uint32_t Mo1 = 1u << S->shift;
+                for (uint32_t k = G.glane; k < ns * ns; k += NWAY) {
+                    const EncSym e = S->syms[k];
+                    ssym[k] = e;
+                    if (PK) {
+                        const uint32_t fq = Mo1 - (e.cmpl_shift >> 16);
+                        reinterpret_cast<uint2*>(gsm + NSCAP * NSCAP * 16 + 256)[k] =
+                            make_uint2(e.rcp_freq, (e.bias & 0x1fffu) | (fq << 13) | ((e.cmpl_shift & 31u) << 26));
+                    }
+                }
+            } else syms = S->syms;
         }
         __syncwarp();
 
@@ -1496,6 +1516,9 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
                     for (int j = 0; j < 4; j++) nq[j] = word(wa - 4 * (j + 1));
                     wa -= 16;
                     const uint32_t ssym_a = smem_addr(ssym), srank_a = smem_addr(srank);
+                    const uint32_t spk_a = smem_addr(gsm + NSCAP * NSCAP * 16 + 256);
+                    const uint32_t tbits = act_s ? S->shift : 12u, Mo1 = 1u << tbits;
+                    const uint32_t xs = (BYTE ? 23u + 8u : 15u + 16u) - tbits;      // x_max = freq << xs (make_sym)
                     for (; k + 17 <= maxsteps; k += 16) {
                         uint32_t c[4];
 #pragma unroll
@@ -1512,8 +1535,17 @@ __global__ void __launch_bounds__(32) enc_rans_kernel(EncWork* W, uint32_t curso
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
                                 const uint32_t rc = lds_u8(srank_a + __byte_perm(cur, 0, 0x4443 - u));
-                                const uint4 v = lds_v4(ssym_a + ((rc * ns + rs) << 4));
-                                sy[u].x_max = v.x; sy[u].rcp_freq = v.y; sy[u].bias = v.z; sy[u].cmpl_shift = v.w;
+                                if (PK) {
+                                    const uint2 v = lds_v2(spk_a + ((rc * ns + rs) << 3));
+                                    const uint32_t fq = (v.y >> 13) & 0x1fffu;
+                                    sy[u].rcp_freq = v.x;
+                                    sy[u].bias = v.y & 0x1fffu;
+                                    sy[u].x_max = fq << xs;
+                                    sy[u].cmpl_shift = __byte_perm(v.y >> 26, Mo1 - fq, 0x5410);
+                                } else {
+                                    const uint4 v = lds_v4(ssym_a + ((rc * ns + rs) << 4));
+                                    sy[u].x_max = v.x; sy[u].rcp_freq = v.y; sy[u].bias = v.z; sy[u].cmpl_shift = v.w;
+                                }
                                 rs = rc;
                             }
                             run4(sy);
@@ -1871,10 +1903,10 @@ template <typename K> int occ_grid(K kernel, int smem, int sms) {
 }
 
 constexpr int SM_O0_32 = ENC_O0_SMEM_PER_GROUP, SM_O0_4 = ENC_O0_SMEM_PER_GROUP * 8;
-constexpr int SM_O1_32_S = 16 * 16 * 16 + 256, SM_O1_32_L = 48 * 48 * 16 + 256;     // small / large alphabet variants
-constexpr int SM_O1_4_S = (16 * 16 * 16 + 256) * 8;                                  // 4-way: small only (larger: global)
+constexpr int SM_O1_32_S = enc_o1_smem(16), SM_O1_32_L = enc_o1_smem(48);           // small / large alphabet variants
+constexpr int SM_O1_4_S = enc_o1_smem(16) * 8;                                       // 4-way: small only (larger: global)
 constexpr int SM_O0_4_C = (256 + 48 * 16) * 8;                                       // 4-way order 0, compact symbol tables
-constexpr int SM_O1_4_T = (9 * 9 * 16 + 256) * 8;                                    // 4-way order 1, <= 9 symbols
+constexpr int SM_O1_4_T = enc_o1_smem(9) * 8;                                        // 4-way order 1, <= 9 symbols
 int g_grid_o0_4_c = 0, g_grid_o1_4_t = 0, g_grid_o0_8_c = 0, g_grid_o1_8_t = 0;
 int g_grid_o1_32_s = 0, g_grid_o1_32_l = 0, g_grid_o1_4_s = 0;
 
